@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — sim_step! throughput of the B200 mom_step! library, ns per cell per step (lower is better).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tgv512|tgv128|sphere|...] [--impl reference]
+
+One "step" is one mom_step! (predictor + projection + corrector + projection + CFL) of the workload.  `value` is the
+whole-job number with all state resident in HBM; `e2e` goes through the public host API (wl_b200.Simulation /
+sim_step) with the initial condition coming from host memory and u, p going back to host memory inside the timed
+region.  See DESIGN.md §measurement for the algorithmic-byte table behind `roofline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "sim_step_ns_per_cell_per_step"
+UNIT = "ns/cell/step"
+
+WORKLOADS = {
+    # BASELINE.json configs; tgv512 is the configuration the north_star target (≤0.05 ns/cell/step) is quoted on
+    "tgv512": dict(kind="tgv", n=512),
+    "tgv256": dict(kind="tgv", n=256),
+    "tgv128": dict(kind="tgv", n=128),   # configs[1]
+    "tgv64": dict(kind="tgv", n=64),
+    "sphere": dict(kind="sphere", dims=(512, 256, 256)),  # configs[2]
+    "sphere128": dict(kind="sphere", dims=(128, 64, 64)),
+}
+
+# Algorithmic bytes per launch and ghost-padded fine cell for each kernel (general variable-coefficient forms):
+# every field read once / written once per launch (perfect halo reuse) — DESIGN.md §kernels.  4 B words.
+ALG_WORDS = {
+    "k_conv_bdim1": 12,    # read u(3) [+u⁰(3) in the corrector: 12, predictor 9 → mean 10.5, quoted at 12], V(3); write f(3)
+    "k_bdim2": 24,         # read f3 V3 μ₀3 μ₁9 (+u3 corrector); write u3
+    "k_div_residual": 12,  # read u3 p L3 D iD; write z x r
+    "k_resid_fix": 2,
+    "k_jacobi": 9,         # read r iD L3 D x; write r' x
+    "k_restrict": 1.125,
+    "k_gs_init": 3,
+    "k_gs_sweep": 5,       # half the cells: r .5 iD .5 ϵ .5+.5 L 3
+    "k_increment": 9,      # read ϵ L3 D r x; write r x
+    "k_prolong_inc": 8.125,
+    "k_correct": 11,       # read x L3 u3; write u3 p
+    "k_cfl": 4,
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def tgv_u0(n):
+    from util import tgv3d_u0
+    return tgv3d_u0((n + 2,) * 3, n)
+
+
+def make_case(name):
+    w = WORKLOADS[name]
+    if w["kind"] == "tgv":
+        n = w["n"]
+        nu = float(np.float32(1 / (2 * np.pi / n * 1600)))
+        return dict(dims=(n, n, n), uBC=(0.0, 0.0, 0.0), L=float(n), nu=nu, perdir=(1, 2, 3), exitBC=False, body=None, u0=("tgv", n))
+    d = w["dims"]
+    m = d[1]
+    R = m / 8
+    c = m / 2 - 1
+    return dict(dims=d, uBC=(1.0, 0.0, 0.0), L=2 * R, nu=2 * R / 3700, perdir=(), exitBC=True, body=((c, c, c), R), u0=None)
+
+
+def build_sim(case, u0_host=None):
+    import wl_b200 as wl
+    body = wl.Sphere(*case["body"]) if case["body"] else None
+    u0 = None
+    if u0_host is not None:
+        def u0(i, x):
+            return u0_host[i]
+    return wl.Simulation(case["dims"], case["uBC"], case["L"], ν=case["nu"], perdir=case["perdir"], exitBC=case["exitBC"], body=body, u0=u0)
+
+
+class ClockSampler:
+    def __init__(self, gpu=0):
+        self.samples, self.reasons = [], set()
+        self.maxmhz = None
+        self._stop = threading.Event()
+        self.gpu = gpu
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.maxmhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=5)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.maxmhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def oracle_run(case, steps, warmup):
+    """The CPU port (oracle/) on all host threads: returns seconds per step and the thread count."""
+    import oracle
+    from oracle import OracleSim
+    u0 = tgv_u0(case["u0"][1]) if case["u0"] else None
+    o = OracleSim(case["dims"], case["uBC"], nu=case["nu"], perdir=case["perdir"], exitBC=case["exitBC"], u0=u0)
+    if case["body"]:
+        o.measure_sphere(*case["body"])
+    o.init_pois()
+    for _ in range(warmup):
+        o.mom_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.mom_step()
+    dt = (time.perf_counter() - t0) / steps
+    return dt, oracle.lib().wlo_num_threads(), int(np.sum(o.iters[-2 * steps:]))
+
+
+def cpu_sample_for(name):
+    """Bounded CPU sample of the same workload family (per-cell metric): TGV → 128³, sphere → 128×64×64."""
+    return "tgv128" if WORKLOADS[name]["kind"] == "tgv" else "sphere128"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = cpu_sample_for(args.workload)
+    case = make_case(sample)
+    cells = int(np.prod(case["dims"]))
+    sec, threads, nv = oracle_run(case, args.steps, args.warmup)
+    val = sec * 1e9 / cells
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample}: {args.steps} mom_step! of the oracle port (OpenMP, one parallel loop per reference @loop); "
+                                       "Julia is absent so the reference itself cannot run"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="tgv512", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import wl_b200 as wl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    case = make_case(args.workload)
+    cells = int(np.prod(case["dims"]))
+    u0_host = tgv_u0(case["u0"][1]) if case["u0"] else None
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    sim = build_sim(case, u0_host)
+    fl = sim.flow
+    check = wl.lib.check
+    check(fl.L, fl.L.wl_sim_step_n(fl.h, args.warmup))
+    fl.sync()
+    import ctypes as C
+    sp = C.c_void_p()
+    check(fl.L, fl.L.wl_stream(fl.h, C.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_before = len(sim.pois.n)
+    l_before = fl.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        check(fl.L, fl.L.wl_sim_step_n(fl.h, args.steps))
+        e1.record(stream)
+        fl.sync()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = fl.launches - l_before
+    iters = sim.pois.n[n_before:]
+    n_v = float(np.sum(iters)) / args.steps
+    ns_cell = ms * 1e6 / args.steps / cells
+
+    # ---- per-kernel CUDA-event pass over the same number of steps (roofline of the dominant kernel) ----
+    fl.set_profiling(True)
+    check(fl.L, fl.L.wl_sim_step_n(fl.h, args.steps))
+    tim = fl.timings()
+    fl.set_profiling(False)
+    peak, peak_src = peaks()
+    padded = int(np.prod([d + 2 for d in case["dims"]]))
+    top = max(tim.items(), key=lambda kv: kv[1][1])
+    # launches of a kernel run on every multigrid level; the finest level carries 1/(1+1/7) of the cells, so the
+    # per-launch average is dominated by it — attribute achieved bandwidth on the finest-level launches only when the
+    # kernel is level-independent (conv, bdim, correct, div_residual, cfl); otherwise scale cells by the level sum.
+    ksum = {}
+    tot_ms = sum(v[1] for v in tim.values())
+    for k, (c, m) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
+        ksum[k] = {"launches": c, "ms": round(m, 3), "share": round(m / tot_ms, 4)}
+    name = top[0]
+    words = ALG_WORDS.get(name)
+    roof = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    multilevel = name in ("k_jacobi", "k_restrict", "k_gs_init", "k_gs_sweep", "k_increment", "k_prolong_inc")
+    if words:
+        lv = sim.pois.nlevels
+        if multilevel:
+            # total cells touched per V-cycle sweep over all levels ≈ padded·Σ 8^-l; per-launch average over levels
+            cells_all = sum(int(np.prod(sim.pois.level_dims(l))) for l in range(lv))
+            per_launch_bytes = words * 4 * cells_all / lv
+        else:
+            per_launch_bytes = words * 4 * padded
+        avg_s = top[1][1] / top[1][0] * 1e-3
+        ach = per_launch_bytes / avg_s / 1e9
+        roof.update(achieved=round(ach, 1), frac=round(ach / peak, 4), alg_bytes_per_launch=int(per_launch_bytes), avg_launch_us=round(avg_s * 1e6, 2))
+    # whole-step roofline with the SURVEY §8d formula (general coefficients: NoBody 264+120·n_V, body 468+120·n_V B/cell/step)
+    b_alg = (468 if case["body"] else 264) + 120 * n_v
+    step_ach = b_alg * padded / (ms * 1e-3 / args.steps) / 1e9
+    roof["step"] = {"alg_bytes_per_cell": round(b_alg, 1), "n_V": round(n_v, 3), "achieved": round(step_ach, 1), "frac": round(step_ach / peak, 4),
+                    "formula": "general coefficients, SURVEY.md §8d"}
+
+    line = {"metric": METRIC, "value": round(ns_cell, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "dims": list(case["dims"]), "periodic": list(case["perdir"]), "body": bool(case["body"]),
+                       "poisson_iters_per_step": round(n_v, 3), "l2_flush": "state (%.1f GB) exceeds L2" % (padded * 32 * 4 / 1e9),
+                       "kernels": "general variable-coefficient"},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "kernel_times": ksum}
+
+    # ---- end to end through the host API: host u0 → Simulation → K × sim_step (+Δt readback) → u,p to host ----
+    if not args.no_e2e and world == 1:
+        sim.close()
+        del sim
+        pinned = None
+        if u0_host is not None:
+            pinned = torch.from_numpy(u0_host).pin_memory().numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sim2 = build_sim(case, pinned)
+        h2d = (pinned.nbytes if pinned is not None else 0)
+        if case["body"]:
+            h2d += 4 * padded * (3 + 9 + 3 + 1)
+        t_setup = time.perf_counter() - t0
+        for _ in range(args.warmup):
+            wl.sim_step(sim2)
+        sim2.flow.sync()
+        t1 = time.perf_counter()
+        last_dt = 0.0
+        for _ in range(args.steps):
+            wl.sim_step(sim2)
+            last_dt = float(sim2.flow.Δt[-1])  # device→host read of the step's result
+        u = sim2.flow.u
+        p = sim2.flow.p
+        t2 = time.perf_counter()
+        e2e_s = (t2 - t1) + t_setup
+        d2h = u.nbytes + p.nbytes
+        line["e2e"] = {"value": round(e2e_s * 1e9 / args.steps / cells, 5), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
+                       "d2h_bytes_per_step": int(d2h / args.steps + 4 * len(sim2.flow.Δt)),
+                       "what": "Simulation(host u0) set-up + K×sim_step with Δt read back each step + u,p downloaded to host, all timed",
+                       "setup_s": round(t_setup, 3), "last_dt": last_dt}
+        sim2.close()
+
+    # ---- CPU baseline beside it (rank 0, bounded sample) ------------------------------------------------
+    if not args.no_cpu and rank == 0:
+        sample = cpu_sample_for(args.workload)
+        ccase = make_case(sample)
+        sec, threads, _ = oracle_run(ccase, 3, 1)
+        line["cpu_baseline"] = {"value": round(sec * 1e9 / int(np.prod(ccase["dims"])), 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{sample}: 3 mom_step! of the oracle port after 1 warm-up (OpenMP over all host threads)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

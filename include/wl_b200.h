@@ -1,0 +1,152 @@
+/* wl_b200.h — C ABI of the B200-native `mom_step!` library (libwl_b200.so).
+ *
+ * This is the drop-in boundary for WaterLily.jl's per-time-step hot path.  Host code
+ * (Julia `ccall`, Python ctypes, C) owns configuration and set-up; the library owns all
+ * device state (re-pitched fields, multigrid hierarchy, reduction cells, streams).
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * WaterLily.jl tree, v1.8.0).  The Julia-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on error; wl_last_error() returns a
+ *    thread-local message.  Nothing throws, longjmps or calls back into the host runtime.
+ *  - Fields cross the boundary in the REFERENCE layout: Float32, ghost-padded
+ *    (N_k = n_k+2), column-major with x fastest and the vector component slowest,
+ *    i.e. u[x,y,z,c] at linear index x + N1*(y + N2*(z + N3*c)) (0-based).
+ *  - `src_is_device`/`dst_is_device` != 0 means the pointer is a CUDA device pointer on
+ *    the handle's device (e.g. a CuArray); otherwise host memory.
+ *  - One host thread per handle.  Calls are asynchronous with respect to the GPU except
+ *    the getters, wl_download to host memory and wl_sync.
+ *  - There is no CPU fallback: every compute entry point fails if no CUDA device exists.
+ */
+#ifndef WL_B200_H
+#define WL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wl_handle wl_handle;
+
+/* convective scheme λ(u,c,d): src/Flow.jl:4-6, `λ` keyword of Simulation (src/WaterLily.jl:95) */
+enum { WL_QUICK = 0, WL_CDS = 1, WL_VANLEER = 2 };
+/* pressure solver: MultiLevelPoisson (default pois_ctor, src/WaterLily.jl:97) or Poisson */
+enum { WL_POIS_MULTILEVEL = 0, WL_POIS_SINGLE = 1 };
+/* `smooth!` (src/MultiLevelPoisson.jl:106): GaussSeidelRB! (default) or pcg! */
+enum { WL_SMOOTH_GSRB = 0, WL_SMOOTH_PCG = 1 };
+/* fields of Flow (src/Flow.jl:114-124) addressable through wl_upload / wl_download */
+enum { WL_U = 0, WL_U0 = 1, WL_F = 2, WL_P = 3, WL_SIGMA = 4, WL_V = 5, WL_MU0 = 6, WL_MU1 = 7 };
+/* arrays of one Poisson level (src/Poisson.jl:22-31) addressable through wl_download_level */
+enum { WL_LVL_L = 0, WL_LVL_D = 1, WL_LVL_ID = 2, WL_LVL_X = 3, WL_LVL_EPS = 4, WL_LVL_R = 5, WL_LVL_Z = 6 };
+
+/* Keyword arguments of Simulation / Flow (src/WaterLily.jl:93-98, src/Flow.jl:133-134) that
+ * reach the hot path.  Function-valued uBC / g / udf / u0 are host closures and are not
+ * representable here: the host evaluates u0 itself and uploads u (see wl_apply_bc). */
+typedef struct wl_config {
+  int32_t D;         /* 2 or 3 */
+  int32_t n[3];      /* interior cells per dimension (`dims`) */
+  float uBC[3];      /* constant boundary velocity tuple */
+  int32_t perdir[3]; /* perdir[d] != 0: dimension d+1 is periodic */
+  int32_t exitBC;    /* convective exit in x (src/core.jl:226) */
+  int32_t lambda;    /* WL_QUICK | WL_CDS | WL_VANLEER */
+  float nu;          /* kinematic viscosity ν */
+  float dt0;         /* initial Δt (default 0.25) */
+  int32_t pois_kind; /* WL_POIS_MULTILEVEL | WL_POIS_SINGLE */
+  int32_t smoother;  /* WL_SMOOTH_GSRB | WL_SMOOTH_PCG */
+  float tol;         /* solver tolerance on Σr² (reference default 1e-4) */
+  int32_t itmx;      /* max solver iterations (32 for MultiLevelPoisson, 1000 for Poisson; 0 = default) */
+  int32_t device;    /* CUDA device ordinal */
+  int32_t flags;     /* WL_FLAG_* */
+} wl_config;
+
+enum {
+  WL_FLAG_GENERAL_COEFF = 1, /* never use the constant-coefficient (NoBody) kernel variants */
+};
+
+const char* wl_last_error(void);
+int wl_device_count(void);
+
+/* Flow(N,uBC;…) with a tuple initial condition (src/Flow.jl:133-147): allocates u,u⁰,f,p,σ,V,μ₀,μ₁,
+ * sets u=uBC, BC!, exitBC!(u,u,0), μ₀=1 with BC!(μ₀,0), Δt=[dt0]; then builds the pressure
+ * solver like pois_ctor(flow) (src/WaterLily.jl:105; MultiLevelPoisson ctor src/MultiLevelPoisson.jl:68-76). */
+int wl_create(const wl_config* cfg, wl_handle** out);
+int wl_destroy(wl_handle* h);
+
+/* Array accessors replacing direct reads/writes of flow.u, flow.p, flow.σ, flow.f, flow.V, flow.μ₀, flow.μ₁
+ * (src/Flow.jl:116-124; used by Metrics/JLD2/VTK extensions).  Buffers hold ncomp*ΠN floats in the reference layout. */
+int wl_upload(wl_handle* h, int field, const float* src, int src_is_device);
+int wl_download(wl_handle* h, int field, float* dst, int dst_is_device);
+
+/* After uploading u from a function initial condition: BC!(u,uBC,exitBC,perdir); exitBC!(u,u,0); u⁰=copy(u)
+ * (src/Flow.jl:141-142). */
+int wl_apply_bc(wl_handle* h);
+
+/* Tail of measure!(flow,body) (src/Body.jl:49-50) after the host uploaded μ₀ and V:
+ * BC!(μ₀,0,false,perdir); BC!(V,0,exitBC,perdir). */
+int wl_measure_bc(wl_handle* h);
+
+/* update!(pois) (src/WaterLily.jl:148, src/MultiLevelPoisson.jl:79-86, src/Poisson.jl:47): call after uploading μ₀
+ * (measure!): set_diag! on level 1 and restrictL! + set_diag! on every coarse level. */
+int wl_update(wl_handle* h);
+
+/* mom_step!(flow,pois) without udf (src/Flow.jl:156-167): appends one Δt and two Poisson iteration counts. */
+int wl_mom_step(wl_handle* h);
+/* `for _ in 1:nsteps sim_step!(sim; remeasure=false) end` without returning to the host in between. */
+int wl_sim_step_n(wl_handle* h, int nsteps);
+/* sim_step!(sim,t_end; remeasure=false, max_steps) (src/WaterLily.jl:128-135): steps while time*U/L < t_end. */
+int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t max_steps, int64_t* steps_taken);
+
+/* mom_project!(a,b,w,t) (src/Flow.jl:223-232) on the current u. */
+int wl_project(wl_handle* h, float w);
+/* Pieces of the step exposed for operator-level parity tests:
+ * conv_diff!(f,u or u⁰,σ,λ) (src/Flow.jl:38-53) — without BDIM: f receives the raw flux sum r; */
+int wl_conv_diff(wl_handle* h, int from_u0);
+/* CFL(a) (src/Flow.jl:234-237) — returns the value, does not push it. */
+int wl_cfl(wl_handle* h, float* dt_out);
+
+/* Standalone operator API on the handle's pressure system (x≡p, L≡μ₀, z≡σ):
+ * mult!(pois,x) (src/Poisson.jl:63-69): σ = A·p, ghosts 0.
+ * solver!(pois) (src/Poisson.jl:204-214, src/MultiLevelPoisson.jl:108-127): solves A·p = σ in place, returns iterations. */
+int wl_pois_mult(wl_handle* h);
+int wl_pois_solve(wl_handle* h, int* iters_out);
+/* residual!(p) then L₂(p) (src/Poisson.jl:92-98,189). */
+int wl_pois_residual(wl_handle* h, float* r2_out);
+/* One smoother application on a level: kind 0 GaussSeidelRB!(it=4,ω), 1 Jacobi!(ω), 2 pcg!  (src/Poisson.jl:111-186) */
+int wl_pois_smooth(wl_handle* h, int level, int kind, float omega);
+/* One Vcycle!(ml;ω) (src/MultiLevelPoisson.jl:88-101). */
+int wl_pois_vcycle(wl_handle* h, float omega);
+int wl_num_levels(wl_handle* h, int* nlevels);
+/* Ghost-padded size of a level (N[3], N[2]=1 in 2-D) and its arrays in the reference layout. */
+int wl_level_dims(wl_handle* h, int level, int32_t* N);
+int wl_download_level(wl_handle* h, int level, int which, float* dst);
+int wl_upload_level(wl_handle* h, int level, int which, const float* src);
+
+/* Histories mirrored to the host: flow.Δt (src/Flow.jl:127) and pois.n (src/MultiLevelPoisson.jl:66).
+ * Call with buf=NULL to query the length. */
+int wl_get_dt(wl_handle* h, float* buf, int* len);
+int wl_set_dt(wl_handle* h, const float* buf, int len); /* restart: load!(flow.Δt) (ext/WaterLilyJLD2Ext.jl:40-50) */
+int wl_get_iters(wl_handle* h, int16_t* buf, int* len);
+/* The reference's solver log (src/MultiLevelPoisson.jl:111,116): rows of (iter, r2, omega). */
+int wl_get_solver_log(wl_handle* h, float* buf, int* rows);
+int wl_set_logging(wl_handle* h, int enabled);
+/* time(a) = sum(Δt[1:end-1]) (src/Flow.jl:174) */
+int wl_time(wl_handle* h, double* t);
+
+/* Per-kernel CUDA-event timing on the launching stream (the tracing hook the reference lacks).
+ * wl_get_timings writes a text table "kernel launches total_ms\n" and clears the records; buf=NULL queries the size. */
+int wl_set_profiling(wl_handle* h, int enabled);
+int wl_get_timings(wl_handle* h, char* buf, int* len);
+
+int wl_sync(wl_handle* h);
+/* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
+int wl_launch_count(wl_handle* h, int64_t* count);
+/* 1 if the constant-coefficient (NoBody) kernel variants are active. */
+int wl_is_const_coeff(wl_handle* h, int* flag);
+/* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */
+int wl_stream(wl_handle* h, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WL_B200_H */

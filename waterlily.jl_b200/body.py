@@ -1,0 +1,174 @@
+"""Immersed-body set-up on the host (numpy, Float32): `measure!` for static bodies.
+
+Body measurement is set-up only on this path (BASELINE.json north_star): the host evaluates the signed
+distance function, fills μ₀, μ₁, V, σ exactly as `measure!(flow,body;ϵ)` does (src/Body.jl:28-51,
+src/AutoBody.jl:29-37) and uploads them through wl_upload; wl_update then rebuilds the Poisson hierarchy.
+"""
+import numpy as np
+
+F = np.float32
+
+
+class NoBody:
+    """struct NoBody (src/Body.jl:81-83)"""
+
+
+class AutoBody:
+    """AutoBody(sdf) (src/AutoBody.jl:10-14) for a static map.  `sdf(x)` takes a tuple of D coordinate arrays and
+    returns the signed distance; `grad(x)` returns the D gradient components (the reference gets them from
+    ForwardDiff; here the caller supplies them, or central differences in Float64 are used)."""
+
+    def __init__(self, sdf, grad=None):
+        self.sdf = sdf
+        self._grad = grad
+
+    def grad(self, x):
+        if self._grad is not None:
+            return self._grad(x)
+        h = 1e-4
+        x64 = [np.asarray(c, np.float64) for c in x]
+        out = []
+        for d in range(len(x)):
+            xp = list(x64)
+            xm = list(x64)
+            xp[d] = x64[d] + h
+            xm[d] = x64[d] - h
+            out.append(((np.asarray(self.sdf(xp), np.float64) - np.asarray(self.sdf(xm), np.float64)) / (2 * h)).astype(F))
+        return out
+
+
+class Sphere(AutoBody):
+    """AutoBody((x,t)->√sum(abs2, x .- center) - radius)  (README.md:118-119; circle in 2-D)"""
+
+    def __init__(self, center, radius):
+        self.c = [F(v) for v in center]
+        self.R = F(radius)
+        super().__init__(self._sdf, self._g)
+
+    def _sdf(self, x):
+        s = F(0)
+        for d, xd in enumerate(x):
+            s = s + (xd - self.c[d]) * (xd - self.c[d])
+        return np.sqrt(s) - self.R
+
+    def _g(self, x):
+        s = F(0)
+        for d, xd in enumerate(x):
+            s = s + (xd - self.c[d]) * (xd - self.c[d])
+        m = np.sqrt(s)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return [(xd - self.c[d]) / m for d, xd in enumerate(x)]
+
+
+class Torus(AutoBody):
+    """Torus with its axis along x (WaterLily-Examples ThreeD_Donut recipe): major radius R, minor radius r."""
+
+    def __init__(self, center, R, r):
+        self.c = [F(v) for v in center]
+        self.R = F(R)
+        self.r = F(r)
+        super().__init__(self._sdf, self._g)
+
+    def _parts(self, x):
+        xx, y, z = x[0] - self.c[0], x[1] - self.c[1], x[2] - self.c[2]
+        rho = np.sqrt(y * y + z * z)
+        q = rho - self.R
+        m = np.sqrt(q * q + xx * xx)
+        return xx, y, z, rho, q, m
+
+    def _sdf(self, x):
+        return self._parts(x)[5] - self.r
+
+    def _g(self, x):
+        xx, y, z, rho, q, m = self._parts(x)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return [xx / m, (q / m) * (y / rho), (q / m) * (z / rho)]
+
+
+def _sinpi(x):
+    return np.sin(np.pi * x.astype(np.float64)).astype(F)
+
+
+def _cospi(x):
+    return np.cos(np.pi * x.astype(np.float64)).astype(F)
+
+
+def _kern0(d):  # src/Body.jl:55
+    return (F(1) + d + _sinpi(d) / F(np.pi)) / F(2)
+
+
+def _kern1(d):  # src/Body.jl:56
+    return (F(1) - d * d) / F(4) - (d * _sinpi(d) + (F(1) + _cospi(d)) / F(np.pi)) / (F(2) * F(np.pi))
+
+
+def mu0_kernel(d, eps):
+    """μ₀(d,ϵ) = d/ϵ < -1+√eps(d) ? 0 : kern₀(min(d/ϵ,1))  (src/Body.jl:59); eps(d) is the ulp at d."""
+    d = np.asarray(d, F)
+    e = F(eps)
+    s = d / e
+    ulp = np.spacing(np.abs(d)).astype(F)
+    return np.where(s < F(-1) + np.sqrt(ulp), F(0), _kern0(np.minimum(s, F(1)))).astype(F)
+
+
+def mu1_kernel(d, eps):
+    """μ₁(d,ϵ) = ϵ·kern₁(clamp(d/ϵ,-1,1))  (src/Body.jl:60)"""
+    d = np.asarray(d, F)
+    e = F(eps)
+    return (e * _kern1(np.clip(d / e, F(-1), F(1)))).astype(F)
+
+
+def _loc(N, i):
+    """Coordinate arrays of loc(i,I) for every cell (src/core.jl:177); i=-1 gives cell centres.  C-order shapes."""
+    D = len(N)
+    shape = tuple(reversed(N))
+    out = []
+    for d in range(D):
+        idx = np.arange(1, N[d] + 1, dtype=F) - F(1.5) - (F(0.5) if d == i else F(0))
+        sh = [1] * D
+        sh[D - 1 - d] = N[d]
+        out.append(np.broadcast_to(idx.reshape(sh), shape))
+    return out
+
+
+def measure_body(N, body, eps=1.0):
+    """measure!(flow,body;ϵ) for a static AutoBody (src/Body.jl:28-51 + src/AutoBody.jl:29-37) before the two BC!
+    calls (those run on the device).  N = ghost-padded sizes.  Returns (mu0[D,...], mu1[D*D,...], V[D,...], sigma[...])
+    in C order (component slowest, x fastest); μ₁[I,i,j] is component i + D*j."""
+    D = len(N)
+    shape = tuple(reversed(N))
+    eps = F(eps)
+    V = np.zeros((D,) + shape, F)
+    mu0 = np.ones((D,) + shape, F)
+    mu1 = np.zeros((D * D,) + shape, F)
+    sigma = np.zeros(shape, F)
+    d2 = F((F(2) + eps) ** 2)
+    inner = tuple(slice(1, -1) for _ in range(D))
+    xc = [c[inner] for c in _loc(N, -1)]
+    sig_in = np.asarray(body.sdf(xc), F)
+    sigma[inner] = sig_in
+    band = sig_in * sig_in < d2
+    inside_far = (~band) & (sig_in < 0)
+    for i in range(D):
+        xf = [c[inner][band] for c in _loc(N, i)]
+        d = np.asarray(body.sdf(xf), F)
+        near = ~(d * d > d2)  # measure(): skip n when d² > fastd²
+        g = [np.asarray(c, F) for c in body.grad(xf)]
+        bad = np.zeros(d.shape, bool)
+        for c in g:
+            bad |= np.isnan(c)
+        use = near & ~bad
+        m = np.sqrt(sum((c * c for c in g), F(0))).astype(F)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            dn = np.where(use, d / m, d).astype(F)
+            n = [np.where(use, c / m, F(0)).astype(F) for c in g]
+        di = np.where(np.abs(dn) <= F(0.5), dn, np.copysign(dn, sig_in[band])).astype(F)
+        tmp = mu0[i][inner]
+        tmp[band] = mu0_kernel(di, eps)
+        tmp[inside_far] = F(0)
+        mu0[i][inner] = tmp
+        k1 = mu1_kernel(di, eps)
+        for j in range(D):
+            tmp = mu1[i + D * j][inner]
+            tmp[band] = k1 * n[j]
+            mu1[i + D * j][inner] = tmp
+    return mu0, mu1, V, sigma

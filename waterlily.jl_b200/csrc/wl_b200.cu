@@ -1,0 +1,996 @@
+// wl_b200.cu — host side of libwl_b200.so: the C ABI declared in include/wl_b200.h and the
+// orchestration of mom_step! (src/Flow.jl:156-167) and solver!(::MultiLevelPoisson)
+// (src/MultiLevelPoisson.jl:108-127) over the kernels in wl_kernels.cuh.
+//
+// There is no CPU fallback anywhere in this file: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wl_b200.h"
+#include "wl_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_) return r_;       \
+  } while (0)
+
+enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4, SLOT_RHO = 5, SLOT_SIG = 6, SLOT_LINF = 7, NSLOTS = 16 };
+
+struct Level {
+  Grid g;
+  float *L = nullptr, *Dg = nullptr, *iD = nullptr, *x = nullptr, *eps = nullptr, *r = nullptr, *r2 = nullptr, *z = nullptr;
+  int c[3] = {0, 0, 0};  // coarsening mask from the previous (finer) level
+  bool ownL = false, ownz = false;
+  Lvl dev() const {
+    Lvl l;
+    l.g = g;
+    l.L = L;
+    l.Dg = Dg;
+    l.iD = iD;
+    l.x = x;
+    l.eps = eps;
+    l.r = r;
+    l.r2 = r2;
+    l.z = z;
+    return l;
+  }
+  Box inside() const {
+    Box b;
+    for (int d = 0; d < 3; d++) {
+      b.lo[d] = d < g.D ? 1 : 0;
+      b.n[d] = d < g.D ? g.N[d] - 2 : 1;
+    }
+    return b;
+  }
+  Box all() const {
+    Box b;
+    for (int d = 0; d < 3; d++) {
+      b.lo[d] = 0;
+      b.n[d] = g.N[d];
+    }
+    return b;
+  }
+  size_t cells() const { return (size_t)g.sc; }
+};
+
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+
+struct wl_handle {
+  wl_config cfg;
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+  std::string prof_text;
+  int D;
+  Grid g;
+  float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
+  std::vector<Level> levels;
+  RedBuf red{nullptr, nullptr, nullptr};
+  double* h_out = nullptr;  // pinned mirror of red.out
+  float* d_dthist = nullptr;
+  size_t dt_cap = 0;
+  float* d_scal = nullptr;  // [0]=omega, [1]=one, [2]=alpha, [3]=beta, [4]=scratch dt
+  float* h_scal = nullptr;  // pinned
+  std::vector<float> dt;    // host mirror of flow.Δt
+  size_t dt_dev_len = 0;    // entries valid on the device
+  std::vector<int16_t> iters;
+  std::vector<float> log;  // rows of (iter, rinf, r2, omega)
+  bool logging = false;
+  cudaStream_t st = nullptr;
+  int64_t launches = 0;
+  double tol;
+  int itmx;
+  std::vector<void*> allocs;
+};
+
+// Optional per-kernel CUDA-event timing on the launching stream (wl_set_profiling / wl_get_timings).
+static void prof_begin(wl_handle* h, const char* name) {
+  if (!h->prof) return;
+  ProfRec r;
+  r.name = name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, h->st);
+  h->prof_recs.push_back(r);
+}
+static void prof_end(wl_handle* h) {
+  if (!h->prof) return;
+  cudaEventRecord(h->prof_recs.back().b, h->st);
+}
+
+static Grid make_grid(int D, const int* N, const int* per) {
+  Grid g;
+  g.D = D;
+  for (int d = 0; d < 3; d++) {
+    g.N[d] = d < D ? N[d] : 1;
+    g.per[d] = d < D ? (per[d] != 0) : 0;
+  }
+  g.px = ((g.N[0] + 31) / 32) * 32;
+  g.s[0] = 1;
+  g.s[1] = g.px;
+  g.s[2] = (i64)g.px * g.N[1];
+  g.sc = (i64)g.px * g.N[1] * g.N[2];
+  return g;
+}
+
+static inline dim3 blk(int D) { return D == 3 ? dim3(32, 4, 4) : dim3(32, 8, 1); }
+static inline dim3 grd(const Box& b, dim3 t) { return dim3(cdiv(b.n[0], t.x), cdiv(b.n[1], t.y), cdiv(b.n[2], t.z)); }
+static inline size_t nblocks(const Box& b, dim3 t) {
+  dim3 g = grd(b, t);
+  return (size_t)g.x * g.y * g.z;
+}
+
+#define LAUNCH(h, kern, grid, block, ...)                \
+  do {                                                   \
+    prof_begin(h, #kern);                                \
+    kern<<<(grid), (block), 0, (h)->st>>>(__VA_ARGS__);  \
+    prof_end(h);                                         \
+    (h)->launches++;                                     \
+  } while (0)
+// dispatch on the spatial dimension
+#define LAUNCH_D(h, kern, grid, block, ...)                       \
+  do {                                                            \
+    if ((h)->D == 3)                                              \
+      LAUNCH(h, kern<3>, grid, block, __VA_ARGS__);               \
+    else                                                          \
+      LAUNCH(h, kern<2>, grid, block, __VA_ARGS__);               \
+  } while (0)
+
+static int dalloc(wl_handle* h, float** p, size_t nfloats) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, nfloats * sizeof(float));
+  if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", nfloats * sizeof(float), cudaGetErrorString(e));
+  e = cudaMemsetAsync(q, 0, nfloats * sizeof(float), h->st);
+  if (e != cudaSuccess) return fail("cudaMemset: %s", cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (float*)q;
+  return 0;
+}
+
+static const float* dtp(wl_handle* h) { return h->d_dthist + (h->dt_dev_len - 1); }
+
+// ---- boundary conditions ------------------------------------------------------------------
+static void launch_bc_vec(wl_handle* h, const Grid& g, float* a, const float* U, int saveexit, const float* keep_src) {
+  // planes are at most max(N)² cells; one launch covers all 3·D planes (blockIdx.z)
+  int m0 = std::max(g.N[0], g.N[1]), m1 = g.D == 3 ? std::max(g.N[1], g.N[2]) : 1;
+  if (g.D == 3) m0 = std::max(m0, g.N[0]);
+  dim3 b = g.D == 3 ? dim3(32, 8, 1) : dim3(64, 1, 1);
+  dim3 gr(cdiv(m0, b.x), cdiv(m1, b.y), 3 * g.D);
+  if (g.D == 3)
+    LAUNCH(h, k_bc_vec<3>, gr, b, g, a, keep_src, U[0], U[1], U[2], saveexit);
+  else
+    LAUNCH(h, k_bc_vec<2>, gr, b, g, a, keep_src, U[0], U[1], U[2], saveexit);
+}
+static void launch_perbc(wl_handle* h, const Grid& g, float* a) {
+  if (!(g.per[0] || g.per[1] || g.per[2])) return;
+  int m0 = std::max(g.N[0], g.N[1]), m1 = g.D == 3 ? std::max(g.N[1], g.N[2]) : 1;
+  dim3 b = g.D == 3 ? dim3(32, 8, 1) : dim3(64, 1, 1);
+  dim3 gr(cdiv(m0, b.x), cdiv(m1, b.y), 2 * g.D);
+  if (g.D == 3)
+    LAUNCH(h, k_perbc<3>, gr, b, g, a);
+  else
+    LAUNCH(h, k_perbc<2>, gr, b, g, a);
+}
+static void launch_exitbc(wl_handle* h, float* u, const float* u0, float dt_scale) {
+  const Grid& g = h->g;
+  dim3 b = g.D == 3 ? dim3(16, 16, 1) : dim3(256, 1, 1);
+  dim3 gr(cdiv(g.N[1] - 2, b.x), g.D == 3 ? cdiv(g.N[2] - 2, b.y) : 1, 1);
+  for (int stage = 0; stage < 3; stage++) LAUNCH_D(h, k_exitbc, gr, b, g, u, u0, dtp(h), dt_scale, h->red, SLOT_EXIT0, stage);
+}
+
+// ---- Poisson hierarchy ---------------------------------------------------------------------
+static inline bool divisible(int N) { return N % 2 == 0 && N > 4; }  // src/MultiLevelPoisson.jl:52
+
+static int build_levels(wl_handle* h) {
+  Level l0;
+  l0.g = h->g;
+  l0.L = h->mu0;
+  l0.z = h->sigma;
+  h->levels.push_back(l0);
+  if (h->cfg.pois_kind == WL_POIS_MULTILEVEL) {
+    const int maxlevels = 10;
+    while ((int)h->levels.size() <= maxlevels) {  // src/MultiLevelPoisson.jl:70-72
+      const Grid& gf = h->levels.back().g;
+      bool any = false;
+      int N[3];
+      Level lc;
+      for (int d = 0; d < 3; d++) {
+        const bool c = d < gf.D && divisible(gf.N[d]);
+        lc.c[d] = c;
+        N[d] = c ? 1 + gf.N[d] / 2 : gf.N[d];
+        any |= c;
+      }
+      if (!any) break;
+      lc.g = make_grid(gf.D, N, gf.per);
+      lc.ownL = lc.ownz = true;
+      h->levels.push_back(lc);
+    }
+    if (h->levels.size() <= 2) return fail("MultiLevelPoisson requires size=a2^n, where n>2");
+  }
+  for (size_t i = 0; i < h->levels.size(); i++) {
+    Level& l = h->levels[i];
+    const size_t n = l.cells();
+    if (l.ownL) TRY(dalloc(h, &l.L, n * l.g.D));
+    if (l.ownz) TRY(dalloc(h, &l.z, n));
+    TRY(dalloc(h, &l.Dg, n));
+    TRY(dalloc(h, &l.iD, n));
+    TRY(dalloc(h, &l.x, n));
+    TRY(dalloc(h, &l.eps, n));
+    TRY(dalloc(h, &l.r, n));
+    TRY(dalloc(h, &l.r2, n));
+  }
+  return 0;
+}
+
+static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.jl:79-86
+  const float zero[3] = {0, 0, 0};
+  for (size_t i = 0; i < h->levels.size(); i++) {
+    Level& l = h->levels[i];
+    dim3 b = blk(h->D);
+    if (i > 0) {
+      const Level& fl = h->levels[i - 1];
+      LAUNCH_D(h, k_restrictL, grd(l.inside(), b), b, l.g, fl.g, l.inside(), l.L, (const float*)fl.L, l.c[0], l.c[1], l.c[2]);
+      launch_bc_vec(h, l.g, l.L, zero, 0, l.L);
+    }
+    LAUNCH_D(h, k_set_diag, grd(l.inside(), b), b, l.g, l.inside(), (const float*)l.L, l.Dg, l.iD);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static void set_scalar(wl_handle* h, int idx, float v) {
+  LAUNCH(h, k_set_scalar, 1, 1, h->d_scal + idx, v);
+}
+static int read_slot(wl_handle* h, int slot, double* out) {
+  CK(cudaMemcpyAsync(h->h_out + slot, h->red.out + slot, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  *out = h->h_out[slot];
+  return 0;
+}
+
+// GaussSeidelRB!(p;it=4,ω)  src/Poisson.jl:141-148
+static void gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  Lvl d = l.dev();
+  LAUNCH_D(h, k_gs_init, grd(in, b), b, d, in);
+  Box half = in;
+  half.n[0] = (in.n[0] + 1) / 2;
+  for (int k0 = 1; k0 <= 4; k0++) LAUNCH_D(h, k_gs_sweep, grd(half, b), b, d, in, k0);
+  LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, h->red, SLOT_R2);
+}
+// Jacobi!(p;ω=1)  src/Poisson.jl:111-114
+static void jacobi(wl_handle* h, Level& l, int x_is_zero) {
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
+  std::swap(l.r, l.r2);
+}
+// pcg!(p;it=6)  src/Poisson.jl:166-186 — host-driven (three dots per iteration decide early exits)
+static int pcg(wl_handle* h, Level& l, int it = 6) {
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  Lvl d = l.dev();
+  const float eps32 = 1.1920929e-7f;
+  double v;
+  LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 0, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
+  TRY(read_slot(h, SLOT_RHO, &v));
+  float rho = (float)v;
+  if (std::fabs(rho) < 10 * eps32) return 0;
+  for (int i = 1; i <= it; i++) {
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 1, (const float*)h->d_scal + 2, h->red, SLOT_SIG);
+    TRY(read_slot(h, SLOT_SIG, &v));
+    const float alpha = rho / (float)v;
+    if (std::fabs(alpha) < 1e-2 || std::fabs(alpha) > 1e2) return 0;
+    set_scalar(h, 2, alpha);
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 2, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
+    if (i == it) return 0;
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 3, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
+    TRY(read_slot(h, SLOT_RHO, &v));
+    const float rho2 = (float)v;
+    if (std::fabs(rho2) < 10 * eps32) return 0;
+    const float beta = rho2 / rho;
+    set_scalar(h, 3, beta);
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 4, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
+    rho = rho2;
+  }
+  return 0;
+}
+static int l2_norm(wl_handle* h, Level& l, float* out, int want_max = 0) {
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, h->red, want_max ? SLOT_LINF : SLOT_R2, want_max);
+  double v;
+  TRY(read_slot(h, want_max ? SLOT_LINF : SLOT_R2, &v));
+  *out = (float)v;
+  return 0;
+}
+// smooth!(p;ω)  src/MultiLevelPoisson.jl:106
+static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
+  if (h->cfg.smoother == WL_SMOOTH_GSRB) {
+    gs_smooth(h, l, wp, x_is_zero, with_l2);
+    return 0;
+  }
+  if (x_is_zero) CK(cudaMemsetAsync(l.x, 0, l.cells() * sizeof(float), h->st));
+  TRY(pcg(h, l));
+  if (with_l2) {
+    dim3 b = blk(h->D);
+    Box in = l.inside();
+    LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, h->red, SLOT_R2, 0);
+  }
+  return 0;
+}
+// Vcycle!(ml;l,ω)  src/MultiLevelPoisson.jl:88-101
+static int vcycle(wl_handle* h, size_t li, const float* wp) {
+  Level& fine = h->levels[li];
+  Level& coarse = h->levels[li + 1];
+  dim3 b = blk(h->D);
+  jacobi(h, fine, li > 0);
+  Box cin = coarse.inside();
+  LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
+  const bool last = (li + 2 >= h->levels.size());
+  if (!last) TRY(vcycle(h, li + 1, wp));
+  TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
+  Box fin = fine.inside();
+  LAUNCH_D(h, k_prolong_inc, grd(fin, b), b, fine.dev(), coarse.g, (const float*)coarse.x, fin, wp, coarse.c[0], coarse.c[1], coarse.c[2]);
+  return 0;
+}
+
+static void log_row(wl_handle* h, int it, float rinf, float r2, float w) {
+  h->log.push_back((float)it);
+  h->log.push_back(rinf);
+  h->log.push_back(r2);
+  h->log.push_back(w);
+}
+
+// residual!(p) + L₂  (src/Poisson.jl:92-98,189); with_div fuses div + x.*=dt of mom_project! (src/Flow.jl:225)
+static int residual(wl_handle* h, int with_div, float w, float* r2) {
+  Level& l = h->levels[0];
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
+  float count = 1;
+  for (int d = 0; d < h->D; d++) count *= (float)(l.g.N[d] - 2);
+  LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
+  double v;
+  TRY(read_slot(h, SLOT_R2, &v));
+  *r2 = (float)v;
+  return 0;
+}
+
+// solver!(ml) src/MultiLevelPoisson.jl:108-127  /  solver!(p::Poisson) src/Poisson.jl:204-214   (after residual!)
+static int solve_after_residual(wl_handle* h, float r2, int* iters_out) {
+  Level& p = h->levels[0];
+  float rinf = NAN;
+  if (h->logging) TRY(l2_norm(h, p, &rinf, 1));
+  int np = 0;
+  if (h->cfg.pois_kind == WL_POIS_MULTILEVEL) {
+    float w = 1.f;
+    log_row(h, np, rinf, r2, w);
+    while (np < h->itmx) {
+      set_scalar(h, 0, w);
+      TRY(vcycle(h, 0, h->d_scal + 0));
+      TRY(smooth(h, p, h->d_scal + 0, 0, 1));
+      double v;
+      TRY(read_slot(h, SLOT_R2, &v));
+      const float rnew = (float)v;
+      np++;
+      if (h->logging) TRY(l2_norm(h, p, &rinf, 1));
+      log_row(h, np, rinf, rnew, w);
+      if (rnew >= r2)
+        w = (float)std::max(0.2, 0.9 * (double)w);
+      else if (rnew < r2)
+        w = (float)std::min(1.0, 1.02 * (double)w);
+      r2 = rnew;
+      if ((double)r2 < h->tol) break;
+    }
+  } else {
+    log_row(h, np, rinf, r2, 1.f);
+    while (np < h->itmx) {
+      TRY(pcg(h, p));
+      TRY(l2_norm(h, p, &r2));
+      np++;
+      if (h->logging) TRY(l2_norm(h, p, &rinf, 1));
+      log_row(h, np, rinf, r2, 1.f);
+      if ((double)r2 < h->tol) break;
+    }
+  }
+  h->iters.push_back((int16_t)np);
+  if (iters_out) *iters_out = np;
+  return 0;
+}
+
+// ---- momentum -------------------------------------------------------------------------------
+template <int LAM>
+static void conv_launch(wl_handle* h, const float* ua, int mode) {
+  const Grid& g = h->g;
+  dim3 b = blk(h->D);
+  Box all = h->levels[0].all();
+  prof_begin(h, "k_conv_bdim1");
+  if (h->D == 3)
+    k_conv_bdim1<3, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode);
+  else
+    k_conv_bdim1<2, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode);
+  prof_end(h);
+  h->launches++;
+}
+static void conv_bdim1(wl_handle* h, const float* ua, int mode) {
+  if (h->cfg.lambda == WL_QUICK)
+    conv_launch<0>(h, ua, mode);
+  else if (h->cfg.lambda == WL_CDS)
+    conv_launch<1>(h, ua, mode);
+  else
+    conv_launch<2>(h, ua, mode);
+}
+
+// mom_project!(a,b,w,t)  src/Flow.jl:223-232
+static int project(wl_handle* h, float w) {
+  float r2;
+  TRY(residual(h, 1, w, &r2));
+  TRY(solve_after_residual(h, r2, nullptr));
+  Level& l = h->levels[0];
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
+  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  return 0;
+}
+
+static int ensure_dt_capacity(wl_handle* h, size_t need) {
+  if (need <= h->dt_cap) return 0;
+  size_t cap = std::max<size_t>(need * 2, 1 << 16);
+  float* q = nullptr;
+  CK(cudaMalloc(&q, cap * sizeof(float)));
+  if (h->d_dthist) {
+    CK(cudaMemcpyAsync(q, h->d_dthist, h->dt_dev_len * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaFree(h->d_dthist));
+  }
+  h->d_dthist = q;
+  h->dt_cap = cap;
+  return 0;
+}
+static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vector
+  if (h->dt.size() < h->dt_dev_len) {
+    const size_t old = h->dt.size();
+    h->dt.resize(h->dt_dev_len);
+    CK(cudaMemcpyAsync(h->dt.data() + old, h->d_dthist + old, (h->dt_dev_len - old) * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  return 0;
+}
+
+// mom_step!(a,b)  src/Flow.jl:156-167
+static int mom_step(wl_handle* h) {
+  TRY(ensure_dt_capacity(h, h->dt_dev_len + 1));
+  const Grid& g = h->g;
+  dim3 b = blk(h->D);
+  Level& l = h->levels[0];
+  Box in = l.inside(), all = l.all();
+  std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
+  // predictor  src/Flow.jl:190-196
+  conv_bdim1(h, h->u0, 1);
+  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, 0);
+  launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u0);
+  if (h->cfg.exitBC) launch_exitbc(h, h->u, h->u0, 1.f);
+  TRY(project(h, 1.f));
+  // corrector  src/Flow.jl:205-210
+  conv_bdim1(h, h->u, 1);
+  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, 1);
+  launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  TRY(project(h, 0.5f));
+  // push!(a.Δt, CFL(a))
+  LAUNCH_D(h, k_cfl, grd(all, b), b, g, all, (const float*)h->u, h->sigma, h->cfg.nu, h->d_dthist + h->dt_dev_len, h->red, SLOT_CFL);
+  h->dt_dev_len++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- field table --------------------------------------------------------------------------
+static int field_ptr(wl_handle* h, int field, float** p, int* ncomp) {
+  const int D = h->D;
+  switch (field) {
+    case WL_U: *p = h->u; *ncomp = D; return 0;
+    case WL_U0: *p = h->u0; *ncomp = D; return 0;
+    case WL_F: *p = h->f; *ncomp = D; return 0;
+    case WL_P: *p = h->p; *ncomp = 1; return 0;
+    case WL_SIGMA: *p = h->sigma; *ncomp = 1; return 0;
+    case WL_V: *p = h->V; *ncomp = D; return 0;
+    case WL_MU0: *p = h->mu0; *ncomp = D; return 0;
+    case WL_MU1: *p = h->mu1; *ncomp = D * D; return 0;
+  }
+  return fail("unknown field id %d", field);
+}
+static int copy_in(wl_handle* h, const Grid& g, float* dst, const float* src, int ncomp, int src_is_device) {
+  const size_t rows = (size_t)g.N[1] * g.N[2] * ncomp;
+  CK(cudaMemcpy2DAsync(dst, (size_t)g.px * 4, src, (size_t)g.N[0] * 4, (size_t)g.N[0] * 4, rows,
+                       src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+  if (!src_is_device) CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+static int copy_out(wl_handle* h, const Grid& g, float* dst, const float* src, int ncomp, int dst_is_device) {
+  const size_t rows = (size_t)g.N[1] * g.N[2] * ncomp;
+  CK(cudaMemcpy2DAsync(dst, (size_t)g.N[0] * 4, src, (size_t)g.px * 4, (size_t)g.N[0] * 4, rows,
+                       dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
+  if (!dst_is_device) CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+// ============================================================================================
+extern "C" {
+
+const char* wl_last_error(void) { return g_err.c_str(); }
+
+int wl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int wl_create(const wl_config* cfg, wl_handle** out) {
+  if (!cfg || !out) return fail("null argument");
+  if (cfg->D != 2 && cfg->D != 3) return fail("D must be 2 or 3 (got %d)", cfg->D);
+  for (int d = 0; d < cfg->D; d++)
+    if (cfg->n[d] < 2) return fail("dims[%d]=%d too small", d, cfg->n[d]);
+  if (cfg->lambda < 0 || cfg->lambda > 2) return fail("unknown convective scheme %d", cfg->lambda);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: libwl_b200 has no CPU fallback (cudaGetDeviceCount found %d devices)", ndev);
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  wl_handle* h = new wl_handle();
+  h->cfg = *cfg;
+  h->D = cfg->D;
+  h->tol = cfg->tol > 0 ? (double)cfg->tol : 1e-4;
+  h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
+  int N[3];
+  for (int d = 0; d < 3; d++) N[d] = d < cfg->D ? cfg->n[d] + 2 : 1;
+  h->g = make_grid(cfg->D, N, cfg->perdir);
+  int rc = 0;
+  do {
+    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+      rc = fail("cudaStreamCreate failed");
+      break;
+    }
+    const size_t n = (size_t)h->g.sc;
+    const int D = h->D;
+    if ((rc = dalloc(h, &h->u, n * D)) || (rc = dalloc(h, &h->u0, n * D)) || (rc = dalloc(h, &h->f, n * D)) || (rc = dalloc(h, &h->p, n)) ||
+        (rc = dalloc(h, &h->sigma, n)) || (rc = dalloc(h, &h->V, n * D)) || (rc = dalloc(h, &h->mu0, n * D)) || (rc = dalloc(h, &h->mu1, n * D * D)))
+      break;
+    if ((rc = build_levels(h))) break;
+    // reduction buffers
+    Box all = h->levels[0].all();
+    const size_t nb = std::max(nblocks(all, blk(D)), (size_t)1024);
+    void* q;
+    if (cudaMalloc(&q, nb * 2 * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc partials"); break; }
+    h->red.partials = (double*)q;
+    h->allocs.push_back(q);
+    if (cudaMalloc(&q, 256) != cudaSuccess) { rc = fail("cudaMalloc ticket"); break; }
+    cudaMemsetAsync(q, 0, 256, h->st);
+    h->red.ticket = (unsigned int*)q;
+    h->allocs.push_back(q);
+    if (cudaMalloc(&q, NSLOTS * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc out"); break; }
+    cudaMemsetAsync(q, 0, NSLOTS * sizeof(double), h->st);
+    h->red.out = (double*)q;
+    h->allocs.push_back(q);
+    if (cudaMallocHost((void**)&h->h_out, NSLOTS * sizeof(double)) != cudaSuccess) { rc = fail("cudaMallocHost"); break; }
+    if ((rc = dalloc(h, &h->d_scal, 16))) break;
+    if ((rc = ensure_dt_capacity(h, 1024))) break;
+    // Flow ctor: Δt=[dt0]; u = uBC everywhere; BC!; exitBC!(u,u,0); u⁰=copy(u); μ₀=1; BC!(μ₀,0)
+    h->dt.assign(1, cfg->dt0);
+    if (cudaMemcpyAsync(h->d_dthist, h->dt.data(), sizeof(float), cudaMemcpyHostToDevice, h->st) != cudaSuccess) { rc = fail("memcpy dt"); break; }
+    h->dt_dev_len = 1;
+    set_scalar(h, 0, 1.f);
+    set_scalar(h, 1, 1.f);
+    for (int i = 0; i < D; i++) {
+      LAUNCH(h, k_fill, 1024, 256, h->u + (size_t)i * n, n, cfg->uBC[i]);
+      LAUNCH(h, k_fill, 1024, 256, h->mu0 + (size_t)i * n, n, 1.f);
+    }
+    const float zero[3] = {0, 0, 0};
+    launch_bc_vec(h, h->g, h->mu0, zero, 0, h->mu0);
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = fail("init sync: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    if ((rc = wl_apply_bc(h))) break;
+    if ((rc = update_levels(h))) break;
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = fail("init sync: %s", cudaGetErrorString(cudaGetLastError())); break; }
+  } while (0);
+  if (rc) {
+    std::string keep = g_err;
+    wl_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int wl_destroy(wl_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  for (void* q : h->allocs) cudaFree(q);
+  if (h->d_dthist) cudaFree(h->d_dthist);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
+  if (!h || !src) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(field_ptr(h, field, &p, &nc));
+  return copy_in(h, h->g, p, src, nc, src_is_device);
+}
+
+int wl_download(wl_handle* h, int field, float* dst, int dst_is_device) {
+  if (!h || !dst) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(field_ptr(h, field, &p, &nc));
+  if (field == WL_P) launch_perbc(h, h->g, h->p);  // perBC!(p.x) at the end of solver! (ghosts are materialised lazily)
+  return copy_out(h, h->g, dst, p, nc, dst_is_device);
+}
+
+int wl_apply_bc(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  launch_exitbc(h, h->u, h->u, 0.f);
+  CK(cudaMemcpyAsync(h->u0, h->u, (size_t)h->g.sc * h->D * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_measure_bc(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  const float zero[3] = {0, 0, 0};
+  launch_bc_vec(h, h->g, h->mu0, zero, 0, h->mu0);
+  launch_bc_vec(h, h->g, h->V, zero, h->cfg.exitBC, h->V);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_update(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  return update_levels(h);
+}
+
+int wl_mom_step(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  return mom_step(h);
+}
+
+int wl_sim_step_n(wl_handle* h, int nsteps) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < nsteps; i++) TRY(mom_step(h));
+  return 0;
+}
+
+int wl_time(wl_handle* h, double* t) {
+  if (!h || !t) return fail("null argument");
+  TRY(sync_dt(h));
+  float s = 0.f;  // Float32 running sum like sum(@view(a.Δt[1:end-1]))
+  for (size_t i = 0; i + 1 < h->dt.size(); i++) s += h->dt[i];
+  *t = (double)s;
+  return 0;
+}
+
+int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t max_steps, int64_t* steps_taken) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int64_t k = 0;
+  for (;;) {
+    double t;
+    TRY(wl_time(h, &t));
+    if (!(t * U / L < t_end) || k >= max_steps) break;
+    TRY(mom_step(h));
+    k++;
+  }
+  if (steps_taken) *steps_taken = k;
+  return 0;
+}
+
+int wl_project(wl_handle* h, float w) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  return project(h, w);
+}
+
+int wl_conv_diff(wl_handle* h, int from_u0) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  conv_bdim1(h, from_u0 ? h->u0 : h->u, 0);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_cfl(wl_handle* h, float* dt_out) {
+  if (!h || !dt_out) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  dim3 b = blk(h->D);
+  Box all = h->levels[0].all();
+  LAUNCH_D(h, k_cfl, grd(all, b), b, h->g, all, (const float*)h->u, h->sigma, h->cfg.nu, h->d_scal + 4, h->red, SLOT_CFL);
+  CK(cudaMemcpyAsync(dt_out, h->d_scal + 4, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int wl_pois_mult(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  Level& l = h->levels[0];
+  CK(cudaMemsetAsync(l.z, 0, l.cells() * sizeof(float), h->st));
+  dim3 b = blk(h->D);
+  Box in = l.inside();
+  LAUNCH_D(h, k_mult, grd(in, b), b, l.dev(), in, (const float*)h->p, l.z);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int load_x_from_p(wl_handle* h) {
+  Level& l = h->levels[0];
+  CK(cudaMemcpyAsync(l.x, h->p, l.cells() * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+  return 0;
+}
+static int store_x_to_p(wl_handle* h) {
+  Level& l = h->levels[0];
+  CK(cudaMemcpyAsync(h->p, l.x, l.cells() * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+  return 0;
+}
+
+int wl_pois_residual(wl_handle* h, float* r2_out) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  TRY(load_x_from_p(h));
+  float r2;
+  TRY(residual(h, 0, 1.f, &r2));
+  if (r2_out) *r2_out = r2;
+  return 0;
+}
+
+int wl_pois_solve(wl_handle* h, int* iters_out) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  TRY(load_x_from_p(h));
+  float r2;
+  TRY(residual(h, 0, 1.f, &r2));
+  TRY(solve_after_residual(h, r2, iters_out));
+  TRY(store_x_to_p(h));
+  launch_perbc(h, h->g, h->p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_pois_smooth(wl_handle* h, int level, int kind, float omega) {
+  if (!h) return fail("null handle");
+  if (level < 0 || level >= (int)h->levels.size()) return fail("level %d out of range", level);
+  CK(cudaSetDevice(h->cfg.device));
+  Level& l = h->levels[level];
+  set_scalar(h, 0, omega);
+  if (kind == 0)
+    gs_smooth(h, l, h->d_scal + 0, 0, 0);
+  else if (kind == 1)
+    jacobi(h, l, 0);  // reference Jacobi!(p) default ω=1
+  else
+    TRY(pcg(h, l));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_pois_vcycle(wl_handle* h, float omega) {
+  if (!h) return fail("null handle");
+  if (h->levels.size() < 2) return fail("single-level Poisson has no V-cycle");
+  CK(cudaSetDevice(h->cfg.device));
+  set_scalar(h, 0, omega);
+  TRY(vcycle(h, 0, h->d_scal + 0));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_num_levels(wl_handle* h, int* nlevels) {
+  if (!h || !nlevels) return fail("null argument");
+  *nlevels = (int)h->levels.size();
+  return 0;
+}
+
+int wl_level_dims(wl_handle* h, int level, int32_t* N) {
+  if (!h || !N) return fail("null argument");
+  if (level < 0 || level >= (int)h->levels.size()) return fail("level %d out of range", level);
+  for (int d = 0; d < 3; d++) N[d] = h->levels[level].g.N[d];
+  return 0;
+}
+
+static int level_ptr(wl_handle* h, int level, int which, float** p, int* nc) {
+  if (level < 0 || level >= (int)h->levels.size()) return fail("level %d out of range", level);
+  Level& l = h->levels[level];
+  *nc = 1;
+  switch (which) {
+    case WL_LVL_L: *p = l.L; *nc = h->D; return 0;
+    case WL_LVL_D: *p = l.Dg; return 0;
+    case WL_LVL_ID: *p = l.iD; return 0;
+    case WL_LVL_X: *p = l.x; return 0;
+    case WL_LVL_EPS: *p = l.eps; return 0;
+    case WL_LVL_R: *p = l.r; return 0;
+    case WL_LVL_Z: *p = l.z; return 0;
+  }
+  return fail("unknown level array %d", which);
+}
+int wl_download_level(wl_handle* h, int level, int which, float* dst) {
+  if (!h || !dst) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(level_ptr(h, level, which, &p, &nc));
+  return copy_out(h, h->levels[level].g, dst, p, nc, 0);
+}
+int wl_upload_level(wl_handle* h, int level, int which, const float* src) {
+  if (!h || !src) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(level_ptr(h, level, which, &p, &nc));
+  return copy_in(h, h->levels[level].g, p, src, nc, 0);
+}
+
+int wl_get_dt(wl_handle* h, float* buf, int* len) {
+  if (!h || !len) return fail("null argument");
+  TRY(sync_dt(h));
+  if (buf) {
+    const int n = std::min<int>(*len, (int)h->dt.size());
+    std::copy(h->dt.begin(), h->dt.begin() + n, buf);
+  }
+  *len = (int)h->dt.size();
+  return 0;
+}
+
+int wl_set_dt(wl_handle* h, const float* buf, int len) {
+  if (!h || !buf || len < 1) return fail("bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_dt_capacity(h, (size_t)len + 1));
+  h->dt.assign(buf, buf + len);
+  CK(cudaMemcpyAsync(h->d_dthist, h->dt.data(), len * sizeof(float), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  h->dt_dev_len = len;
+  return 0;
+}
+
+int wl_get_iters(wl_handle* h, int16_t* buf, int* len) {
+  if (!h || !len) return fail("null argument");
+  if (buf) {
+    const int n = std::min<int>(*len, (int)h->iters.size());
+    std::copy(h->iters.begin(), h->iters.begin() + n, buf);
+  }
+  *len = (int)h->iters.size();
+  return 0;
+}
+
+int wl_get_solver_log(wl_handle* h, float* buf, int* rows) {
+  if (!h || !rows) return fail("null argument");
+  const int have = (int)h->log.size() / 4;
+  if (buf) {
+    const int n = std::min(*rows, have);
+    std::copy(h->log.begin(), h->log.begin() + 4 * n, buf);
+  }
+  *rows = have;
+  return 0;
+}
+
+int wl_set_logging(wl_handle* h, int enabled) {
+  if (!h) return fail("null handle");
+  h->logging = enabled != 0;
+  return 0;
+}
+
+int wl_sync(wl_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_launch_count(wl_handle* h, int64_t* count) {
+  if (!h || !count) return fail("null argument");
+  *count = h->launches;
+  return 0;
+}
+
+int wl_set_profiling(wl_handle* h, int enabled) {
+  if (!h) return fail("null handle");
+  h->prof = enabled != 0;
+  return 0;
+}
+
+// Text table "kernel launches total_ms\n" of everything recorded since the last call; clears the records.
+int wl_get_timings(wl_handle* h, char* buf, int* len) {
+  if (!h || !len) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->st));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<long> cnt;
+  for (auto& r : h->prof_recs) {
+    float t = 0;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    std::string nm(r.name);
+    const size_t lt = nm.find('<');
+    if (lt != std::string::npos) nm = nm.substr(0, lt);
+    size_t k = 0;
+    for (; k < names.size(); k++)
+      if (names[k] == nm) break;
+    if (k == names.size()) {
+      names.push_back(nm);
+      ms.push_back(0);
+      cnt.push_back(0);
+    }
+    ms[k] += t;
+    cnt[k]++;
+  }
+  h->prof_recs.clear();
+  std::string& out = h->prof_text;
+  char line[256];
+  for (size_t k = 0; k < names.size(); k++) {
+    snprintf(line, sizeof line, "%s %ld %.6f\n", names[k].c_str(), cnt[k], ms[k]);
+    out += line;
+  }
+  const int need = (int)out.size() + 1;
+  if (buf) {
+    const int n = std::min<int>(*len - 1, (int)out.size());
+    if (n >= 0) {
+      memcpy(buf, out.data(), n);
+      buf[n] = 0;
+    }
+    out.clear();
+  }
+  *len = need;
+  return 0;
+}
+
+int wl_is_const_coeff(wl_handle* h, int* flag) {
+  if (!h || !flag) return fail("null argument");
+  *flag = 0;
+  return 0;
+}
+
+int wl_stream(wl_handle* h, void** stream) {
+  if (!h || !stream) return fail("null argument");
+  *stream = (void*)h->st;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,648 @@
+// wl_kernels.cuh — sm_100a kernels for WaterLily.jl's mom_step! path (general, variable-coefficient forms).
+// Each kernel cites the reference @loop(s) it fuses (paths relative to the WaterLily.jl tree).
+// Indices are 0-based here: Julia index I ↔ I-1; interior = 1 .. N-2; ghosts 0 and N-1.
+#pragma once
+#include "wl_common.cuh"
+
+// ------------------------------------------------------------------------------------
+// limiters  (src/Flow.jl:4-6, :27-36)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float median3(float a, float b, float c) {
+  if (a > b) {
+    if (b >= c) return b;
+    if (a > c) return c;
+  } else {
+    if (b <= c) return b;
+    if (a < c) return c;
+  }
+  return a;
+}
+template <int LAM>
+__device__ __forceinline__ float limiter(float u, float c, float d) {
+  if (LAM == 0) return median3((5.f * c + 2.f * d - u) / 6.f, c, median3(10.f * c - 9.f * u, c, d));  // quick
+  if (LAM == 1) return (c + d) / 2.f;                                                                  // cds
+  return (c <= fminf(u, d) || c >= fmaxf(u, d)) ? c : c + (d - c) * (c - u) / (d - u);                // vanLeer
+}
+
+// Flux through the LOWER j-face of cell I for momentum component i:
+//   F = ϕu*(j,CI(I,i),u,ϕ(i,CI(I,j),u),λ) − ν ∂(j,CI(I,i),u)
+// with the boundary variants of lowerBoundary!/upperBoundary! (src/Flow.jl:47,56-62):
+//   I_j == 1      : ϕuL (one-sided) or, periodic, ϕuP with the upwind point wrapped to N_j-3
+//   I_j == N_j-1  : ϕuR, or, periodic, the flux stored at the wrapped cell I_j → 1
+//   otherwise     : ϕu
+template <int D, int LAM>
+__device__ __forceinline__ float face_flux(const Grid& g, const float* __restrict__ ui, const float* __restrict__ uj, int i, int j, int Ij, i64 o,
+                                           float nu) {
+  const i64 sj = g.s[j], si = g.s[i];
+  const int Nj = g.N[j];
+  if (g.per[j] && Ij == Nj - 1) {
+    o -= (i64)(Nj - 2) * sj;
+    Ij = 1;
+  }
+  const float uf = (uj[o] + uj[o - si]) / 2.f;  // ϕ(i,CI(I,j),u)
+  const float c = ui[o - sj], d = ui[o];
+  const float diff = nu * (d - c);
+  float conv;
+  if (Ij == 1) {
+    if (g.per[j])
+      conv = uf > 0.f ? uf * limiter<LAM>(ui[o + (i64)(Nj - 4) * sj], c, d) : uf * limiter<LAM>(ui[o + sj], d, c);
+    else
+      conv = uf > 0.f ? uf * ((d + c) / 2.f) : uf * limiter<LAM>(ui[o + sj], d, c);
+  } else if (Ij == Nj - 1) {
+    conv = uf < 0.f ? uf * ((d + c) / 2.f) : uf * limiter<LAM>(ui[o - 2 * sj], c, d);
+  } else {
+    conv = uf > 0.f ? uf * limiter<LAM>(ui[o - 2 * sj], c, d) : uf * limiter<LAM>(ui[o + sj], d, c);
+  }
+  return conv - diff;
+}
+
+// conv_diff!(f,u,Φ,λ) in gather form (src/Flow.jl:38-62) fused with BDIM-1 (src/Flow.jl:178):
+//   r[I,i] = Σ_j [ F_ij(I) − F_ij(I+δ_j) ]  accumulated in the reference's order (+lo, −hi for j=1,2,3)
+//   f[I,i] = u⁰[I,i] + Δt·r[I,i] − V[I,i]            over ALL cells (ghost rows included, App. A.9-2)
+// and the stale-Φ bookkeeping of σ on upper-ghost cells that later enters maximum(σ) in CFL (App. A.9-1).
+// mode 0: write raw r (wl_conv_diff);  mode 1: write BDIM-1 f.
+template <int D, int LAM>
+__global__ void __launch_bounds__(512) k_conv_bdim1(Grid g, Box box, const float* __restrict__ ua, const float* __restrict__ u0,
+                                                    const float* __restrict__ V, float* __restrict__ f, float* __restrict__ sigma,
+                                                    const float* __restrict__ dtp, float nu, int mode) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  bool lowok = true;  // all I_k >= 1
+#pragma unroll
+  for (int d = 0; d < D; d++) lowok = lowok && (I[d] >= 1);
+  const float dt = *dtp;
+  float Fd_last = 0.f;  // F_{D-1,j}(I) for the stale-Φ record
+  int jphi = -1;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    const float* ui = ua + (i64)i * g.sc;
+    float r = 0.f;
+    if (lowok) {
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        if (I[j] <= g.N[j] - 2) {
+          const float* uj = ua + (i64)j * g.sc;
+          const float Flo = face_flux<D, LAM>(g, ui, uj, i, j, I[j], o, nu);
+          const float Fhi = face_flux<D, LAM>(g, ui, uj, i, j, I[j] + 1, o + g.s[j], nu);
+          r += Flo;
+          r -= Fhi;
+          if (i == D - 1 && I[j] >= (g.per[j] ? 1 : 2)) {
+            Fd_last = Flo;
+            jphi = j;
+          }
+        }
+      }
+    }
+    const i64 oc = o + (i64)i * g.sc;
+    f[oc] = mode ? (u0[oc] + dt * r - V[oc]) : r;
+  }
+  bool ghost = false;
+#pragma unroll
+  for (int d = 0; d < D; d++) ghost = ghost || (I[d] == g.N[d] - 1);
+  if (ghost && jphi >= 0) sigma[o] = Fd_last;
+}
+
+// BDIM-2 (src/Flow.jl:179) fused with scale_u! (src/Flow.jl:211-214):
+//   X = μddn(I,μ₁,f) + V + μ₀ f ;  predictor: u = X (u was scaled by 0) ; corrector: u = (u + X)·0.5
+template <int D>
+__global__ void __launch_bounds__(512) k_bdim2(Grid g, Box box, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ V,
+                                               const float* __restrict__ mu0, const float* __restrict__ mu1, int corrector) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    const float* fi = f + (i64)i * g.sc;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; j++) s += mu1[o + g.sc * (i + D * j)] * (fi[o + g.s[j]] - fi[o - g.s[j]]);
+    const i64 oc = o + (i64)i * g.sc;
+    const float X = s / 2.f + V[oc] + mu0[oc] * fi[o];
+    u[oc] = corrector ? (u[oc] + X) * 0.5f : X;
+  }
+}
+
+// BC!(a,U,saveexit,perdir) for a constant U (src/core.jl:200-219) in ONE launch.  The reference fills planes
+// sequentially for i, for j; the final value of any ghost cell is found by resolving dimensions from the last to
+// the first: periodic → opposite interior, normal → U, tangential → inward neighbour.
+// blockIdx.z selects the plane: (j, lower ghost | upper ghost | first interior).
+template <int D>
+__global__ void k_bc_vec(Grid g, float* a, const float* keep, float U0, float U1, float U2, int saveexit) {
+  const int plane = blockIdx.z;
+  const int j = plane / 3, which = plane % 3;
+  if (which == 2 && g.per[j]) return;
+  // plane coordinates: the two (or one) dims other than j
+  int I[3] = {0, 0, 0};
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t1 = blockIdx.y * blockDim.y + threadIdx.y;
+  int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
+  if (D == 2) {
+    if (t1 > 0) return;
+    if (t0 >= g.N[da]) return;
+    I[da] = t0;
+  } else {
+    if (t0 >= g.N[da] || t1 >= g.N[db]) return;
+    I[da] = t0;
+    I[db] = t1;
+  }
+  I[j] = which == 0 ? 0 : (which == 1 ? g.N[j] - 1 : 1);
+  const i64 o = cell_off(g, I);
+  const float U[3] = {U0, U1, U2};
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    if (which == 2 && i != j) continue;
+    int S[3] = {I[0], I[1], I[2]};
+    bool isconst = false;
+#pragma unroll
+    for (int d = D - 1; d >= 0; d--) {
+      if (g.per[d]) {
+        if (S[d] == 0) S[d] = g.N[d] - 2;
+        else if (S[d] == g.N[d] - 1) S[d] = 1;
+      } else if (d == i) {
+        if (S[d] <= 1 || (S[d] == g.N[d] - 1 && !(saveexit && i == 0))) {
+          isconst = true;
+          break;
+        }
+      } else {
+        if (S[d] == 0) S[d] = 1;
+        else if (S[d] == g.N[d] - 1) S[d] = g.N[d] - 2;
+      }
+    }
+    float* ai = a + (i64)i * g.sc;
+    if (isconst) {
+      ai[o] = U[i];
+    } else {
+      // a source left on the exit plane (saveexit) holds the value from before this step: read it from `keep`
+      const i64 so = cell_off(g, S);
+      const bool kept = saveexit && i == 0 && !g.per[0] && S[0] == g.N[0] - 1;
+      if (so != o) ai[o] = kept ? keep[so] : ai[so];
+    }
+  }
+}
+
+// perBC!(a,perdir) for a scalar (src/core.jl:239-243) in one launch, same plane scheme.
+template <int D>
+__global__ void k_perbc(Grid g, float* __restrict__ a) {
+  const int plane = blockIdx.z;
+  const int j = plane / 2, which = plane % 2;
+  if (!g.per[j]) return;
+  int I[3] = {0, 0, 0};
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t1 = blockIdx.y * blockDim.y + threadIdx.y;
+  int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
+  if (D == 2) {
+    if (t1 > 0 || t0 >= g.N[da]) return;
+    I[da] = t0;
+  } else {
+    if (t0 >= g.N[da] || t1 >= g.N[db]) return;
+    I[da] = t0;
+    I[db] = t1;
+  }
+  I[j] = which == 0 ? 0 : g.N[j] - 1;
+  int S[3] = {I[0], I[1], I[2]};
+#pragma unroll
+  for (int d = 0; d < D; d++)
+    if (g.per[d]) {
+      if (S[d] == 0) S[d] = g.N[d] - 2;
+      else if (S[d] == g.N[d] - 1) S[d] = 1;
+    }
+  a[cell_off(g, I)] = a[cell_off(g, S)];
+}
+
+// exitBC!(u,u⁰,Δt) (src/core.jl:226-233) as three plane kernels with deterministic in-kernel means.
+//  stage 0: partial sums of u[1,·,·,0]                     → out[slot]   (inflow mass flux U·len)
+//  stage 1: u[N-1] = u⁰[N-1] − U·Δt·(u⁰[N-1] − u⁰[N-2]); partial sums of the new plane → out[slot+1]
+//  stage 2: u[N-1] −= (mean − U)
+template <int D>
+__global__ void __launch_bounds__(256) k_exitbc(Grid g, float* __restrict__ u, const float* __restrict__ u0, const float* __restrict__ dtp,
+                                                float dt_scale, RedBuf R, int slot, int stage) {
+  int J[3] = {0, 0, 0};
+  J[1] = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  J[2] = (D == 3) ? 1 + blockIdx.y * blockDim.y + threadIdx.y : 0;
+  const bool ok = J[1] <= g.N[1] - 2 && (D == 2 || J[2] <= g.N[2] - 2);
+  const float len = (D == 3) ? (float)((i64)(g.N[1] - 2) * (g.N[2] - 2)) : (float)(g.N[1] - 2);
+  double v[1] = {0.0}, fin[1];
+  if (stage == 0) {
+    J[0] = 1;
+    if (ok) v[0] = (double)u[cell_off(g, J)];
+    grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+  } else if (stage == 1) {
+    const float Um = (float)R.out[slot] / len;
+    const float dt = (*dtp) * dt_scale;
+    J[0] = g.N[0] - 1;
+    if (ok) {
+      const i64 o = cell_off(g, J);
+      const float nv = u0[o] - Um * dt * (u0[o] - u0[o - 1]);
+      u[o] = nv;
+      v[0] = (double)nv;
+    }
+    grid_reduce<RED_SUM, 1>(v, R, slot + 1, fin);
+  } else {
+    const float Um = (float)R.out[slot] / len;
+    const float flux = (float)R.out[slot + 1] / len - Um;
+    J[0] = g.N[0] - 1;
+    if (ok) u[cell_off(g, J)] -= flux;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Poisson operator pieces (src/Poisson.jl)
+// ------------------------------------------------------------------------------------
+struct Lvl {
+  Grid g;
+  const float* L;  // D components (level 1: flow.μ₀)
+  float* Dg;
+  float* iD;
+  float* x;
+  float* eps;
+  float* r;
+  float* r2;  // ping-pong partner of r for Jacobi
+  float* z;
+};
+
+// mult(I,L,D,x) (src/Poisson.jl:70-76)
+template <int D>
+__device__ __forceinline__ float mult_at(const Grid& g, const float* __restrict__ x, const float* __restrict__ L, const float* __restrict__ Dg, i64 o,
+                                         const i64 lo[3], const i64 hi[3]) {
+  float s = x[o] * Dg[o];
+#pragma unroll
+  for (int d = 0; d < D; d++) s += x[o + lo[d]] * L[o + g.sc * d] + x[o + hi[d]] * L[o + g.sc * d + g.s[d]];
+  return s;
+}
+
+// set_diag!(D,iD,L) (src/Poisson.jl:43-55)
+template <int D>
+__global__ void k_set_diag(Grid g, Box box, const float* __restrict__ L, float* __restrict__ Dg, float* __restrict__ iD) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; d++) s -= L[o + g.sc * d] + L[o + g.sc * d + g.s[d]];
+  Dg[o] = s;
+  iD[o] = (s == 0.f) ? s : 1.f / s;
+}
+
+// restrictL!(a,b,c) interior part (src/MultiLevelPoisson.jl:42-46, :20-26, upL :9-11); BC!(a,0) follows via k_bc_vec.
+template <int D>
+__global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const int c[3] = {c0, c1, c2};
+  const i64 o = cell_off(gc, I);
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      // Julia: fine 2I-2 : 2I-1  (1-based)  ↔  0-based 2I0-1 : 2I0
+      if (j == i) {
+        lo[j] = hi[j] = c[i] ? 2 * I[j] - 1 : I[j];
+      } else {
+        lo[j] = c[j] ? 2 * I[j] - 1 : I[j];
+        hi[j] = c[j] ? 2 * I[j] : I[j];
+      }
+    }
+    float s = 0.f;
+    for (int k = lo[2]; k <= hi[2]; k++)
+      for (int jj = lo[1]; jj <= hi[1]; jj++)
+        for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)ii + gf.s[1] * jj + gf.s[2] * k + gf.sc * i];
+    a[o + gc.sc * i] = c[i] ? s / 2.f : s;
+  }
+}
+
+// @inside z = div(I,u) (src/Flow.jl:225, :13-19) fused with x .*= dt and residual!(p) part 1 (src/Poisson.jl:93-95):
+//   z = Σ_i (u[I+δ_i,i] − u[I,i]);  x = p·dt;  r = iD==0 ? 0 : z − A x;  Σr → out[slot]
+// with_div=0 skips the divergence and the scaling (standalone residual! on x, z).
+template <int D>
+__global__ void __launch_bounds__(512) k_div_residual(Lvl l, Box box, const float* __restrict__ u, const float* __restrict__ p,
+                                                      const float* __restrict__ dtp, float w, int with_div, RedBuf R, int slot) {
+  const Grid& g = l.g;
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[1] = {0.0}, fin[1];
+  if (ok) {
+    const i64 o = cell_off(g, I);
+    i64 lo[3], hi[3];
+    nbr_offsets<D>(g, I, lo, hi);
+    float z, xs, Ax;
+    if (with_div) {
+      const float dt = w * (*dtp);
+      z = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; d++) z += u[o + g.sc * d + g.s[d]] - u[o + g.sc * d];
+      l.z[o] = z;
+      xs = p[o] * dt;
+      Ax = xs * l.Dg[o];
+#pragma unroll
+      for (int d = 0; d < D; d++) Ax += (p[o + lo[d]] * dt) * l.L[o + g.sc * d] + (p[o + hi[d]] * dt) * l.L[o + g.sc * d + g.s[d]];
+      l.x[o] = xs;
+    } else {
+      z = l.z[o];
+      Ax = mult_at<D>(g, l.x, l.L, l.Dg, o, lo, hi);
+    }
+    const float r = (l.iD[o] == 0.f) ? 0.f : z - Ax;
+    l.r[o] = r;
+    v[0] = (double)r;
+  }
+  grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+}
+
+// residual! part 2 (src/Poisson.jl:95-97) fused with L₂(p) (src/Poisson.jl:189):
+//   s = Σr/|inside|;  |s| > 2eps ? r -= s ;  Σ r² → out[slot_out]
+template <int D>
+__global__ void __launch_bounds__(512) k_resid_fix(Lvl l, Box box, float count, RedBuf R, int slot_in, int slot_out) {
+  const Grid& g = l.g;
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  const float s = (float)R.out[slot_in] / count;
+  double v[1] = {0.0}, fin[1];
+  if (ok) {
+    const i64 o = cell_off(g, I);
+    float r = l.r[o];
+    if (fabsf(s) > 2.f * 1.1920929e-7f) {
+      r = r - s;
+      l.r[o] = r;
+    }
+    v[0] = (double)r * (double)r;
+  }
+  grid_reduce<RED_SUM, 1>(v, R, slot_out, fin);
+}
+
+// Jacobi!(p) with ω=1 (src/Poisson.jl:111-114 + increment! :100-104) without materialising ϵ:
+//   ϵ = r·iD (neighbours recomputed on the fly, periodic wrap = perBC!(ϵ));  r' = r − Aϵ;  x (+)= ϵ
+// r' goes to the ping-pong buffer r2 because neighbours still need the old r.
+template <int D>
+__global__ void __launch_bounds__(512) k_jacobi(Lvl l, Box box, int x_is_zero) {
+  const Grid& g = l.g;
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  i64 lo[3], hi[3];
+  nbr_offsets<D>(g, I, lo, hi);
+  const float e = l.r[o] * l.iD[o];
+  float s = e * l.Dg[o];
+#pragma unroll
+  for (int d = 0; d < D; d++)
+    s += (l.r[o + lo[d]] * l.iD[o + lo[d]]) * l.L[o + g.sc * d] + (l.r[o + hi[d]] * l.iD[o + hi[d]]) * l.L[o + g.sc * d + g.s[d]];
+  l.r2[o] = l.r[o] - 1.f * s;
+  l.x[o] = x_is_zero ? e : l.x[o] + 1.f * e;
+}
+
+// restrict!(a,b,c) (src/MultiLevelPoisson.jl:49, :13-19): coarse r = Σ fine r over up(I,c), x fastest.
+template <int D>
+__global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const int c[3] = {c0, c1, c2};
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    lo[j] = c[j] ? 2 * I[j] - 1 : I[j];
+    hi[j] = c[j] ? 2 * I[j] : I[j];
+  }
+  float s = 0.f;
+  for (int k = lo[2]; k <= hi[2]; k++)
+    for (int jj = lo[1]; jj <= hi[1]; jj++)
+      for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)ii + gf.s[1] * jj + gf.s[2] * k];
+  a[cell_off(gc, I)] = s;
+}
+
+// GaussSeidelRB! line 1: @inside ϵ = r·iD (src/Poisson.jl:142).  perBC!(ϵ) is NOT materialised: the sweeps
+// below read r·iD of the wrapped cell across periodic faces, which is exactly the stale ghost the reference sees.
+template <int D>
+__global__ void k_gs_init(Lvl l, Box box) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(l.g, I);
+  l.eps[o] = l.r[o] * l.iD[o];
+}
+
+// One red/black half-sweep gauss_rb(ϵ,r,L,iD,k₀,·) (src/Poisson.jl:116-132,145).  Thread t along x handles the cell
+// x = 1 + 2t + shift of the sweep's colour: Σ(1-based idx) ≡ 1+k₀ (mod 2).  The reference's half_rangek only reaches
+// last-dim indices k with Iv=(k+1+p)/2 ≤ N_d÷2 (matters for odd N_d).
+template <int D>
+__global__ void __launch_bounds__(512) k_gs_sweep(Lvl l, Box box, int k0) {
+  const Grid& g = l.g;
+  int I[3];
+  I[1] = box.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  I[2] = (D == 3) ? box.lo[2] + blockIdx.z * blockDim.z + threadIdx.z : 0;
+  if (I[1] >= box.lo[1] + box.n[1]) return;
+  if (D == 3 && I[2] >= box.lo[2] + box.n[2]) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // 1-based index sum parity must equal (1+k0)&1 :  (Σ0 + D) & 1 == (1+k0) & 1
+  const int rest = I[1] + I[2] + D + 1 + k0;  // x0 must make (x0 + rest) even
+  I[0] = 1 + 2 * t + ((1 + rest) & 1);
+  if (I[0] > g.N[0] - 2) return;
+  {  // half_rangek reach in the last dimension
+    const int d = D - 1;
+    const int k1 = I[d] + 1;  // 1-based
+    int front = 0;
+#pragma unroll
+    for (int q = 0; q < D - 1; q++) front += I[q] + 1;
+    const int pp = (front + k0) & 1;
+    const int Iv = (k1 + 1 + pp) / 2;
+    if (Iv > g.N[d] / 2) return;
+  }
+  const i64 o = cell_off(g, I);
+  float s = l.r[o];
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    float elo, ehi;
+    if (g.per[d] && I[d] == 1) {
+      const i64 w = o + (i64)(g.N[d] - 3) * g.s[d];
+      elo = l.r[w] * l.iD[w];
+    } else
+      elo = l.eps[o - g.s[d]];
+    if (g.per[d] && I[d] == g.N[d] - 2) {
+      const i64 w = o - (i64)(g.N[d] - 3) * g.s[d];
+      ehi = l.r[w] * l.iD[w];
+    } else
+      ehi = l.eps[o + g.s[d]];
+    s -= elo * l.L[o + g.sc * d] + ehi * l.L[o + g.sc * d + g.s[d]];
+  }
+  l.eps[o] = s * l.iD[o];
+}
+
+// increment!(p;ω) (src/Poisson.jl:100-104): r −= ω·Aϵ; x += ω·ϵ (periodic wrap = perBC!(ϵ)), optionally fused with
+// L₂(p) = r⋅r (src/Poisson.jl:189) → out[slot].
+template <int D>
+__global__ void __launch_bounds__(512) k_increment(Lvl l, Box box, const float* __restrict__ wp, int x_is_zero, int with_l2, RedBuf R, int slot) {
+  const Grid& g = l.g;
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[1] = {0.0}, fin[1];
+  if (ok) {
+    const float w = *wp;
+    const i64 o = cell_off(g, I);
+    i64 lo[3], hi[3];
+    nbr_offsets<D>(g, I, lo, hi);
+    const float Ae = mult_at<D>(g, l.eps, l.L, l.Dg, o, lo, hi);
+    const float r = l.r[o] - w * Ae;
+    l.r[o] = r;
+    const float e = l.eps[o];
+    l.x[o] = x_is_zero ? w * e : l.x[o] + w * e;
+    v[0] = (double)r * (double)r;
+  }
+  if (with_l2) grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+}
+
+// prolongate!(fine.ϵ,coarse.x,c) + increment!(fine;ω) (src/MultiLevelPoisson.jl:50,99-100) without materialising ϵ:
+// ϵ[I] = x_c[down(I,c)], down = (I+2)÷2 (1-based) ↔ (I0+1)/2 (0-based) in coarsened dims.
+template <int D>
+__global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float* __restrict__ xc, Box box, const float* __restrict__ wp, int c0, int c1,
+                                                     int c2) {
+  const Grid& g = l.g;
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const int c[3] = {c0, c1, c2};
+  const float w = *wp;
+  const i64 o = cell_off(g, I);
+  auto ec = [&](int a, int b, int cc) -> float {
+    int J[3] = {a, b, cc};
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      if (g.per[d]) {  // perBC!(ϵ): wrap to the opposite interior cell
+        if (J[d] == 0) J[d] = g.N[d] - 2;
+        else if (J[d] == g.N[d] - 1) J[d] = 1;
+      }
+      if (c[d]) J[d] = (J[d] + 1) / 2;
+    }
+    return xc[cell_off(gc, J)];
+  };
+  const float e = ec(I[0], I[1], I[2]);
+  float s = e * l.Dg[o];
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    int A[3] = {I[0], I[1], I[2]}, B[3] = {I[0], I[1], I[2]};
+    A[d] -= 1;
+    B[d] += 1;
+    s += ec(A[0], A[1], A[2]) * l.L[o + g.sc * d] + ec(B[0], B[1], B[2]) * l.L[o + g.sc * d + g.s[d]];
+  }
+  l.r[o] = l.r[o] - w * s;
+  l.x[o] = l.x[o] + w * e;
+}
+
+// Velocity correction and pressure unscale of mom_project! (src/Flow.jl:227-230):
+//   u[I,i] −= L[I,i]·(x[I] − x[I−δ_i]);  p = x/dt   (x keeps the scaled iterate; p is the observable pressure)
+template <int D>
+__global__ void __launch_bounds__(512) k_correct(Lvl l, Box box, float* __restrict__ u, float* __restrict__ p, const float* __restrict__ dtp, float w) {
+  const Grid& g = l.g;
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  i64 lo[3], hi[3];
+  nbr_offsets<D>(g, I, lo, hi);
+  const float dt = w * (*dtp);
+  const float x = l.x[o];
+#pragma unroll
+  for (int d = 0; d < D; d++) u[o + g.sc * d] -= l.L[o + g.sc * d] * (x - l.x[o + lo[d]]);
+  p[o] = x / dt;
+}
+
+// CFL (src/Flow.jl:234-244): σ = flux_out(I,u) on the interior; maximum(σ) over ALL cells (ghost σ holds stale Φ, lower
+// ghosts 0).  The last block turns the max into Δt = min(10, 1/(max+5ν)) and stores it at dt_out.
+template <int D>
+__global__ void __launch_bounds__(512) k_cfl(Grid g, Box box, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
+                                             RedBuf R, int slot) {
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[1] = {0.0}, fin[1];  // lower ghosts hold 0, so the max is at least 0
+  if (ok) {
+    const i64 o = cell_off(g, I);
+    bool interior = true;
+#pragma unroll
+    for (int d = 0; d < D; d++) interior = interior && I[d] >= 1 && I[d] <= g.N[d] - 2;
+    float s;
+    if (interior) {
+      s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; d++) s += fmaxf(0.f, u[o + g.sc * d + g.s[d]]) + fmaxf(0.f, -u[o + g.sc * d]);
+      sigma[o] = s;
+    } else
+      s = sigma[o];
+    v[0] = (double)s;
+  }
+  if (grid_reduce<RED_MAX, 1>(v, R, slot, fin)) {
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+      const float m = (float)fin[0];
+      *dt_out = fminf(10.f, 1.f / (m + 5.f * nu));
+    }
+  }
+}
+
+// mult!(p,x) (src/Poisson.jl:63-69): z = A x on the interior (ghosts zeroed by the caller).
+template <int D>
+__global__ void k_mult(Lvl l, Box box, const float* __restrict__ x, float* __restrict__ z) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(l.g, I);
+  i64 lo[3], hi[3];
+  nbr_offsets<D>(l.g, I, lo, hi);
+  z[o] = mult_at<D>(l.g, x, l.L, l.Dg, o, lo, hi);
+}
+
+// ---- pcg! pieces (src/Poisson.jl:166-186) -------------------------------------------------
+// stage 0: z = ϵ = r·iD ; ρ = r⋅z                       (:168-169)
+// stage 1: z = Aϵ ; σ = z⋅ϵ                              (:173-174)
+// stage 2: x += αϵ ; r −= αz                            (:176-177)   α = sc[0]
+// stage 3: z = r·iD ; ρ₂ = r⋅z                          (:179-180)
+// stage 4: ϵ = βϵ + z                                    (:183)       β = sc[1]
+template <int D>
+__global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, const float* __restrict__ sc, RedBuf R, int slot) {
+  const Grid& g = l.g;
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[1] = {0.0}, fin[1];
+  if (ok) {
+    const i64 o = cell_off(g, I);
+    if (stage == 0) {
+      const float z = l.r[o] * l.iD[o];
+      l.z[o] = z;
+      l.eps[o] = z;
+      v[0] = (double)l.r[o] * (double)z;
+    } else if (stage == 1) {
+      i64 lo[3], hi[3];
+      nbr_offsets<D>(g, I, lo, hi);
+      const float z = mult_at<D>(g, l.eps, l.L, l.Dg, o, lo, hi);
+      l.z[o] = z;
+      v[0] = (double)z * (double)l.eps[o];
+    } else if (stage == 2) {
+      const float a = sc[0];
+      l.x[o] += a * l.eps[o];
+      l.r[o] -= a * l.z[o];
+    } else if (stage == 3) {
+      const float z = l.r[o] * l.iD[o];
+      l.z[o] = z;
+      v[0] = (double)l.r[o] * (double)z;
+    } else {
+      l.eps[o] = sc[1] * l.eps[o] + l.z[o];
+    }
+  }
+  if (stage == 0 || stage == 1 || stage == 3) grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+}
+
+// L₂(p) = r⋅r and L∞(p) = maximum(abs,r) (src/Poisson.jl:189-190) as a standalone reduction.
+template <int D>
+__global__ void __launch_bounds__(512) k_norms(Lvl l, Box box, RedBuf R, int slot, int want_max) {
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[1] = {0.0}, fin[1];
+  if (ok) {
+    const float r = l.r[cell_off(l.g, I)];
+    v[0] = want_max ? (double)fabsf(r) : (double)r * (double)r;
+  }
+  if (want_max)
+    grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+  else
+    grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+}
+
+// generic helpers
+__global__ void k_fill(float* __restrict__ a, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) a[i] = v;
+}
+__global__ void k_set_scalar(float* p, float v) { *p = v; }

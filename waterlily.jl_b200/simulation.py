@@ -1,0 +1,86 @@
+"""`Simulation`, `sim_step!`, `sim_time`, `measure!` (src/WaterLily.jl:86-149) over the B200 library."""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .body import NoBody, measure_body
+from .flow import Flow, MultiLevelPoisson, Poisson, quick
+
+F = np.float32
+
+
+class Simulation:
+    """Simulation(dims,uBC,L;U,Δt,ν,ϵ,perdir,u0,exitBC,λ,body,T,flow_ctor,pois_ctor) (src/WaterLily.jl:93-106).
+
+    `mem` is implied (the B200); `flow_ctor(dims,uBC,**kw)` and `pois_ctor(flow)` are the reference's plug-in
+    factories and default to the B200 `Flow` and `MultiLevelPoisson`."""
+
+    def __init__(self, dims, uBC, L, U=None, Δt=0.25, ν=0.0, g=None, ϵ=1, perdir=(), u0=None, exitBC=False, λ=quick,
+                 body=None, T=np.float32, flow_ctor=None, pois_ctor=None, **kw):
+        if callable(uBC) and U is None:
+            raise AssertionError("`U` (velocity scale) must be specified if boundary conditions `uBC` is a `Function`")
+        if U is None:
+            U = float(np.sqrt(sum(float(v) ** 2 for v in uBC)))
+        self.U, self.L, self.ϵ = U, L, ϵ
+        self.body = body if body is not None else NoBody()
+        pois = kw.pop("pois", "multilevel")
+        if flow_ctor is None:
+            def flow_ctor(dims, uBC, **k):
+                return Flow(dims, uBC, **k)
+        self.flow = flow_ctor(dims, uBC, u0=u0, Δt=Δt, ν=ν, g=g, λ=λ, T=T, perdir=perdir, exitBC=exitBC, pois=pois, **kw)
+        if pois_ctor is None:
+            def pois_ctor(flow):
+                return MultiLevelPoisson(flow) if pois == "multilevel" else Poisson(flow)
+        self.pois = pois_ctor(self.flow)
+        measure(self)
+
+    def close(self):
+        self.flow.close()
+
+
+def measure(sim, t=None):
+    """measure!(sim) (src/WaterLily.jl:146-149): measure!(flow,body;ϵ) + update!(pois).  Static bodies only."""
+    if isinstance(sim.body, NoBody):
+        return
+    fl = sim.flow
+    mu0, mu1, V, sigma = measure_body(fl.N, sim.body, sim.ϵ)
+    fl.upload("mu0", mu0)
+    fl.upload("mu1", mu1)
+    fl.upload("V", V)
+    fl.upload("sigma", sigma)
+    _lib.check(fl.L, fl.L.wl_measure_bc(fl.h))
+    sim.pois.update()
+
+
+def sim_time(sim):
+    """sim_time(sim) = time(sim)*U/L (src/WaterLily.jl:117)"""
+    return sim.flow.time() * sim.U / sim.L
+
+
+def sim_step(sim, t_end=None, remeasure=False, max_steps=2**62, verbose=False, udf=None):
+    """sim_step!(sim,t_end;remeasure,max_steps,verbose) and sim_step!(sim;remeasure) (src/WaterLily.jl:128-139).
+    `remeasure=True` needs a body-motion closure on the host and is not supported on this path."""
+    if udf is not None:
+        raise _lib.WLError("udf is a host closure: not supported by the B200 C ABI")
+    if remeasure and not isinstance(sim.body, NoBody):
+        raise _lib.WLError("remeasure=true (moving bodies) is outside the static-body hot path; pass remeasure=False")
+    fl = sim.flow
+    if t_end is None:
+        _lib.check(fl.L, fl.L.wl_mom_step(fl.h))
+        return 1
+    if verbose:
+        k = 0
+        while sim_time(sim) < t_end and k < max_steps:
+            _lib.check(fl.L, fl.L.wl_mom_step(fl.h))
+            sim_info(sim)
+            k += 1
+        return k
+    k = C.c_int64()
+    _lib.check(fl.L, fl.L.wl_sim_step_until(fl.h, float(t_end), float(sim.U), float(sim.L), int(max_steps), C.byref(k)))
+    return k.value
+
+
+def sim_info(sim):
+    """sim_info(sim) (src/WaterLily.jl:155)"""
+    print(f"tU/L={round(sim_time(sim), 4)}, Δt={round(float(sim.flow.Δt[-1]), 3)}")
