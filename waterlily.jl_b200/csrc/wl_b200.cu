@@ -14,7 +14,7 @@
 #include <vector>
 
 #include "../../include/wl_b200.h"
-#include "wl_kernels.cuh"
+#include "wl_fast.cuh"
 
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -38,13 +38,33 @@ static int fail(const char* fmt, ...) {
     if (r_) return r_;       \
   } while (0)
 
-enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4, SLOT_RHO = 5, SLOT_SIG = 6, SLOT_LINF = 7, NSLOTS = 16 };
+enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4, SLOT_RHO = 5, SLOT_SIG = 6, SLOT_LINF = 7, SLOT_UNI = 8, SLOT_PHIMAX = 9, SLOT_CFLINT = 10, NSLOTS = 16 };
 
 struct Level {
   Grid g;
   float *L = nullptr, *Dg = nullptr, *iD = nullptr, *x = nullptr, *eps = nullptr, *r = nullptr, *r2 = nullptr, *z = nullptr;
   int c[3] = {0, 0, 0};  // coarsening mask from the previous (finer) level
   bool ownL = false, ownz = false;
+  bool fast = false;     // march kernels apply (3-D, interior x size a multiple of 4)
+  bool fullc = false;    // built from the finer level by coarsening all three directions
+  float Lc[3] = {1.f, 1.f, 1.f};  // uniform face coefficients (valid when the handle is in uniform mode)
+  Coef coef(bool uni) const {
+    Coef k;
+    k.L = L;
+    k.Dg = Dg;
+    k.iD = iD;
+    float s = 0.f;
+    for (int d = 0; d < 3; d++) {
+      k.Lc[d] = Lc[d];
+      if (d < g.D) s -= Lc[d] + Lc[d];
+    }
+    k.Dc = s;
+    k.iDc = (s == 0.f) ? s : 1.f / s;
+    (void)uni;
+    return k;
+  }
+  int zchunk() const { return std::max(2, std::min(16, (g.N[2] - 2 + 1) / 2 * 2)); }
+  dim3 fgrid() const { return dim3(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, FTY), cdiv(g.N[2] - 2, zchunk())); }
   Lvl dev() const {
     Lvl l;
     l.g = g;
@@ -102,6 +122,7 @@ struct wl_handle {
   std::vector<int16_t> iters;
   std::vector<float> log;  // rows of (iter, rinf, r2, omega)
   bool logging = false;
+  bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   cudaStream_t st = nullptr;
   int64_t launches = 0;
   double tol;
@@ -131,7 +152,8 @@ static Grid make_grid(int D, const int* N, const int* per) {
     g.N[d] = d < D ? N[d] : 1;
     g.per[d] = d < D ? (per[d] != 0) : 0;
   }
-  g.px = ((g.N[0] + 31) / 32) * 32;
+  g.xo = 31;
+  g.px = ((g.N[0] + g.xo + 3 + 31) / 32) * 32;
   g.s[0] = 1;
   g.s[1] = g.px;
   g.s[2] = (i64)g.px * g.N[1];
@@ -229,6 +251,15 @@ static int build_levels(wl_handle* h) {
       if (!any) break;
       lc.g = make_grid(gf.D, N, gf.per);
       lc.ownL = lc.ownz = true;
+      lc.fullc = gf.D == 3 && lc.c[0] && lc.c[1] && lc.c[2];
+      const Level& fl = h->levels.back();
+      for (int d = 0; d < gf.D; d++) {  // restrictL of a uniform field: Σ over the transverse fine faces, /2 if the normal is coarsened
+        float v = fl.Lc[d];
+        for (int j = 0; j < gf.D; j++)
+          if (j != d && lc.c[j]) v *= 2.f;
+        if (lc.c[d]) v /= 2.f;
+        lc.Lc[d] = v;
+      }
       h->levels.push_back(lc);
     }
     if (h->levels.size() <= 2) return fail("MultiLevelPoisson requires size=a2^n, where n>2");
@@ -236,6 +267,7 @@ static int build_levels(wl_handle* h) {
   for (size_t i = 0; i < h->levels.size(); i++) {
     Level& l = h->levels[i];
     const size_t n = l.cells();
+    l.fast = l.g.D == 3 && (l.g.N[0] - 2) % 4 == 0 && l.g.N[2] > 3;
     if (l.ownL) TRY(dalloc(h, &l.L, n * l.g.D));
     if (l.ownz) TRY(dalloc(h, &l.z, n));
     TRY(dalloc(h, &l.Dg, n));
@@ -260,6 +292,15 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
     }
     LAUNCH_D(h, k_set_diag, grd(l.inside(), b), b, l.g, l.inside(), (const float*)l.L, l.Dg, l.iD);
   }
+  // uniform-coefficient specialisation: legal iff no body (μ₀≡1, μ₁≡0, V≡0) and every direction periodic
+  h->uni = false;
+  const Grid& g = h->g;
+  if (h->D == 3 && g.per[0] && g.per[1] && g.per[2] && !(h->cfg.flags & WL_FLAG_GENERAL_COEFF)) {
+    LAUNCH(h, k_check_uniform, dim3(592, 1, 1), dim3(256, 1, 1), (const float*)h->mu0, (const float*)h->mu1, (const float*)h->V, g, h->red, SLOT_UNI);
+    CK(cudaMemcpyAsync(h->h_out + SLOT_UNI, h->red.out + SLOT_UNI, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->uni = (h->h_out[SLOT_UNI] == 0.0);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -283,14 +324,35 @@ static void gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, in
   Box half = in;
   half.n[0] = (in.n[0] + 1) / 2;
   for (int k0 = 1; k0 <= 4; k0++) LAUNCH_D(h, k_gs_sweep, grd(half, b), b, d, in, k0);
-  LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, h->red, SLOT_R2);
+  if (l.fast) {
+    ProlongSrc ps{nullptr, l.g};
+    if (h->uni)
+      LAUNCH(h, (f_increment<true, false>), l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
+             h->red, SLOT_R2);
+    else
+      LAUNCH(h, (f_increment<false, false>), l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(),
+             with_l2, h->red, SLOT_R2);
+  } else
+    LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, h->red, SLOT_R2);
 }
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
-static void jacobi(wl_handle* h, Level& l, int x_is_zero) {
+// With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; returns true if it was.
+static bool jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse = nullptr) {
   dim3 b = blk(h->D);
   Box in = l.inside();
-  LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
+  bool fused = false;
+  if (l.fast) {
+    fused = coarse && coarse->fullc && l.zchunk() % 2 == 0 && (l.g.N[1] - 2) % 2 == 0 && (l.g.N[2] - 2) % 2 == 0;
+    const Grid& gc = fused ? coarse->g : l.g;
+    float* rc = fused ? coarse->r : nullptr;
+    if (h->uni)
+      LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0);
+    else
+      LAUNCH(h, f_jacobi<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0);
+  } else
+    LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
   std::swap(l.r, l.r2);
+  return fused;
 }
 // pcg!(p;it=6)  src/Poisson.jl:166-186 — host-driven (three dots per iteration decide early exits)
 static int pcg(wl_handle* h, Level& l, int it = 6) {
@@ -351,14 +413,23 @@ static int vcycle(wl_handle* h, size_t li, const float* wp) {
   Level& fine = h->levels[li];
   Level& coarse = h->levels[li + 1];
   dim3 b = blk(h->D);
-  jacobi(h, fine, li > 0);
   Box cin = coarse.inside();
-  LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
+  if (!jacobi(h, fine, li > 0, &coarse))
+    LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
   const bool last = (li + 2 >= h->levels.size());
   if (!last) TRY(vcycle(h, li + 1, wp));
   TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
   Box fin = fine.inside();
-  LAUNCH_D(h, k_prolong_inc, grd(fin, b), b, fine.dev(), coarse.g, (const float*)coarse.x, fin, wp, coarse.c[0], coarse.c[1], coarse.c[2]);
+  if (fine.fast && coarse.fullc) {
+    ProlongSrc ps{coarse.x, coarse.g};
+    if (h->uni)
+      LAUNCH(h, (f_increment<true, true>), fine.fgrid(), dim3(32, FTY), fine.g, fine.coef(true), (const float*)nullptr, ps, fine.r, fine.x, wp, 0,
+             fine.zchunk(), 0, h->red, SLOT_R2);
+    else
+      LAUNCH(h, (f_increment<false, true>), fine.fgrid(), dim3(32, FTY), fine.g, fine.coef(false), (const float*)nullptr, ps, fine.r, fine.x, wp, 0,
+             fine.zchunk(), 0, h->red, SLOT_R2);
+  } else
+    LAUNCH_D(h, k_prolong_inc, grd(fin, b), b, fine.dev(), coarse.g, (const float*)coarse.x, fin, wp, coarse.c[0], coarse.c[1], coarse.c[2]);
   return 0;
 }
 
@@ -374,10 +445,20 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
   Level& l = h->levels[0];
   dim3 b = blk(h->D);
   Box in = l.inside();
-  LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
   float count = 1;
   for (int d = 0; d < h->D; d++) count *= (float)(l.g.N[d] - 2);
-  LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
+  if (l.fast && with_div) {
+    if (h->uni)
+      LAUNCH(h, f_div_residual<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
+             l.zchunk(), h->red, SLOT_RSUM);
+    else
+      LAUNCH(h, f_div_residual<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
+             l.zchunk(), h->red, SLOT_RSUM);
+    LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), h->red, SLOT_RSUM, SLOT_R2);
+  } else {
+    LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
+    LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
+  }
   double v;
   TRY(read_slot(h, SLOT_R2, &v));
   *r2 = (float)v;
@@ -449,6 +530,78 @@ static void conv_bdim1(wl_handle* h, const float* ua, int mode) {
     conv_launch<2>(h, ua, mode);
 }
 
+template <int LAM, bool FUSE>
+static void fconv_launch(wl_handle* h, const float* ua, float* out, int corrector) {
+  const Grid& g = h->g;
+  const int XM = FUSE ? g.N[0] - 2 : g.N[0] - 1, YM = FUSE ? g.N[1] - 2 : g.N[1] - 1, ZM = FUSE ? g.N[2] - 2 : g.N[2] - 1;
+  const int zchunk = std::min(32, ZM);
+  dim3 gr(cdiv(XM, 32), cdiv(YM, CTY), cdiv(ZM, zchunk));
+  prof_begin(h, "fm_conv");
+  if (g.per[0] && g.per[1] && g.per[2])
+    fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
+                                                                            h->red, SLOT_PHIMAX);
+  else
+    fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
+                                                                             h->red, SLOT_PHIMAX);
+  prof_end(h);
+  h->launches++;
+}
+template <bool FUSE>
+static void fconv(wl_handle* h, const float* ua, float* out, int corrector) {
+  if (h->cfg.lambda == WL_QUICK)
+    fconv_launch<0, FUSE>(h, ua, out, corrector);
+  else if (h->cfg.lambda == WL_CDS)
+    fconv_launch<1, FUSE>(h, ua, out, corrector);
+  else
+    fconv_launch<2, FUSE>(h, ua, out, corrector);
+}
+
+// Momentum update of mom_predict!/mom_correct! up to (not including) BC!: conv_diff! → BDIM! → scale_u!
+static void momentum(wl_handle* h, int corrector) {
+  const Grid& g = h->g;
+  dim3 b = blk(h->D);
+  Level& l = h->levels[0];
+  Box in = l.inside();
+  if (h->D == 3 && h->uni) {
+    // uniform mode: u_new straight from the flux kernel; the corrector must not update u in place (stencil reads), so it
+    // writes into the f buffer (unused in this mode) and the two are swapped
+    if (!corrector)
+      fconv<true>(h, h->u0, h->u, 0);
+    else {
+      fconv<true>(h, h->u, h->f, 1);
+      std::swap(h->u, h->f);
+    }
+    return;
+  }
+  if (h->D == 3) {
+    fconv<false>(h, corrector ? h->u : h->u0, h->f, corrector);
+    dim3 pb(32, 8, 1);
+    int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
+    LAUNCH(h, k_f_lowghost, dim3(cdiv(m0, 32), cdiv(m1, 8), 3), pb, g, (const float*)h->u0, (const float*)h->V, h->f, dtp(h));
+  } else
+    conv_bdim1(h, corrector ? h->u : h->u0, 1);
+  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, corrector);
+}
+
+// CFL(a) → *dt_out on the device
+static void cfl(wl_handle* h, float* dt_out) {
+  Level& l = h->levels[0];
+  const Grid& g = h->g;
+  if (l.fast) {
+    if (h->uni) {
+      LAUNCH(h, f_cfl<true>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, SLOT_PHIMAX);
+    } else {
+      int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
+      LAUNCH(h, k_sigma_ghostmax, dim3(cdiv(m0, 32), cdiv(m1, 8), 6), dim3(32, 8, 1), g, (const float*)h->sigma, h->red, SLOT_CFL);
+      LAUNCH(h, f_cfl<false>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, SLOT_CFL);
+    }
+    return;
+  }
+  dim3 b = blk(h->D);
+  Box all = l.all();
+  LAUNCH_D(h, k_cfl, grd(all, b), b, g, all, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, h->red, SLOT_CFL);
+}
+
 // mom_project!(a,b,w,t)  src/Flow.jl:223-232
 static int project(wl_handle* h, float w) {
   float r2;
@@ -457,7 +610,13 @@ static int project(wl_handle* h, float w) {
   Level& l = h->levels[0];
   dim3 b = blk(h->D);
   Box in = l.inside();
-  LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
+  if (l.fast) {
+    if (h->uni)
+      LAUNCH(h, f_correct<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, h->u, h->p, dtp(h), w, l.zchunk());
+    else
+      LAUNCH(h, f_correct<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.x, h->u, h->p, dtp(h), w, l.zchunk());
+  } else
+    LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
   launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
   return 0;
 }
@@ -495,18 +654,16 @@ static int mom_step(wl_handle* h) {
   Box in = l.inside(), all = l.all();
   std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
   // predictor  src/Flow.jl:190-196
-  conv_bdim1(h, h->u0, 1);
-  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, 0);
+  momentum(h, 0);
   launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u0);
   if (h->cfg.exitBC) launch_exitbc(h, h->u, h->u0, 1.f);
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
-  conv_bdim1(h, h->u, 1);
-  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, 1);
+  momentum(h, 1);
   launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
   TRY(project(h, 0.5f));
   // push!(a.Δt, CFL(a))
-  LAUNCH_D(h, k_cfl, grd(all, b), b, g, all, (const float*)h->u, h->sigma, h->cfg.nu, h->d_dthist + h->dt_dev_len, h->red, SLOT_CFL);
+  cfl(h, h->d_dthist + h->dt_dev_len);
   h->dt_dev_len++;
   CK(cudaGetLastError());
   return 0;
@@ -529,14 +686,14 @@ static int field_ptr(wl_handle* h, int field, float** p, int* ncomp) {
 }
 static int copy_in(wl_handle* h, const Grid& g, float* dst, const float* src, int ncomp, int src_is_device) {
   const size_t rows = (size_t)g.N[1] * g.N[2] * ncomp;
-  CK(cudaMemcpy2DAsync(dst, (size_t)g.px * 4, src, (size_t)g.N[0] * 4, (size_t)g.N[0] * 4, rows,
+  CK(cudaMemcpy2DAsync(dst + g.xo, (size_t)g.px * 4, src, (size_t)g.N[0] * 4, (size_t)g.N[0] * 4, rows,
                        src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
   if (!src_is_device) CK(cudaStreamSynchronize(h->st));
   return 0;
 }
 static int copy_out(wl_handle* h, const Grid& g, float* dst, const float* src, int ncomp, int dst_is_device) {
   const size_t rows = (size_t)g.N[1] * g.N[2] * ncomp;
-  CK(cudaMemcpy2DAsync(dst, (size_t)g.N[0] * 4, src, (size_t)g.px * 4, (size_t)g.N[0] * 4, rows,
+  CK(cudaMemcpy2DAsync(dst, (size_t)g.N[0] * 4, src + g.xo, (size_t)g.px * 4, (size_t)g.N[0] * 4, rows,
                        dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
   if (!dst_is_device) CK(cudaStreamSynchronize(h->st));
   return 0;
@@ -586,13 +743,13 @@ int wl_create(const wl_config* cfg, wl_handle** out) {
     if ((rc = build_levels(h))) break;
     // reduction buffers
     Box all = h->levels[0].all();
-    const size_t nb = std::max(nblocks(all, blk(D)), (size_t)1024);
+    const size_t nb = std::max(nblocks(all, blk(D)), (size_t)1024) + 4096;
     void* q;
     if (cudaMalloc(&q, nb * 2 * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc partials"); break; }
     h->red.partials = (double*)q;
     h->allocs.push_back(q);
-    if (cudaMalloc(&q, 256) != cudaSuccess) { rc = fail("cudaMalloc ticket"); break; }
-    cudaMemsetAsync(q, 0, 256, h->st);
+    if (cudaMalloc(&q, 8192) != cudaSuccess) { rc = fail("cudaMalloc ticket"); break; }
+    cudaMemsetAsync(q, 0, 8192, h->st);
     h->red.ticket = (unsigned int*)q;
     h->allocs.push_back(q);
     if (cudaMalloc(&q, NSLOTS * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc out"); break; }
@@ -740,9 +897,7 @@ int wl_conv_diff(wl_handle* h, int from_u0) {
 int wl_cfl(wl_handle* h, float* dt_out) {
   if (!h || !dt_out) return fail("null argument");
   CK(cudaSetDevice(h->cfg.device));
-  dim3 b = blk(h->D);
-  Box all = h->levels[0].all();
-  LAUNCH_D(h, k_cfl, grd(all, b), b, h->g, all, (const float*)h->u, h->sigma, h->cfg.nu, h->d_scal + 4, h->red, SLOT_CFL);
+  cfl(h, h->d_scal + 4);
   CK(cudaMemcpyAsync(dt_out, h->d_scal + 4, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   return 0;
@@ -803,7 +958,7 @@ int wl_pois_smooth(wl_handle* h, int level, int kind, float omega) {
   if (kind == 0)
     gs_smooth(h, l, h->d_scal + 0, 0, 0);
   else if (kind == 1)
-    jacobi(h, l, 0);  // reference Jacobi!(p) default ω=1
+    jacobi(h, l, 0, nullptr);  // reference Jacobi!(p) default ω=1
   else
     TRY(pcg(h, l));
   CK(cudaGetLastError());
@@ -948,6 +1103,7 @@ int wl_get_timings(wl_handle* h, char* buf, int* len) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
     std::string nm(r.name);
+    if (!nm.empty() && nm[0] == '(') nm = nm.substr(1);
     const size_t lt = nm.find('<');
     if (lt != std::string::npos) nm = nm.substr(0, lt);
     size_t k = 0;
@@ -983,7 +1139,7 @@ int wl_get_timings(wl_handle* h, char* buf, int* len) {
 
 int wl_is_const_coeff(wl_handle* h, int* flag) {
   if (!h || !flag) return fail("null argument");
-  *flag = 0;
+  *flag = h->uni ? 1 : 0;
   return 0;
 }
 

@@ -2,9 +2,12 @@
 // grid reduction shared by every kernel of libwl_b200.
 //
 // Internal field layout (library-owned): 0-based cell (i,j,k) of a
-// ghost-padded N0×N1×N2 scalar lives at  i + px*(j + N1*k)  with the x-pitch `px`
-// rounded up to 32 floats so every row starts on a 128-byte line; vector component c
-// adds c*sc.  2-D fields have N2 = 1.  All linear offsets are 64-bit (1026³ > 2³¹).
+// ghost-padded N0×N1×N2 scalar lives at  xo + i + px*(j + N1*k).  xo = 31 puts the first
+// INTERIOR cell (i=1) of every row on a 128-byte line (allocations are 256-byte aligned and
+// the x-pitch px is a multiple of 32 floats), so warps that own 4 interior cells per lane
+// issue perfectly aligned 16-byte vector loads; px leaves room for one vector past the
+// upper ghost.  Vector component c adds c*sc.  2-D fields have N2 = 1.  All linear offsets
+// are 64-bit (1026³ > 2³¹).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -15,6 +18,7 @@ struct Grid {
   int D;
   int N[3];    // cells incl. ghosts (N[2]==1 in 2-D)
   int px;      // x pitch in floats
+  int xo;      // storage offset of cell i=0 inside a row
   i64 s[3];    // strides in floats: {1, px, px*N1}
   i64 sc;      // component stride = px*N1*N2
   int per[3];  // periodic flags
@@ -37,7 +41,7 @@ __device__ __forceinline__ bool thread_cell(const Box& b, int I[3]) {
   return ok;
 }
 
-__device__ __forceinline__ i64 cell_off(const Grid& g, const int I[3]) { return (i64)I[0] + g.s[1] * I[1] + g.s[2] * I[2]; }
+__device__ __forceinline__ i64 cell_off(const Grid& g, const int I[3]) { return (i64)(g.xo + I[0]) + g.s[1] * I[1] + g.s[2] * I[2]; }
 
 // Offsets to the lower / upper neighbour of an INTERIOR cell in dimension d for the scalar
 // Poisson fields.  Periodic dimensions wrap to the opposite interior cell, which is what
@@ -57,8 +61,8 @@ __device__ __forceinline__ void nbr_offsets(const Grid& g, const int I[3], i64 l
 // order and stores the results to out[slot0 .. slot0+NV).  Bit-reproducible for a fixed
 // launch geometry; no host round trip.
 struct RedBuf {
-  double* partials;      // capacity >= NV * (number of blocks)
-  unsigned int* ticket;  // zero between launches
+  double* partials;      // capacity >= NV * (number of blocks + gridDim.z)
+  unsigned int* ticket;  // [0] = top ticket, [1+z] = per-layer tickets; all zero between launches
   double* out;           // result slots
 };
 
@@ -82,15 +86,21 @@ __device__ __forceinline__ double warp_reduce(double v) {
 
 // Returns true in every thread of the block that performed the final fold (the last block),
 // after out[] has been written; `fin` then holds the folded values in thread 0.
+// Two levels keep the serial tail short on big grids: the last block of every blockIdx.z
+// layer folds that layer's partials, the last layer folds the layer results.
 template <int OP, int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], const RedBuf& R, int slot0, double (&fin)[NV]) {
   __shared__ double sm[NV][32];
-  __shared__ bool last;
+  __shared__ int last;
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   const int nthreads = blockDim.x * blockDim.y * blockDim.z;
   const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
-  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const unsigned int nlayer = gridDim.x * gridDim.y;  // blocks per layer
+  const unsigned int nz = gridDim.z;
+  const unsigned int bid = blockIdx.x + gridDim.x * blockIdx.y;
+  double* lay = R.partials;                               // [NV][nz][nlayer]
+  double* top = R.partials + (size_t)NV * nz * nlayer;    // [NV][nz]
+  unsigned int* tick_layer = R.ticket + 1 + blockIdx.z;   // one ticket per layer
 #pragma unroll
   for (int q = 0; q < NV; q++) {
     double w = warp_reduce<OP>(v[q]);
@@ -102,21 +112,48 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], const RedBuf& R, in
     for (int q = 0; q < NV; q++) {
       double w = lane < nwarps ? sm[q][lane] : red_identity<OP>();
       w = warp_reduce<OP>(w);
-      if (lane == 0) R.partials[(size_t)q * nblocks + bid] = w;
+      if (lane == 0) lay[((size_t)q * nz + blockIdx.z) * nlayer + bid] = w;
     }
     if (lane == 0) {
       __threadfence();
-      unsigned int t = atomicAdd(R.ticket, 1u);
-      last = (t == nblocks - 1);
+      last = (atomicAdd(tick_layer, 1u) == nlayer - 1) ? 1 : 0;
     }
   }
   __syncthreads();
   if (!last) return false;
+  // ---- fold this layer ----
   __threadfence();
 #pragma unroll
   for (int q = 0; q < NV; q++) {
     double w = red_identity<OP>();
-    for (unsigned int b = tid; b < nblocks; b += nthreads) w = red_op<OP>(w, __ldcg(&R.partials[(size_t)q * nblocks + b]));
+    const double* src = lay + ((size_t)q * nz + blockIdx.z) * nlayer;
+    for (unsigned int b = tid; b < nlayer; b += nthreads) w = red_op<OP>(w, __ldcg(src + b));
+    w = warp_reduce<OP>(w);
+    __syncthreads();
+    if (lane == 0) sm[q][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      double w = lane < nwarps ? sm[q][lane] : red_identity<OP>();
+      w = warp_reduce<OP>(w);
+      if (lane == 0) top[(size_t)q * nz + blockIdx.z] = w;
+    }
+    if (lane == 0) {
+      *tick_layer = 0u;
+      __threadfence();
+      last = (atomicAdd(R.ticket, 1u) == nz - 1) ? 2 : 0;
+    }
+  }
+  __syncthreads();
+  if (last != 2) return false;
+  // ---- fold the layers ----
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double w = red_identity<OP>();
+    for (unsigned int b = tid; b < nz; b += nthreads) w = red_op<OP>(w, __ldcg(top + (size_t)q * nz + b));
     w = warp_reduce<OP>(w);
     __syncthreads();
     if (lane == 0) sm[q][warp] = w;

@@ -1,0 +1,783 @@
+// wl_fast.cuh — the bandwidth-tuned 3-D kernels ("march" kernels) of the pressure path.
+//
+// Geometry: blockDim = (32, FTY).  A lane owns 4 consecutive interior x cells (one aligned 16-byte
+// vector: the layout puts interior cell i=1 on a 128-byte line), a warp owns a 128-cell row segment,
+// a block owns FTY rows and marches over a chunk of z planes keeping the z-1 / z / z+1 values of the
+// stencil field in registers.  Per plane a thread issues one vector load for the new plane and two
+// for the y neighbours (L1/L2 hits: sibling rows of the same block loaded them one step earlier);
+// x neighbours come from warp shuffles, with one scalar load at each end of the row segment.
+// Every DRAM byte of a field is therefore fetched about once per kernel.
+//
+// UNI = uniform-coefficient specialisation: no body and all directions periodic, so on every level
+// L ≡ Lc[d] on all faces, D ≡ -2ΣLc, iD ≡ 1/D and the coefficient arrays are never read
+// (SURVEY.md §8d "constant-coefficient specialisation"; legality is checked on the device by
+// k_check_uniform when the hierarchy is (re)built).  !UNI reads L, D, iD like the reference.
+//
+// All arithmetic is written in the reference's association order; results are bit-identical to the
+// general kernels in wl_kernels.cuh and to the oracle.  Requires (N0-2) % 4 == 0.
+#pragma once
+#include "wl_kernels.cuh"
+
+#define FTY 8
+#define FULLMASK 0xffffffffu
+
+struct Coef {
+  const float* L;
+  const float* Dg;
+  const float* iD;
+  float Lc[3];  // UNI: face coefficient per direction
+  float Dc, iDc;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 mul4(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 scale4(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float get4(const float4& a, int q) { return q == 0 ? a.x : (q == 1 ? a.y : (q == 2 ? a.z : a.w)); }
+
+// Per-thread marching frame
+struct Frame {
+  int lane, x0, y, z0, z1;  // cells x0..x0+3, row y, planes z0..z1-1
+  bool on;                  // this lane owns interior cells
+  bool lastgrp;             // the group ends at the last interior cell (its right neighbour is not in the next lane)
+  int xl, xr;               // x index of the left neighbour of cell x0 and of the right neighbour of cell x0+3 (periodic wrap applied)
+  int ym, yp;               // neighbouring rows (periodic wrap applied)
+  i64 row;                  // offset of (i=0, y, k=0) incl. xo
+  i64 rowm, rowp;           // same for rows ym, yp
+};
+
+__device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk) {
+  Frame f;
+  f.lane = threadIdx.x;
+  f.x0 = 1 + 4 * (32 * blockIdx.x + threadIdx.x);
+  f.y = 1 + FTY * blockIdx.y + threadIdx.y;
+  f.z0 = 1 + zchunk * blockIdx.z;
+  f.z1 = min(f.z0 + zchunk, g.N[2] - 1);
+  f.on = f.x0 <= g.N[0] - 2 && f.y <= g.N[1] - 2;
+  f.lastgrp = f.x0 + 4 > g.N[0] - 2;
+  f.xl = (g.per[0] && f.x0 == 1) ? g.N[0] - 2 : f.x0 - 1;
+  f.xr = (g.per[0] && f.x0 + 3 == g.N[0] - 2) ? 1 : f.x0 + 4;
+  const int yy = min(f.y, g.N[1] - 2);
+  f.ym = (g.per[1] && yy == 1) ? g.N[1] - 2 : yy - 1;
+  f.yp = (g.per[1] && yy == g.N[1] - 2) ? 1 : yy + 1;
+  f.row = (i64)g.xo + g.s[1] * yy;
+  f.rowm = (i64)g.xo + g.s[1] * f.ym;
+  f.rowp = (i64)g.xo + g.s[1] * f.yp;
+  return f;
+}
+__device__ __forceinline__ int zwrap_lo(const Grid& g, int z) { return (g.per[2] && z == 1) ? g.N[2] - 2 : z - 1; }
+__device__ __forceinline__ int zwrap_hi(const Grid& g, int z) { return (g.per[2] && z == g.N[2] - 2) ? 1 : z + 1; }
+
+// x neighbours of a (transformed) vector: left of .x and right of .w.  `edge_l`/`edge_r` are the already transformed
+// scalars to use at the ends of the warp's row segment.  All lanes must call this (warp shuffles).
+__device__ __forceinline__ void x_nbrs(const Frame& f, const float4& c, float edge_l, float edge_r, float& left, float& right) {
+  left = __shfl_up_sync(FULLMASK, c.w, 1);
+  right = __shfl_down_sync(FULLMASK, c.x, 1);
+  if (f.lane == 0) left = edge_l;
+  if (f.lane == 31 || f.lastgrp) right = edge_r;
+}
+
+// A x at the 4 cells of a lane for the uniform operator: s = x·D + (xl·L0 + xr·L0) + (ym·L1 + yp·L1) + (zm·L2 + zp·L2)
+__device__ __forceinline__ float4 mult_uni(const Coef& c, const float4& xc, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                                           const float4& zp) {
+  float4 s;
+  const float L0 = c.Lc[0], L1 = c.Lc[1], L2 = c.Lc[2], D = c.Dc;
+  s.x = xc.x * D;
+  s.x += left * L0 + xc.y * L0;
+  s.x += ym.x * L1 + yp.x * L1;
+  s.x += zm.x * L2 + zp.x * L2;
+  s.y = xc.y * D;
+  s.y += xc.x * L0 + xc.z * L0;
+  s.y += ym.y * L1 + yp.y * L1;
+  s.y += zm.y * L2 + zp.y * L2;
+  s.z = xc.z * D;
+  s.z += xc.y * L0 + xc.w * L0;
+  s.z += ym.z * L1 + yp.z * L1;
+  s.z += zm.z * L2 + zp.z * L2;
+  s.w = xc.w * D;
+  s.w += xc.z * L0 + right * L0;
+  s.w += ym.w * L1 + yp.w * L1;
+  s.w += zm.w * L2 + zp.w * L2;
+  return s;
+}
+
+// General operator: coefficients from memory.  Llo0 = L[I,0] (4 values), Lhi0r = L[I+δ0,0] of the LAST cell (the others are
+// Llo0 shifted), Llo1/Lhi1 = L[I,1], L[I+δ1,1]; Llo2/Lhi2 likewise; Dg = D[I].
+__device__ __forceinline__ float4 mult_gen(const float4& xc, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                                           const float4& zp, const float4& Dg, const float4& Llo0, float Lhi0r, const float4& Llo1, const float4& Lhi1,
+                                           const float4& Llo2, const float4& Lhi2) {
+  float4 s;
+  s.x = xc.x * Dg.x;
+  s.x += left * Llo0.x + xc.y * Llo0.y;
+  s.x += ym.x * Llo1.x + yp.x * Lhi1.x;
+  s.x += zm.x * Llo2.x + zp.x * Lhi2.x;
+  s.y = xc.y * Dg.y;
+  s.y += xc.x * Llo0.y + xc.z * Llo0.z;
+  s.y += ym.y * Llo1.y + yp.y * Lhi1.y;
+  s.y += zm.y * Llo2.y + zp.y * Lhi2.y;
+  s.z = xc.z * Dg.z;
+  s.z += xc.y * Llo0.z + xc.w * Llo0.w;
+  s.z += ym.z * Llo1.z + yp.z * Lhi1.z;
+  s.z += zm.z * Llo2.z + zp.z * Lhi2.z;
+  s.w = xc.w * Dg.w;
+  s.w += xc.z * Llo0.w + right * Lhi0r;
+  s.w += ym.w * Llo1.w + yp.w * Lhi1.w;
+  s.w += zm.w * Llo2.w + zp.w * Lhi2.w;
+  return s;
+}
+
+// Loads the coefficient vectors of the lane's 4 cells on plane offset `pz` (= s2*z) and applies the operator.
+template <bool UNI>
+__device__ __forceinline__ float4 apply_A(const Grid& g, const Coef& c, const Frame& f, i64 pz, const float4& xc, float left, float right, const float4& ym,
+                                          const float4& yp, const float4& zm, const float4& zp) {
+  if (UNI) return mult_uni(c, xc, left, right, ym, yp, zm, zp);
+  const i64 o = f.row + pz + f.x0;
+  const float4 Dg = ld4(c.Dg + o);
+  const float4 Llo0 = ld4(c.L + o);
+  const float Lhi0r = c.L[o + 4];
+  const float4 Llo1 = ld4(c.L + g.sc + o), Lhi1 = ld4(c.L + g.sc + o + g.s[1]);
+  const float4 Llo2 = ld4(c.L + 2 * g.sc + o), Lhi2 = ld4(c.L + 2 * g.sc + o + g.s[2]);
+  return mult_gen(xc, left, right, ym, yp, zm, zp, Dg, Llo0, Lhi0r, Llo1, Lhi1, Llo2, Lhi2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stencil-field reader with a pointwise transform:  kind 0: q          (ϵ, x)
+//                                                   kind 1: q · s      (x = p·dt,  s scalar)
+//                                                   kind 2: q · w[o]   (ϵ = r·iD with iD from memory)
+// In UNI mode r·iD uses kind 1 with s = iDc.
+// ------------------------------------------------------------------------------------------------
+struct SField {
+  const float* q;
+  const float* w;
+  float s;
+  int kind;
+  __device__ __forceinline__ float4 v4(i64 o) const {
+    float4 a = ld4(q + o);
+    if (kind == 1) a = scale4(a, s);
+    if (kind == 2) a = mul4(a, ld4(w + o));
+    return a;
+  }
+  __device__ __forceinline__ float v1(i64 o) const {
+    float a = q[o];
+    if (kind == 1) a = a * s;
+    if (kind == 2) a = a * w[o];
+    return a;
+  }
+};
+
+// The common marching loop.  For every plane z of the chunk it hands the functor the centre vector and its six
+// neighbours of the stencil field:  body(z, pz, o, c, left, right, ym, yp, zm, zp).
+template <class Body>
+__device__ __forceinline__ void march7(const Grid& g, const Frame& f, const SField& F, Body body) {
+  float4 zm = f4zero(), c = f4zero(), zp = f4zero();
+  if (f.on) {
+    zm = F.v4(f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0);
+    c = F.v4(f.row + g.s[2] * f.z0 + f.x0);
+  }
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 pz = g.s[2] * z;
+    float4 ym = f4zero(), yp = f4zero();
+    float el = 0.f, er = 0.f;
+    if (f.on) {
+      zp = F.v4(f.row + g.s[2] * zwrap_hi(g, z) + f.x0);
+      ym = F.v4(f.rowm + pz + f.x0);
+      yp = F.v4(f.rowp + pz + f.x0);
+      if (f.lane == 0) el = F.v1(f.row + pz + f.xl);
+      if (f.lane == 31 || f.lastgrp) er = F.v1(f.row + pz + f.xr);
+    }
+    float left, right;
+    x_nbrs(f, c, el, er, left, right);
+    body(z, pz, f.row + pz + f.x0, c, left, right, ym, yp, zm, zp);
+    zm = c;
+    c = zp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi!(p) with ω=1 fused with increment! and restrict! (src/Poisson.jl:111-114,100-104; src/MultiLevelPoisson.jl:49,92-94):
+//   ϵ = r·iD;  r' = r − Aϵ → r2;  x (+)= ϵ;   coarse.r[I] = Σ r' over up(I)  (x fastest, then y, then z)
+// The y pair of a coarse cell sits in two adjacent warps: r' is exchanged through shared memory once per plane.
+// ------------------------------------------------------------------------------------------------
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
+                                                     int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict) {
+  __shared__ float4 ex[FTY][32];
+  const Frame f = make_frame(g, zchunk);
+  SField F;
+  F.q = r;
+  F.w = c.iD;
+  F.s = c.iDc;
+  F.kind = UNI ? 1 : 2;
+  float2 acc = make_float2(0.f, 0.f);  // running sums of the two coarse cells this lane contributes to
+  march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& e, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                      const float4& zp) {
+    float4 rn = f4zero();
+    if (f.on) {
+      const float4 Ae = apply_A<UNI>(g, c, f, pz, e, left, right, ym, yp, zm, zp);
+      const float4 ro = ld4(r + o);
+      rn = make_float4(ro.x - 1.f * Ae.x, ro.y - 1.f * Ae.y, ro.z - 1.f * Ae.z, ro.w - 1.f * Ae.w);
+      st4(r2 + o, rn);
+      if (x_is_zero)
+        st4(x + o, e);
+      else {
+        const float4 xo = ld4(x + o);
+        st4(x + o, make_float4(xo.x + 1.f * e.x, xo.y + 1.f * e.y, xo.z + 1.f * e.z, xo.w + 1.f * e.w));
+      }
+    }
+    if (do_restrict) {
+      // restrict(I,b,c) sums b[J] for J ∈ up(I): x fastest, then y, then z  (src/MultiLevelPoisson.jl:13-19)
+      ex[threadIdx.y][f.lane] = rn;
+      __syncthreads();
+      const bool ylow = (threadIdx.y & 1) == 0;  // tile origin y=1 is the first row of a pair
+      if (ylow) {
+        const float4 up = ex[threadIdx.y + 1][f.lane];
+        const bool zlow = ((z - 1) & 1) == 0;
+        if (zlow) {
+          acc.x = 0.f;
+          acc.y = 0.f;
+        }
+        acc.x += rn.x;
+        acc.x += rn.y;
+        acc.x += up.x;
+        acc.x += up.y;
+        acc.y += rn.z;
+        acc.y += rn.w;
+        acc.y += up.z;
+        acc.y += up.w;
+        if (!zlow && f.on) {
+          // coarse cell indices: (x0+1)/2, (x0+3)/2 ; (y+1)/2 ; (z+1)/2
+          const i64 oc = (i64)gc.xo + (f.x0 + 1) / 2 + gc.s[1] * ((f.y + 1) / 2) + gc.s[2] * ((z + 1) / 2);
+          rc[oc] = acc.x;
+          rc[oc + 1] = acc.y;
+        }
+      }
+      __syncthreads();
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// increment!(p;ω) (src/Poisson.jl:100-104) with the ϵ source either the level's own ϵ array (after GaussSeidelRB!) or
+// the prolongation of the coarse solution, ϵ[I] = coarse.x[down(I)] (src/MultiLevelPoisson.jl:50,99-100), never stored:
+//   r −= ω·Aϵ ;  x += ω·ϵ ;  optionally Σr² → out[slot]  (L₂, src/Poisson.jl:189)
+// ------------------------------------------------------------------------------------------------
+struct ProlongSrc {  // reads ϵ = xc[down(·)] for a fine row segment
+  const float* xc;
+  Grid gc;
+};
+
+template <bool UNI, bool PROLONG>
+__global__ void __launch_bounds__(32 * FTY) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
+                                                        float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
+                                                        RedBuf R, int slot) {
+  const Frame f = make_frame(g, zchunk);
+  const float w = *wp;
+  double l2 = 0.0;
+  if (!PROLONG) {
+    SField F;
+    F.q = eps;
+    F.w = nullptr;
+    F.s = 1.f;
+    F.kind = 0;
+    march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& e, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                        const float4& zp) {
+      if (f.on) {
+        const float4 Ae = apply_A<UNI>(g, c, f, pz, e, left, right, ym, yp, zm, zp);
+        const float4 ro = ld4(r + o);
+        const float4 rn = make_float4(ro.x - w * Ae.x, ro.y - w * Ae.y, ro.z - w * Ae.z, ro.w - w * Ae.w);
+        st4(r + o, rn);
+        if (x_is_zero)
+          st4(x + o, make_float4(w * e.x, w * e.y, w * e.z, w * e.w));
+        else {
+          const float4 xo = ld4(x + o);
+          st4(x + o, make_float4(xo.x + w * e.x, xo.y + w * e.y, xo.z + w * e.z, xo.w + w * e.w));
+        }
+        l2 += (double)rn.x * rn.x + (double)rn.y * rn.y + (double)rn.z * rn.z + (double)rn.w * rn.w;
+      }
+    });
+  } else {
+    // Prolongation source: a fine group x0..x0+3 (x0 odd) maps to coarse cells cx, cx+1 with cx=(x0+1)/2:
+    //   fine x0-1 → cx-1 ; x0,x0+1 → cx ; x0+2,x0+3 → cx+1 ; x0+4 → cx+2   (with the fine periodic wrap applied first)
+    const Grid& gc = ps.gc;
+    auto crow = [&](int yf, int zf) -> i64 { return (i64)gc.xo + gc.s[1] * ((yf + 1) / 2) + gc.s[2] * ((zf + 1) / 2); };
+    auto ld2 = [&](i64 rowc) -> float4 {  // ϵ at the lane's 4 fine cells on a coarse row
+      const int cx = (f.x0 + 1) / 2;
+      const float a = ps.xc[rowc + cx], b = ps.xc[rowc + cx + 1];
+      return make_float4(a, a, b, b);
+    };
+    for (int z = f.z0; z < f.z1; z++) {
+      if (!f.on) continue;
+      const i64 pz = g.s[2] * z;
+      const i64 o = f.row + pz + f.x0;
+      const i64 rc0 = crow(f.y, z);
+      const float4 e = ld2(rc0);
+      const float left = ps.xc[rc0 + (f.xl + 1) / 2];
+      const float right = ps.xc[rc0 + (f.xr + 1) / 2];
+      const float4 ym = ld2(crow(f.ym, z)), yp = ld2(crow(f.yp, z));
+      const float4 zm = ld2(crow(f.y, zwrap_lo(g, z))), zp = ld2(crow(f.y, zwrap_hi(g, z)));
+      const float4 Ae = apply_A<UNI>(g, c, f, pz, e, left, right, ym, yp, zm, zp);
+      const float4 ro = ld4(r + o);
+      const float4 rn = make_float4(ro.x - w * Ae.x, ro.y - w * Ae.y, ro.z - w * Ae.z, ro.w - w * Ae.w);
+      st4(r + o, rn);
+      const float4 xo = ld4(x + o);
+      st4(x + o, make_float4(xo.x + w * e.x, xo.y + w * e.y, xo.z + w * e.z, xo.w + w * e.w));
+    }
+  }
+  if (with_l2) {
+    double v[1] = {l2}, fin[1];
+    grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// div + x.*=dt + residual! part 1 (src/Flow.jl:225, src/Poisson.jl:93-95):
+//   z = Σ_d (u_d[I+δ_d] − u_d[I]);  x = p·dt;  r = iD==0 ? 0 : z − A x;   Σr → out[slot], Σr² → out[slot+1]
+// σ (=z) is not stored in UNI mode (it is pure scratch there; CFL rewrites the interior every step).
+// ------------------------------------------------------------------------------------------------
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
+                                                           float* __restrict__ r, float* __restrict__ zarr, const float* __restrict__ dtp, float wdt,
+                                                           int zchunk, RedBuf R, int slot) {
+  const Frame f = make_frame(g, zchunk);
+  const float dt = wdt * (*dtp);
+  SField F;
+  F.q = p;
+  F.w = nullptr;
+  F.s = dt;
+  F.kind = 1;
+  double sum = 0.0;
+  march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& xs, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                      const float4& zp) {
+    // u_x needs the value one cell to the right of the group
+    float4 ux = f4zero();
+    float uxr_edge = 0.f;
+    if (f.on) {
+      ux = ld4(u + o);
+      if (f.lane == 31 || f.lastgrp) uxr_edge = u[o + 4];
+    }
+    float uxr = __shfl_down_sync(FULLMASK, ux.x, 1);
+    if (f.lane == 31 || f.lastgrp) uxr = uxr_edge;
+    if (f.on) {
+      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + o + g.s[1]);
+      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + o + g.s[2]);
+      float4 dv;
+      dv.x = 0.f + (ux.y - ux.x);
+      dv.x += uyp.x - uy.x;
+      dv.x += uzp.x - uz.x;
+      dv.y = 0.f + (ux.z - ux.y);
+      dv.y += uyp.y - uy.y;
+      dv.y += uzp.y - uz.y;
+      dv.z = 0.f + (ux.w - ux.z);
+      dv.z += uyp.z - uy.z;
+      dv.z += uzp.z - uz.z;
+      dv.w = 0.f + (uxr - ux.w);
+      dv.w += uyp.w - uy.w;
+      dv.w += uzp.w - uz.w;
+      const float4 Ax = apply_A<UNI>(g, c, f, pz, xs, left, right, ym, yp, zm, zp);
+      float4 rr = make_float4(dv.x - Ax.x, dv.y - Ax.y, dv.z - Ax.z, dv.w - Ax.w);
+      if (!UNI) {
+        const float4 iD = ld4(c.iD + o);
+        if (iD.x == 0.f) rr.x = 0.f;
+        if (iD.y == 0.f) rr.y = 0.f;
+        if (iD.z == 0.f) rr.z = 0.f;
+        if (iD.w == 0.f) rr.w = 0.f;
+        st4(zarr + o, dv);
+      }
+      st4(x + o, xs);
+      st4(r + o, rr);
+      sum += (double)rr.x + (double)rr.y + (double)rr.z + (double)rr.w;
+    }
+  });
+  double v[1] = {sum}, fin[1];
+  grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+}
+
+// residual! part 2 + L₂ (src/Poisson.jl:95-97,189): s = Σr/|inside|; |s|>2eps ⇒ r −= s; Σr² → out[slot_out]
+__global__ void __launch_bounds__(32 * FTY) f_resid_fix(Grid g, float* __restrict__ r, float count, int zchunk, RedBuf R, int slot_in, int slot_out) {
+  const Frame f = make_frame(g, zchunk);
+  const float s = (float)R.out[slot_in] / count;
+  const bool fix = fabsf(s) > 2.f * 1.1920929e-7f;
+  double l2 = 0.0;
+  if (f.on) {
+    for (int z = f.z0; z < f.z1; z++) {
+      const i64 o = f.row + g.s[2] * z + f.x0;
+      float4 v = ld4(r + o);
+      if (fix) {
+        v = make_float4(v.x - s, v.y - s, v.z - s, v.w - s);
+        st4(r + o, v);
+      }
+      l2 += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+  }
+  double v[1] = {l2}, fin[1];
+  grid_reduce<RED_SUM, 1>(v, R, slot_out, fin);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Velocity correction + pressure unscale of mom_project! (src/Flow.jl:227-230), optionally fused with CFL's flux_out
+// on the corrected field is NOT done here: flux_out needs BC-filled ghosts, it stays in k_cfl.
+//   u_d[I] −= L[I,d]·(x[I] − x[I−δ_d]);  p = x/dt
+// ------------------------------------------------------------------------------------------------
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
+                                                      const float* __restrict__ dtp, float wdt, int zchunk) {
+  const Frame f = make_frame(g, zchunk);
+  const float dt = wdt * (*dtp);
+  float4 zm = f4zero();
+  if (f.on) zm = ld4(x + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0);
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 pz = g.s[2] * z;
+    const i64 o = f.row + pz + f.x0;
+    float4 xc = f4zero(), ym = f4zero();
+    float el = 0.f;
+    if (f.on) {
+      xc = ld4(x + o);
+      ym = ld4(x + f.rowm + pz + f.x0);
+      if (f.lane == 0) el = x[f.row + pz + f.xl];
+    }
+    float left = __shfl_up_sync(FULLMASK, xc.w, 1);
+    if (f.lane == 0) left = el;
+    if (f.on) {
+      float4 L0, L1, L2;
+      if (UNI) {
+        L0 = make_float4(c.Lc[0], c.Lc[0], c.Lc[0], c.Lc[0]);
+        L1 = make_float4(c.Lc[1], c.Lc[1], c.Lc[1], c.Lc[1]);
+        L2 = make_float4(c.Lc[2], c.Lc[2], c.Lc[2], c.Lc[2]);
+      } else {
+        L0 = ld4(c.L + o);
+        L1 = ld4(c.L + g.sc + o);
+        L2 = ld4(c.L + 2 * g.sc + o);
+      }
+      float4 a = ld4(u + o);
+      a.x -= L0.x * (xc.x - left);
+      a.y -= L0.y * (xc.y - xc.x);
+      a.z -= L0.z * (xc.z - xc.y);
+      a.w -= L0.w * (xc.w - xc.z);
+      st4(u + o, a);
+      float4 b = ld4(u + g.sc + o);
+      b.x -= L1.x * (xc.x - ym.x);
+      b.y -= L1.y * (xc.y - ym.y);
+      b.z -= L1.z * (xc.z - ym.z);
+      b.w -= L1.w * (xc.w - ym.w);
+      st4(u + g.sc + o, b);
+      float4 d = ld4(u + 2 * g.sc + o);
+      d.x -= L2.x * (xc.x - zm.x);
+      d.y -= L2.y * (xc.y - zm.y);
+      d.z -= L2.z * (xc.z - zm.z);
+      d.w -= L2.w * (xc.w - zm.w);
+      st4(u + 2 * g.sc + o, d);
+      st4(p + o, make_float4(xc.x / dt, xc.y / dt, xc.z / dt, xc.w / dt));
+    }
+    zm = xc;
+  }
+}
+
+// Device check that the uniform-coefficient specialisation is legal: μ₀ ≡ 1 on every cell the operator reads, μ₁ ≡ 0, V ≡ 0.
+// Writes the number of offending values (as a max-reduced 0/1 flag) to out[slot].
+__global__ void __launch_bounds__(256) k_check_uniform(const float* __restrict__ mu0, const float* __restrict__ mu1, const float* __restrict__ V, Grid g,
+                                                       RedBuf R, int slot) {
+  // whole allocation incl. padding is zero-initialised: test only real cells
+  const i64 ncell = (i64)g.N[0] * g.N[1] * g.N[2];
+  double bad = 0.0;
+  for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += (i64)gridDim.x * blockDim.x) {
+    const int i = (int)(q % g.N[0]);
+    const i64 t = q / g.N[0];
+    const int j = (int)(t % g.N[1]);
+    const int k = (int)(t / g.N[1]);
+    const i64 o = (i64)g.xo + i + g.s[1] * j + g.s[2] * k;
+    for (int d = 0; d < 3; d++) {
+      if (mu0[o + g.sc * d] != 1.f) bad = 1.0;
+      if (V[o + g.sc * d] != 0.f) bad = 1.0;
+    }
+    for (int d = 0; d < 9; d++)
+      if (mu1[o + g.sc * d] != 0.f) bad = 1.0;
+  }
+  double v[1] = {bad}, fin[1];
+  grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+}
+
+// ================================================================================================
+// Momentum: conv_diff! in gather form with shared fluxes (src/Flow.jl:38-62), fused with BDIM
+// (src/Flow.jl:176-180) and scale_u! (src/Flow.jl:211-214).
+//
+// Geometry: blockDim = (32, CTY); a thread owns one (x,y) column and marches over a z chunk.  The three
+// velocity components of the six planes z-2 … z+3 live in a shared-memory ring with an in-plane halo of 2,
+// loaded with periodic wrap (ghost cells are exact periodic copies after BC!, so the wrapped loads make the
+// reference's lowerBoundary!/upperBoundary! periodic variants identical to the inner formula).  Each face flux
+// is evaluated once where that is free: the lower z flux is carried over from the previous plane and the upper x
+// flux comes from the next lane by shuffle; the upper y flux is recomputed.
+//
+// FUSE = uniform mode (no body, periodic): u_new is produced directly (predictor: u = u⁰+Δt·r; corrector:
+// u = (u + u⁰+Δt·r)/2) on interior cells, nothing else is read or written; the stale-Φ values that the reference
+// leaves on the upper ghost cells of σ (they enter maximum(σ) in CFL, App. A.9-1) are max-reduced into out[slot]
+// from their periodic images instead of being stored.
+// !FUSE writes f = u⁰ + Δt·r − V on every cell with all indices ≥ 1 (interior and upper ghost rows, App. A.9-2)
+// and the stale Φ on upper ghost cells of σ; lower ghost planes of f are filled by k_f_lowghost.
+// ================================================================================================
+#define CTY 8
+#define CRING 6
+#define CW 36
+#define CH (CTY + 4)
+
+struct ConvTile {
+  float v[CRING][3][CH][CW];
+};
+
+template <int LAM>
+__device__ __forceinline__ float flux_from(float uf, float um2, float um1, float u0c, float up1, float nu, int variant) {
+  // variant 0: ϕu (inner / periodic), 1: ϕuL (lower non-periodic boundary), 2: ϕuR (upper non-periodic boundary)
+  const float diff = nu * (u0c - um1);
+  const bool pos = uf > 0.f;
+  float conv;
+  if (variant == 1)
+    conv = pos ? uf * ((u0c + um1) / 2.f) : uf * limiter<LAM>(up1, u0c, um1);
+  else if (variant == 2)
+    conv = uf < 0.f ? uf * ((u0c + um1) / 2.f) : uf * limiter<LAM>(um2, um1, u0c);
+  else
+    conv = uf * limiter<LAM>(pos ? um2 : up1, pos ? um1 : u0c, pos ? u0c : um1);
+  return conv - diff;
+}
+
+template <int LAM, bool FUSE, bool PER3>
+__global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restrict__ ua, const float* __restrict__ u0, const float* __restrict__ V,
+                                                    float* __restrict__ out, float* __restrict__ sigma, const float* __restrict__ dtp, float nu, int zchunk,
+                                                    int corrector, RedBuf R, int slot) {
+  extern __shared__ float smem_raw[];
+  float* const T = smem_raw;  // [CRING][3][CH][CW]
+  constexpr int PL = CH * CW;  // one component plane
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int tid = lane + 32 * ty;
+  const int xb = 1 + 32 * blockIdx.x, yb = 1 + CTY * blockIdx.y;
+  const int x = xb + lane, y = yb + ty;
+  const int XM = FUSE ? g.N[0] - 2 : g.N[0] - 1, YM = FUSE ? g.N[1] - 2 : g.N[1] - 1, ZM = FUSE ? g.N[2] - 2 : g.N[2] - 1;
+  const int z0 = 1 + zchunk * blockIdx.z, z1 = min(z0 + zchunk, ZM + 1);
+  const bool on = x <= XM && y <= YM;
+  const float dt = *dtp;
+
+  auto wrap = [&](int v, int d) -> int {  // periodic image inside [0, N-1]; clamp otherwise (clamped values are never used)
+    const int N = g.N[d];
+    if (g.per[d]) {
+      if (v < 0) v += N - 2;
+      else if (v > N - 1) v -= N - 2;
+    }
+    return max(0, min(N - 1, v));
+  };
+  // tile elements this thread loads on every plane (fixed across planes): in-plane global offset and shared index
+  constexpr int NE = (PL + 32 * CTY - 1) / (32 * CTY);
+  i64 go[NE];
+  int so[NE];
+#pragma unroll
+  for (int k = 0; k < NE; k++) {
+    const int e = tid + k * 32 * CTY;
+    const int ry = e / CW, rx = e - ry * CW;
+    so[k] = e < PL ? e : -1;
+    go[k] = (i64)g.xo + wrap(xb - 2 + rx, 0) + g.s[1] * wrap(yb - 2 + min(ry, CH - 1), 1);
+  }
+  auto load_plane = [&](int zz) {
+    int slotp = zz % CRING;
+    if (slotp < 0) slotp += CRING;
+    float* dst = T + slotp * 3 * PL;
+    const i64 pz = g.s[2] * wrap(zz, 2);
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+      if (so[k] >= 0) {
+        const i64 o = go[k] + pz;
+        dst[so[k]] = ua[o];
+        dst[PL + so[k]] = ua[o + g.sc];
+        dst[2 * PL + so[k]] = ua[o + 2 * g.sc];
+      }
+    }
+  };
+  // po[k]: offset of this thread's column on plane z-2+k (k = 0..5) inside the ring; refreshed every step
+  int po[6];
+  const int colbase = (ty + 2) * CW + lane + 2;
+  // U(c, dx, dy, dz): component c at (x+dx, y+dy) on plane z+dz, dz ∈ [-2, 3]
+  auto U = [&](int c, int dx, int dy, int dz) -> float { return T[po[dz + 2] + c * PL + dy * CW + dx]; };
+  int zc = 0;
+  // lower-face flux of component i in direction j for the cell at offset (ox,oy,oz) from this thread's cell on plane zc
+  auto flux = [&](int i, int j, int ox, int oy, int oz) -> float {
+    int variant = 0;
+    if (!PER3) {
+      const int I[3] = {x + ox, y + oy, zc + oz};
+      if (!g.per[j]) variant = I[j] == 1 ? 1 : (I[j] == g.N[j] - 1 ? 2 : 0);
+    }
+    const int dx = (j == 0), dy = (j == 1), dz = (j == 2);
+    const int ix = (i == 0), iy = (i == 1), iz = (i == 2);
+    const float uf = (U(j, ox, oy, oz) + U(j, ox - ix, oy - iy, oz - iz)) / 2.f;
+    const float um2 = U(i, ox - 2 * dx, oy - 2 * dy, oz - 2 * dz);
+    const float um1 = U(i, ox - dx, oy - dy, oz - dz);
+    const float u0c = U(i, ox, oy, oz);
+    const float up1 = U(i, ox + dx, oy + dy, oz + dz);
+    return flux_from<LAM>(uf, um2, um1, u0c, up1, nu, variant);
+  };
+
+  for (int zz = z0 - 2; zz <= z0 + 1; zz++) load_plane(zz);
+  float Fz[3] = {0.f, 0.f, 0.f};
+  bool haveFz = false;
+  double gmax = 0.0;
+  for (int z = z0; z < z1; z++) {
+    load_plane(z + 2);
+    zc = z;
+    {
+      int sl = (z - 2) % CRING;
+      if (sl < 0) sl += CRING;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        po[k] = sl * 3 * PL + colbase;
+        sl = (sl + 1 == CRING) ? 0 : sl + 1;
+      }
+    }
+    __syncthreads();
+    // which directions contribute to this cell (all for interior cells; upper ghost rows only get the others)
+    const bool ax = x <= g.N[0] - 2, ay = y <= g.N[1] - 2, az = z <= g.N[2] - 2;
+    float Fxlo[3], Fxhi[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) Fxlo[i] = flux(i, 0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++) Fxhi[i] = __shfl_down_sync(FULLMASK, Fxlo[i], 1);
+    if (lane == 31 || x == XM) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) Fxhi[i] = (x + 1 <= g.N[0] - 1) ? flux(i, 0, 1, 0, 0) : 0.f;
+    }
+    if (!haveFz) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) Fz[i] = flux(i, 2, 0, 0, 0);
+      haveFz = true;
+    }
+    float Fzhi[3] = {0.f, 0.f, 0.f};
+    if (z + 1 <= g.N[2] - 1) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) Fzhi[i] = flux(i, 2, 0, 0, 1);
+    }
+    float F2lo_y = 0.f;
+    if (on) {
+      const i64 o = (i64)g.xo + x + g.s[1] * y + g.s[2] * z;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float r = 0.f;
+        const float Fylo = flux(i, 1, 0, 0, 0);
+        if (i == 2) F2lo_y = Fylo;
+        if (ax) {
+          r += Fxlo[i];
+          r -= Fxhi[i];
+        }
+        if (ay) {
+          r += Fylo;
+          r -= flux(i, 1, 0, 1, 0);
+        }
+        if (az) {
+          r += Fz[i];
+          r -= Fzhi[i];
+        }
+        const i64 oc = o + (i64)i * g.sc;
+        if (FUSE) {
+          const float f = u0[oc] + dt * r;  // − V with V ≡ 0; then X = 0/2 + 0 + 1·f
+          out[oc] = corrector ? (U(i, 0, 0, 0) + f) * 0.5f : f;
+        } else {
+          out[oc] = u0[oc] + dt * r - V[oc];
+        }
+      }
+      if (FUSE) {
+        // periodic images of the stale Φ on upper ghost cells (see header): candidates by T = {k : I_k == 1}
+        const bool t0 = x == 1, t1 = y == 1, t2 = z == 1;
+        if (t0 || t1) gmax = fmax(gmax, (double)Fz[2]);
+        if (t2) gmax = fmax(gmax, (double)F2lo_y);
+        if (t2 && t1) gmax = fmax(gmax, (double)Fxlo[2]);
+      } else {
+        const bool ghost = x == g.N[0] - 1 || y == g.N[1] - 1 || z == g.N[2] - 1;
+        if (ghost) {
+          // last Φ written by the reference's (i=D, j) loops: the largest j whose range contains the cell
+          const int lo0 = g.per[0] ? 1 : 2, lo1 = g.per[1] ? 1 : 2, lo2 = g.per[2] ? 1 : 2;
+          if (az && z >= lo2) sigma[o] = Fz[2];
+          else if (ay && y >= lo1) sigma[o] = F2lo_y;
+          else if (ax && x >= lo0) sigma[o] = Fxlo[2];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) Fz[i] = Fzhi[i];
+  }
+  if (FUSE) {
+    double v[1] = {gmax}, fin[1];
+    grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+  }
+}
+
+// f on the lower ghost planes (any index 0): r = 0 there, so f = u⁰ + Δt·0 − V  (src/Flow.jl:178 over CartesianIndices(f))
+__global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f, const float* __restrict__ dtp) {
+  const int j = blockIdx.z;  // plane I_j = 0
+  const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (t0 >= g.N[da] || t1 >= g.N[db]) return;
+  int I[3];
+  I[j] = 0;
+  I[da] = t0;
+  I[db] = t1;
+  const i64 o = cell_off(g, I);
+  const float dt = *dtp;
+  for (int i = 0; i < 3; i++) f[o + g.sc * i] = u0[o + g.sc * i] + dt * 0.f - V[o + g.sc * i];
+}
+
+// max of σ over the ghost cells (where the reference's stale Φ lives) → out[slot]; planes selected by blockIdx.z
+__global__ void __launch_bounds__(256) k_sigma_ghostmax(Grid g, const float* __restrict__ sigma, RedBuf R, int slot) {
+  const int plane = blockIdx.z;
+  const int j = plane / 2, which = plane % 2;
+  const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y * blockDim.y + threadIdx.y;
+  double v[1] = {0.0}, fin[1];
+  if (t0 < g.N[da] && t1 < g.N[db]) {
+    int I[3];
+    I[j] = which ? g.N[j] - 1 : 0;
+    I[da] = t0;
+    I[db] = t1;
+    v[0] = (double)sigma[cell_off(g, I)];
+  }
+  grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+}
+
+// CFL (src/Flow.jl:234-244) on the interior with the march geometry: σ = flux_out(I,u) (stored unless UNI), max-reduced,
+// combined with the ghost maximum in out[slot_ghost]; the last block stores Δt = min(10, 1/(max+5ν)) to dt_out.
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_cfl(Grid g, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
+                                                  int zchunk, RedBuf R, int slot, int slot_ghost) {
+  const Frame f = make_frame(g, zchunk);
+  double m = 0.0;
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 o = f.row + g.s[2] * z + f.x0;
+    float4 ux = f4zero();
+    float e = 0.f;
+    if (f.on) {
+      ux = ld4(u + o);
+      if (f.lane == 31 || f.lastgrp) e = u[o + 4];
+    }
+    float uxr = __shfl_down_sync(FULLMASK, ux.x, 1);
+    if (f.lane == 31 || f.lastgrp) uxr = e;
+    if (f.on) {
+      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + o + g.s[1]);
+      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + o + g.s[2]);
+      float4 s;
+      s.x = 0.f + (fmaxf(0.f, ux.y) + fmaxf(0.f, -ux.x));
+      s.x += fmaxf(0.f, uyp.x) + fmaxf(0.f, -uy.x);
+      s.x += fmaxf(0.f, uzp.x) + fmaxf(0.f, -uz.x);
+      s.y = 0.f + (fmaxf(0.f, ux.z) + fmaxf(0.f, -ux.y));
+      s.y += fmaxf(0.f, uyp.y) + fmaxf(0.f, -uy.y);
+      s.y += fmaxf(0.f, uzp.y) + fmaxf(0.f, -uz.y);
+      s.z = 0.f + (fmaxf(0.f, ux.w) + fmaxf(0.f, -ux.z));
+      s.z += fmaxf(0.f, uyp.z) + fmaxf(0.f, -uy.z);
+      s.z += fmaxf(0.f, uzp.z) + fmaxf(0.f, -uz.z);
+      s.w = 0.f + (fmaxf(0.f, uxr) + fmaxf(0.f, -ux.w));
+      s.w += fmaxf(0.f, uyp.w) + fmaxf(0.f, -uy.w);
+      s.w += fmaxf(0.f, uzp.w) + fmaxf(0.f, -uz.w);
+      if (!UNI) st4(sigma + o, s);
+      m = fmax(m, (double)fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w)));
+    }
+  }
+  double v[1] = {m}, fin[1];
+  if (grid_reduce<RED_MAX, 1>(v, R, slot, fin)) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const float mm = (float)fmax(fin[0], R.out[slot_ghost]);
+      *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
+    }
+  }
+}

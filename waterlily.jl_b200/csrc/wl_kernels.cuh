@@ -7,16 +7,9 @@
 // ------------------------------------------------------------------------------------
 // limiters  (src/Flow.jl:4-6, :27-36)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float median3(float a, float b, float c) {
-  if (a > b) {
-    if (b >= c) return b;
-    if (a > c) return c;
-  } else {
-    if (b <= c) return b;
-    if (a < c) return c;
-  }
-  return a;
-}
+// median(a,b,c) of src/Flow.jl:27-36 returns the middle value; max(min(a,b), min(max(a,b),c)) is the same value
+// (ties return an equal value) without branches.
+__device__ __forceinline__ float median3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
 template <int LAM>
 __device__ __forceinline__ float limiter(float u, float c, float d) {
   if (LAM == 0) return median3((5.f * c + 2.f * d - u) / 6.f, c, median3(10.f * c - 9.f * u, c, d));  // quick
@@ -307,7 +300,7 @@ __global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, co
     float s = 0.f;
     for (int k = lo[2]; k <= hi[2]; k++)
       for (int jj = lo[1]; jj <= hi[1]; jj++)
-        for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)ii + gf.s[1] * jj + gf.s[2] * k + gf.sc * i];
+        for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)(gf.xo + ii) + gf.s[1] * jj + gf.s[2] * k + gf.sc * i];
     a[o + gc.sc * i] = c[i] ? s / 2.f : s;
   }
 }
@@ -405,7 +398,7 @@ __global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, con
   float s = 0.f;
   for (int k = lo[2]; k <= hi[2]; k++)
     for (int jj = lo[1]; jj <= hi[1]; jj++)
-      for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)ii + gf.s[1] * jj + gf.s[2] * k];
+      for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)(gf.xo + ii) + gf.s[1] * jj + gf.s[2] * k];
   a[cell_off(gc, I)] = s;
 }
 
