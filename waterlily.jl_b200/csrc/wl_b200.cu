@@ -123,6 +123,7 @@ struct wl_handle {
   std::vector<float> log;  // rows of (iter, rinf, r2, omega)
   bool logging = false;
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
+  bool fused_gs = true;
   cudaStream_t st = nullptr;
   int64_t launches = 0;
   double tol;
@@ -319,6 +320,23 @@ static int read_slot(wl_handle* h, int slot, double* out) {
 static void gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
   dim3 b = blk(h->D);
   Box in = l.inside();
+  if (l.fast && h->fused_gs && (l.g.N[2] - 2) % 2 == 0) {
+    // ϵ⁰ + sweep 1, then sweeps 2-4 in place, then increment! (+L₂): five vectorised march launches
+    dim3 fb(32, FTY);
+    ProlongSrc ps{nullptr, l.g};
+    if (h->uni) {
+      LAUNCH(h, f_gs_a<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, l.zchunk());
+      for (int k0 = 2; k0 <= 4; k0++) LAUNCH(h, f_gs_half<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, k0, l.zchunk());
+      LAUNCH(h, (f_increment<true, false>), l.fgrid(), fb, l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2, h->red,
+             SLOT_R2);
+    } else {
+      LAUNCH(h, f_gs_a<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, l.zchunk());
+      for (int k0 = 2; k0 <= 4; k0++) LAUNCH(h, f_gs_half<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, k0, l.zchunk());
+      LAUNCH(h, (f_increment<false, false>), l.fgrid(), fb, l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
+             h->red, SLOT_R2);
+    }
+    return;
+  }
   Lvl d = l.dev();
   LAUNCH_D(h, k_gs_init, grd(in, b), b, d, in);
   Box half = in;
@@ -725,6 +743,8 @@ int wl_create(const wl_config* cfg, wl_handle** out) {
   h->cfg = *cfg;
   h->D = cfg->D;
   h->tol = cfg->tol > 0 ? (double)cfg->tol : 1e-4;
+  h->fused_gs = !(cfg->flags & WL_FLAG_UNFUSED_GS);
+
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
   int N[3];
   for (int d = 0; d < 3; d++) N[d] = d < cfg->D ? cfg->n[d] + 2 : 1;

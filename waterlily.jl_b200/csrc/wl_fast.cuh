@@ -29,6 +29,13 @@ struct Coef {
   float Dc, iDc;
 };
 
+// 4-byte asynchronous global→shared copy (LDGSTS) and its completion fence
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -778,6 +785,190 @@ __global__ void __launch_bounds__(32 * FTY) f_cfl(Grid g, const float* __restric
     if (threadIdx.x == 0 && threadIdx.y == 0) {
       const float mm = (float)fmax(fin[0], R.out[slot_ghost]);
       *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
+    }
+  }
+}
+
+// ================================================================================================
+// GaussSeidelRB!(p;it=4,ω) (src/Poisson.jl:141-148) in three march kernels instead of six launches:
+//   f_gs_a : ϵ⁰ = r·iD, sweep 1                      (reads r, writes ϵ)
+//   f_gs_b : sweeps 2 and 3                           (reads ϵ, r; writes ϵ)
+//   f_gs_c : sweep 4, increment!(ω), L₂               (reads ϵ, r, x; writes r, x)
+// Colours: sweep k₀ updates the cells with (x+y+z) ≡ k₀ (mod 2) in 0-based indices (Σ 1-based ≡ 1+k₀, :125).
+// "A" cells (odd) move in sweeps 1 and 3, "B" cells (even) in sweeps 2 and 4.  Within one kernel the second
+// half-sweep needs first-half-sweep values of neighbouring cells; they are RECOMPUTED from the stored field
+// (same operations, same order ⇒ same bits) instead of being exchanged, so no kernel needs a grid-wide
+// dependency and every field is streamed once per kernel.
+// The reference fills the periodic ghosts of ϵ once, before the sweeps (:143), so during all four sweeps a
+// neighbour across a periodic face is the stale ϵ⁰ = r·iD of the wrapped cell; increment! refreshes the ghosts
+// (:101), so the final Aϵ sees current values.  `stale` below implements exactly that.
+// Requires the march geometry, (N2-2) even (half_rangek reaches every interior plane).
+// ================================================================================================
+// lanes of colour A (odd x+y+z) in a group starting at x0 on row (y,z): returns the parity of the first cell
+__device__ __forceinline__ bool first_is_A(int x0, int y, int z) { return ((x0 + y + z) & 1) != 0; }
+__device__ __forceinline__ float4 select_A(bool firstA, const float4& a, const float4& b) {  // A lanes from a, B lanes from b
+  return firstA ? make_float4(a.x, b.y, a.z, b.w) : make_float4(b.x, a.y, b.z, a.w);
+}
+
+template <bool UNI>
+struct Gs {
+  const Grid& g;
+  const Coef& c;
+  const float* eps;
+  const float* r;
+  int lane, x0, xl, xr;
+  bool on, lastgrp, wrapl, wrapr;  // wrapl/wrapr: the row ends of this lane are periodic faces
+
+  __device__ __forceinline__ Gs(const Grid& g_, const Coef& c_, const float* eps_, const float* r_, const Frame& f)
+      : g(g_), c(c_), eps(eps_), r(r_), lane(f.lane), x0(f.x0), xl(f.xl), xr(f.xr), on(f.on), lastgrp(f.lastgrp),
+        wrapl(g_.per[0] && f.x0 == 1), wrapr(g_.per[0] && f.x0 + 3 == g_.N[0] - 2) {}
+
+  __device__ __forceinline__ i64 off(int y, int z) const { return (i64)g.xo + g.s[1] * y + g.s[2] * z; }
+  __device__ __forceinline__ float iD1(i64 o) const { return UNI ? c.iDc : c.iD[o]; }
+  __device__ __forceinline__ float4 iD4(i64 o) const { return UNI ? make_float4(c.iDc, c.iDc, c.iDc, c.iDc) : ld4(c.iD + o); }
+  __device__ __forceinline__ float stale1(i64 o) const { return r[o] * iD1(o); }
+  __device__ __forceinline__ float4 stale4(i64 o) const { return mul4(ld4(r + o), iD4(o)); }
+
+  // gauss(I,r,L,iD,x) (src/Poisson.jl:116-122) for the 4 cells of the lane: (r − Σ_d (lo·L[I,d] + hi·L[I+δ_d,d]))·iD
+  __device__ __forceinline__ float4 gauss4(i64 o, const float4& rr, const float4& ec, float left, float right, const float4& ym, const float4& yp,
+                                           const float4& zm, const float4& zp) const {
+    float4 s = rr;
+    if (UNI) {
+      const float L0 = c.Lc[0], L1 = c.Lc[1], L2 = c.Lc[2];
+      s.x -= left * L0 + ec.y * L0;
+      s.x -= ym.x * L1 + yp.x * L1;
+      s.x -= zm.x * L2 + zp.x * L2;
+      s.y -= ec.x * L0 + ec.z * L0;
+      s.y -= ym.y * L1 + yp.y * L1;
+      s.y -= zm.y * L2 + zp.y * L2;
+      s.z -= ec.y * L0 + ec.w * L0;
+      s.z -= ym.z * L1 + yp.z * L1;
+      s.z -= zm.z * L2 + zp.z * L2;
+      s.w -= ec.z * L0 + right * L0;
+      s.w -= ym.w * L1 + yp.w * L1;
+      s.w -= zm.w * L2 + zp.w * L2;
+    } else {
+      const float4 A0 = ld4(c.L + o);
+      const float A0r = c.L[o + 4];
+      const float4 A1 = ld4(c.L + g.sc + o), B1 = ld4(c.L + g.sc + o + g.s[1]);
+      const float4 A2 = ld4(c.L + 2 * g.sc + o), B2 = ld4(c.L + 2 * g.sc + o + g.s[2]);
+      s.x -= left * A0.x + ec.y * A0.y;
+      s.x -= ym.x * A1.x + yp.x * B1.x;
+      s.x -= zm.x * A2.x + zp.x * B2.x;
+      s.y -= ec.x * A0.y + ec.z * A0.z;
+      s.y -= ym.y * A1.y + yp.y * B1.y;
+      s.y -= zm.y * A2.y + zp.y * B2.y;
+      s.z -= ec.y * A0.z + ec.w * A0.w;
+      s.z -= ym.z * A1.z + yp.z * B1.z;
+      s.z -= zm.z * A2.z + zp.z * B2.z;
+      s.w -= ec.z * A0.w + right * A0r;
+      s.w -= ym.w * A1.w + yp.w * B1.w;
+      s.w -= zm.w * A2.w + zp.w * B2.w;
+    }
+    return mul4(s, iD4(o));
+  }
+  // the same for one cell at x (scalar), neighbours given
+  __device__ __forceinline__ float gauss1(i64 o, float rr, float xm, float xp, float ym, float yp, float zm, float zp) const {
+    float s = rr;
+    if (UNI) {
+      s -= xm * c.Lc[0] + xp * c.Lc[0];
+      s -= ym * c.Lc[1] + yp * c.Lc[1];
+      s -= zm * c.Lc[2] + zp * c.Lc[2];
+    } else {
+      s -= xm * c.L[o] + xp * c.L[o + 1];
+      s -= ym * c.L[g.sc + o] + yp * c.L[g.sc + o + g.s[1]];
+      s -= zm * c.L[2 * g.sc + o] + zp * c.L[2 * g.sc + o + g.s[2]];
+    }
+    return s * iD1(o);
+  }
+
+  // One half-sweep update of ALL four cells of the lane's group on the absolute interior row (y,z), reading the STORED field
+  // `eps` (the caller keeps only the lanes of the colour that moves).  Periodic faces read the stale r·iD.  All lanes must call.
+  __device__ __forceinline__ float4 row_update(int y, int z, float4& stored) const {
+    const i64 ro = off(y, z);
+    const i64 o = ro + x0;
+    float4 ec = f4zero(), rr = f4zero(), vym = f4zero(), vyp = f4zero(), vzm = f4zero(), vzp = f4zero();
+    float el = 0.f, er = 0.f;
+    if (on) {
+      ec = ld4(eps + o);
+      rr = ld4(r + o);
+      if (lane == 0) el = wrapl ? stale1(ro + xl) : eps[ro + xl];
+      if (lane == 31 || lastgrp) er = wrapr ? stale1(ro + xr) : eps[ro + xr];
+      const bool wym = g.per[1] && y == 1, wyp = g.per[1] && y == g.N[1] - 2;
+      const bool wzm = g.per[2] && z == 1, wzp = g.per[2] && z == g.N[2] - 2;
+      const i64 oym = off(wym ? g.N[1] - 2 : y - 1, z) + x0, oyp = off(wyp ? 1 : y + 1, z) + x0;
+      const i64 ozm = off(y, wzm ? g.N[2] - 2 : z - 1) + x0, ozp = off(y, wzp ? 1 : z + 1) + x0;
+      vym = wym ? stale4(oym) : ld4(eps + oym);
+      vyp = wyp ? stale4(oyp) : ld4(eps + oyp);
+      vzm = wzm ? stale4(ozm) : ld4(eps + ozm);
+      vzp = wzp ? stale4(ozp) : ld4(eps + ozp);
+    }
+    stored = ec;
+    float left = __shfl_up_sync(FULLMASK, ec.w, 1), right = __shfl_down_sync(FULLMASK, ec.x, 1);
+    if (lane == 0) left = el;
+    if (lane == 31 || lastgrp) right = er;
+    if (!on) return f4zero();
+    return gauss4(o, rr, ec, left, right, vym, vyp, vzm, vzp);
+  }
+  // The same update for the single interior cell (x,y,z) (used at the two ends of a warp's row segment).
+  __device__ __forceinline__ float cell_update(int x, int y, int z) const {
+    const i64 o = off(y, z) + x;
+    auto nb = [&](int d, int dir) -> float {  // stored value of the neighbour, stale across a periodic face
+      const int I[3] = {x, y, z};
+      const int v = I[d] + dir;
+      const bool w = g.per[d] && (v == 0 || v == g.N[d] - 1);
+      const int vv = w ? (v == 0 ? g.N[d] - 2 : 1) : v;
+      const i64 on_ = o + (i64)(vv - I[d]) * g.s[d];
+      return w ? stale1(on_) : eps[on_];
+    };
+    return gauss1(o, r[o], nb(0, -1), nb(0, 1), nb(1, -1), nb(1, 1), nb(2, -1), nb(2, 1));
+  }
+  // The field after the kernel's first half-sweep (the B colour moves in f_gs_b and f_gs_c) on the interior row (y,z):
+  // stored value on A lanes, recomputed update on B lanes.
+  __device__ __forceinline__ float4 after_first(int y, int z) const {
+    float4 st;
+    const float4 up = row_update(y, z, st);
+    return select_A(first_is_A(x0, y, z), st, up);
+  }
+};
+
+// f_gs_a: ϵ⁰ = r·iD everywhere; A cells take sweep 1 (their neighbours are ϵ⁰, stale and fresh coincide).
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+                                                   float* __restrict__ eps, int zchunk) {
+  const Frame f = make_frame(g, zchunk);
+  const Gs<UNI> G(g, c, eps, r, f);
+  SField F;
+  F.q = r;
+  F.w = c.iD;
+  F.s = c.iDc;
+  F.kind = UNI ? 1 : 2;
+  march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& e, float left, float right, const float4& ym, const float4& yp, const float4& zm,
+                      const float4& zp) {
+    if (f.on) {
+      const float4 up = G.gauss4(o, ld4(r + o), e, left, right, ym, yp, zm, zp);
+      st4(eps + o, select_A(first_is_A(f.x0, f.y, z), up, e));
+    }
+  });
+}
+
+// f_gs_half: one red/black half-sweep (src/Poisson.jl:145) in place: the cells with (x+y+z) ≡ k₀ (mod 2) move.  In-place is race-free:
+// a moving cell reads only cells of the other colour (or stale r·iD across periodic faces), which nobody writes in this launch; the
+// vector store rewrites the other colour's lanes with the values just loaded.
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+                                                      float* eps, int k0, int zchunk) {
+  const Frame f = make_frame(g, zchunk);
+  const Gs<UNI> G(g, c, eps, r, f);
+  const int y = min(f.y, g.N[1] - 2);
+  const bool moveA = (k0 & 1) != 0;
+  for (int z = f.z0; z < f.z1; z++) {
+    float4 st;
+    const float4 up = G.row_update(y, z, st);
+    if (f.on) {
+      const bool firstA = first_is_A(f.x0, y, z);
+      // select_A(firstA, a, b): A lanes from a, B lanes from b
+      st4(eps + G.off(y, z) + f.x0, moveA ? select_A(firstA, up, st) : select_A(firstA, st, up));
     }
   }
 }
