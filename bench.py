@@ -35,22 +35,33 @@ WORKLOADS = {
     "sphere128": dict(kind="sphere", dims=(128, 64, 64)),
 }
 
-# Algorithmic bytes per launch and ghost-padded fine cell for each kernel (general variable-coefficient forms):
-# every field read once / written once per launch (perfect halo reuse) — DESIGN.md §kernels.  4 B words.
+# Algorithmic 4-byte words per launch and ghost-padded cell of the level the launch runs on, every field read once / written once
+# (perfect halo reuse) — DESIGN.md §kernels.  (general variable-coefficient form, uniform-coefficient form)
 ALG_WORDS = {
-    "k_conv_bdim1": 12,    # read u(3) [+u⁰(3) in the corrector: 12, predictor 9 → mean 10.5, quoted at 12], V(3); write f(3)
-    "k_bdim2": 24,         # read f3 V3 μ₀3 μ₁9 (+u3 corrector); write u3
-    "k_div_residual": 12,  # read u3 p L3 D iD; write z x r
-    "k_resid_fix": 2,
-    "k_jacobi": 9,         # read r iD L3 D x; write r' x
-    "k_restrict": 1.125,
-    "k_gs_init": 3,
-    "k_gs_sweep": 5,       # half the cells: r .5 iD .5 ϵ .5+.5 L 3
-    "k_increment": 9,      # read ϵ L3 D r x; write r x
-    "k_prolong_inc": 8.125,
-    "k_correct": 11,       # read x L3 u3; write u3 p
-    "k_cfl": 4,
+    "fm_conv": (10.5, 7.5),        # general: read u/u⁰ 3(+3 corrector) V 3, write f 3; uniform: read u⁰ 3 (+u 3 corrector), write u 3
+    "k_conv_bdim1": (10.5, 10.5),
+    "k_bdim2": (22.5, 22.5),       # read f3 V3 μ₀3 μ₁9 (+u3 corrector); write u3
+    "k_f_lowghost": (0, 0),
+    "f_div_residual": (12, 6),     # read u3 p [L3 D iD]; write x r [z]
+    "k_div_residual": (12, 12),
+    "f_resid_fix": (1, 1),
+    "k_resid_fix": (1, 1),
+    "f_jacobi": (9.125, 4.125),    # read r x [iD L3 D]; write r' x (+ coarse r 1/8)
+    "k_jacobi": (9, 9),
+    "k_restrict": (1.125, 1.125),
+    "f_gs_a": (6, 2),              # read r [iD L3]; write ϵ
+    "f_gs_half": (7, 3),           # read ϵ r [iD L3]; write ϵ
+    "k_gs_init": (3, 3),
+    "k_gs_sweep": (5, 5),
+    "f_increment": (9, 5),         # read ϵ r x [L3 D]; write r x   (prolongation source: ϵ costs 1/8)
+    "k_increment": (9, 9),
+    "k_prolong_inc": (8.125, 8.125),
+    "f_correct": (11, 8),          # read x u3 [L3]; write u3 p
+    "k_correct": (11, 11),
+    "f_cfl": (4, 3),               # read u3 [write σ]
+    "k_cfl": (4, 4),
 }
+MULTILEVEL = {"f_jacobi", "k_jacobi", "k_restrict", "f_gs_a", "f_gs_half", "k_gs_init", "k_gs_sweep", "f_increment", "k_increment", "k_prolong_inc"}
 
 
 def peaks():
@@ -234,41 +245,49 @@ def main():
     fl.set_profiling(False)
     peak, peak_src = peaks()
     padded = int(np.prod([d + 2 for d in case["dims"]]))
-    top = max(tim.items(), key=lambda kv: kv[1][1])
-    # launches of a kernel run on every multigrid level; the finest level carries 1/(1+1/7) of the cells, so the
-    # per-launch average is dominated by it — attribute achieved bandwidth on the finest-level launches only when the
-    # kernel is level-independent (conv, bdim, correct, div_residual, cfl); otherwise scale cells by the level sum.
-    ksum = {}
+    import ctypes as C2
+    uni = C2.c_int(0)
+    check(fl.L, fl.L.wl_is_const_coeff(fl.h, C2.byref(uni)))
+    uni = bool(uni.value)
+    lv = sim.pois.nlevels
+    cells_lvl = [int(np.prod(sim.pois.level_dims(l))) for l in range(lv)]
     tot_ms = sum(v[1] for v in tim.values())
-    for k, (c, m) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
-        ksum[k] = {"launches": c, "ms": round(m, 3), "share": round(m / tot_ms, 4)}
-    name = top[0]
-    words = ALG_WORDS.get(name)
-    roof = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
-    multilevel = name in ("k_jacobi", "k_restrict", "k_gs_init", "k_gs_sweep", "k_increment", "k_prolong_inc")
-    if words:
-        lv = sim.pois.nlevels
-        if multilevel:
-            # total cells touched per V-cycle sweep over all levels ≈ padded·Σ 8^-l; per-launch average over levels
-            cells_all = sum(int(np.prod(sim.pois.level_dims(l))) for l in range(lv))
-            per_launch_bytes = words * 4 * cells_all / lv
-        else:
-            per_launch_bytes = words * 4 * padded
-        avg_s = top[1][1] / top[1][0] * 1e-3
-        ach = per_launch_bytes / avg_s / 1e9
-        roof.update(achieved=round(ach, 1), frac=round(ach / peak, 4), alg_bytes_per_launch=int(per_launch_bytes), avg_launch_us=round(avg_s * 1e6, 2))
-    # whole-step roofline with the SURVEY §8d formula (general coefficients: NoBody 264+120·n_V, body 468+120·n_V B/cell/step)
-    b_alg = (468 if case["body"] else 264) + 120 * n_v
+    ksum = {}
+    for k, (cnt, m) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
+        ent = {"launches": cnt, "ms": round(m, 3), "share": round(m / tot_ms, 4)}
+        words = ALG_WORDS.get(k)
+        if words and words[1 if uni else 0] > 0:
+            w = words[1 if uni else 0]
+            # a multigrid kernel is launched once per level per call: its launches cover Σ_l cells_l per `lv` launches
+            per_launch = w * 4 * (sum(cells_lvl) / lv if k in MULTILEVEL else padded)
+            ach = per_launch / (m / cnt * 1e-3) / 1e9
+            ent.update(alg_bytes_per_launch=int(per_launch), achieved_gbs=round(ach, 1), frac=round(ach / peak, 4))
+        ksum[k] = ent
+    name = next(iter(ksum))  # dominant kernel = largest share of device time
+    top = ksum[name]
+    roof = {"bound": "hbm", "kernel": name, "achieved": top.get("achieved_gbs"), "peak": peak, "unit": "GB/s", "frac": top.get("frac"),
+            "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": top.get("alg_bytes_per_launch"),
+            "avg_launch_us": round(top["ms"] / top["launches"] * 1e3, 2),
+            "note": "achieved = algorithmic bytes per launch / CUDA-event time on the library stream, averaged over the launches of the timed steps "
+                    "(multigrid kernels: averaged over the levels they run on)"}
+    if name == "fm_conv":
+        roof["note"] += "; fm_conv is FP32-issue-bound (≈900 instructions per cell for 15 QUICK flux evaluations), not HBM-bound: see DESIGN.md"
+    # whole-step roofline with the SURVEY §8d formulas
+    if uni:
+        b_alg, formula = 200 + 56 * n_v, "uniform-coefficient (no body, periodic): 200 + 56·n_V B/cell/step (SURVEY.md §8d)"
+    else:
+        b_alg = (468 if case["body"] else 264) + 120 * n_v
+        formula = "general coefficients: %d + 120·n_V B/cell/step (SURVEY.md §8d)" % (468 if case["body"] else 264)
     step_ach = b_alg * padded / (ms * 1e-3 / args.steps) / 1e9
     roof["step"] = {"alg_bytes_per_cell": round(b_alg, 1), "n_V": round(n_v, 3), "achieved": round(step_ach, 1), "frac": round(step_ach / peak, 4),
-                    "formula": "general coefficients, SURVEY.md §8d"}
+                    "formula": formula}
 
     line = {"metric": METRIC, "value": round(ns_cell, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "dims": list(case["dims"]), "periodic": list(case["perdir"]), "body": bool(case["body"]),
                        "poisson_iters_per_step": round(n_v, 3), "l2_flush": "state (%.1f GB) exceeds L2" % (padded * 32 * 4 / 1e9),
-                       "kernels": "general variable-coefficient"},
+                       "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient"},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "kernel_times": ksum}
 
     # ---- end to end through the host API: host u0 → Simulation → K × sim_step (+Δt readback) → u,p to host ----

@@ -139,6 +139,9 @@ int wl_time(wl_handle* h, double* t);
 int wl_set_profiling(wl_handle* h, int enabled);
 int wl_get_timings(wl_handle* h, char* buf, int* len);
 
+/* Device self-test: number of Float32 bit patterns (of all 2^32) for which the kernels' division-free x/6 differs from IEEE x/6. */
+int wl_selftest_div6(uint64_t* nbad);
+
 int wl_sync(wl_handle* h);
 /* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
 int wl_launch_count(wl_handle* h, int64_t* count);

@@ -241,3 +241,13 @@ def test_pcg_smoother_and_single_level_step():
         s.flow.L.wl_mom_step(s.flow.h)
     assert np.abs(np.asarray(o.iters, int) - np.asarray(s.pois.n, int)).max() <= 1
     assert rel_l2(s.flow.u, o.field("u")) < 1e-4
+
+
+def test_div6_is_ieee_division_for_all_floats():
+    """The flux kernels evaluate quick's (5c+2d-u)/6 with two FMAs instead of a division; the device checks all 2^32 inputs."""
+    import ctypes as C
+    import wl_b200 as wl
+    L = wl.load_library()
+    n = C.c_uint64(1)
+    wl.lib.check(L, L.wl_selftest_div6(C.byref(n)))
+    assert n.value == 0

@@ -1103,6 +1103,19 @@ int wl_launch_count(wl_handle* h, int64_t* count) {
   return 0;
 }
 
+int wl_selftest_div6(uint64_t* nbad) {
+  if (!nbad) return fail("null argument");
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+  k_selftest_div6<<<148 * 16, 256>>>(d);
+  unsigned long long v = 0;
+  CK(cudaMemcpy(&v, d, sizeof v, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+  *nbad = v;
+  return 0;
+}
+
 int wl_set_profiling(wl_handle* h, int enabled) {
   if (!h) return fail("null handle");
   h->prof = enabled != 0;

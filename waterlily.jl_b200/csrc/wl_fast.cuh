@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     }
     __syncthreads();
     // which directions contribute to this cell (all for interior cells; upper ghost rows only get the others)
-    const bool ax = x <= g.N[0] - 2, ay = y <= g.N[1] - 2, az = z <= g.N[2] - 2;
+    const bool ax = FUSE || x <= g.N[0] - 2, ay = FUSE || y <= g.N[1] - 2, az = FUSE || z <= g.N[2] - 2;
     float Fxlo[3], Fxhi[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) Fxlo[i] = flux(i, 0, 0, 0, 0);
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     for (int i = 0; i < 3; i++) Fxhi[i] = __shfl_down_sync(FULLMASK, Fxlo[i], 1);
     if (lane == 31 || x == XM) {
 #pragma unroll
-      for (int i = 0; i < 3; i++) Fxhi[i] = (x + 1 <= g.N[0] - 1) ? flux(i, 0, 1, 0, 0) : 0.f;
+      for (int i = 0; i < 3; i++) Fxhi[i] = (FUSE || x + 1 <= g.N[0] - 1) ? flux(i, 0, 1, 0, 0) : 0.f;
     }
     if (!haveFz) {
 #pragma unroll
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
       haveFz = true;
     }
     float Fzhi[3] = {0.f, 0.f, 0.f};
-    if (z + 1 <= g.N[2] - 1) {
+    if (FUSE || z + 1 <= g.N[2] - 1) {
 #pragma unroll
       for (int i = 0; i < 3; i++) Fzhi[i] = flux(i, 2, 0, 0, 1);
     }

@@ -98,6 +98,7 @@ def load_library(fmad=False):
         "wl_is_const_coeff": [H, C.POINTER(C.c_int)],
         "wl_stream": [H, C.POINTER(C.c_void_p)],
     }
+    sig["wl_selftest_div6"] = [C.POINTER(C.c_uint64)]
     for name, args in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
         fn.argtypes = args
