@@ -74,6 +74,15 @@ int wl_device_count(void);
 int wl_create(const wl_config* cfg, wl_handle** out);
 int wl_destroy(wl_handle* h);
 
+/* Multi-GPU (new functionality; the reference has none, README.md:155): the domain is decomposed into z slabs, one process per
+ * GPU.  Rank 0 obtains a 128-byte NCCL id with wl_dist_unique_id and the host broadcasts it (torch.distributed, MPI, …); every
+ * rank then calls wl_create_dist with the GLOBAL configuration.  Each rank owns dims[3]/nranks planes (an even number >= 4);
+ * wl_upload / wl_download move the rank's own slab, ghost planes included: shape (N1, N2, dims[3]/nranks + 2[, ncomp]).
+ * Ghost planes are exchanged by ncclSend/ncclRecv over NVLink, the scalar reductions by ncclAllReduce, and multigrid levels
+ * with fewer than 4 planes per rank are replicated on every rank (ncclAllGather of the restricted residual). */
+int wl_dist_unique_id(void* id128);
+int wl_create_dist(const wl_config* cfg, int rank, int nranks, const void* nccl_id128, wl_handle** out);
+
 /* Array accessors replacing direct reads/writes of flow.u, flow.p, flow.σ, flow.f, flow.V, flow.μ₀, flow.μ₁
  * (src/Flow.jl:116-124; used by Metrics/JLD2/VTK extensions).  Buffers hold ncomp*ΠN floats in the reference layout. */
 int wl_upload(wl_handle* h, int field, const float* src, int src_is_device);

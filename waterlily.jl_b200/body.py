@@ -117,20 +117,21 @@ def mu1_kernel(d, eps):
     return (e * _kern1(np.clip(d / e, F(-1), F(1)))).astype(F)
 
 
-def _loc(N, i):
-    """Coordinate arrays of loc(i,I) for every cell (src/core.jl:177); i=-1 gives cell centres.  C-order shapes."""
+def _loc(N, i, zoff=0):
+    """Coordinate arrays of loc(i,I) for every cell (src/core.jl:177); i=-1 gives cell centres.  C-order shapes.
+    `zoff` = global index of the local plane 0 (z-slab decomposition)."""
     D = len(N)
     shape = tuple(reversed(N))
     out = []
     for d in range(D):
-        idx = np.arange(1, N[d] + 1, dtype=F) - F(1.5) - (F(0.5) if d == i else F(0))
+        idx = np.arange(1, N[d] + 1, dtype=F) + F(zoff if d == 2 else 0) - F(1.5) - (F(0.5) if d == i else F(0))
         sh = [1] * D
         sh[D - 1 - d] = N[d]
         out.append(np.broadcast_to(idx.reshape(sh), shape))
     return out
 
 
-def measure_body(N, body, eps=1.0):
+def measure_body(N, body, eps=1.0, zoff=0):
     """measure!(flow,body;ϵ) for a static AutoBody (src/Body.jl:28-51 + src/AutoBody.jl:29-37) before the two BC!
     calls (those run on the device).  N = ghost-padded sizes.  Returns (mu0[D,...], mu1[D*D,...], V[D,...], sigma[...])
     in C order (component slowest, x fastest); μ₁[I,i,j] is component i + D*j."""
@@ -143,13 +144,13 @@ def measure_body(N, body, eps=1.0):
     sigma = np.zeros(shape, F)
     d2 = F((F(2) + eps) ** 2)
     inner = tuple(slice(1, -1) for _ in range(D))
-    xc = [c[inner] for c in _loc(N, -1)]
+    xc = [c[inner] for c in _loc(N, -1, zoff)]
     sig_in = np.asarray(body.sdf(xc), F)
     sigma[inner] = sig_in
     band = sig_in * sig_in < d2
     inside_far = (~band) & (sig_in < 0)
     for i in range(D):
-        xf = [c[inner][band] for c in _loc(N, i)]
+        xf = [c[inner][band] for c in _loc(N, i, zoff)]
         d = np.asarray(body.sdf(xf), F)
         near = ~(d * d > d2)  # measure(): skip n when d² > fastd²
         g = [np.asarray(c, F) for c in body.grad(xf)]

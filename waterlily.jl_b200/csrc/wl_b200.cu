@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/wl_b200.h"
+#include "wl_dist.h"
 #include "wl_fast.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -38,6 +39,13 @@ static int fail(const char* fmt, ...) {
     if (r_) return r_;       \
   } while (0)
 
+static NcclApi g_nccl;
+#define NCK(call)                                                                               \
+  do {                                                                                          \
+    int r_ = (call);                                                                            \
+    if (r_ != 0) return fail("%s:%d NCCL %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
 enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4, SLOT_RHO = 5, SLOT_SIG = 6, SLOT_LINF = 7, SLOT_UNI = 8, SLOT_PHIMAX = 9, SLOT_CFLINT = 10, NSLOTS = 16 };
 
 struct Level {
@@ -48,6 +56,10 @@ struct Level {
   bool fast = false;     // march kernels apply (3-D, interior x size a multiple of 4)
   bool fullc = false;    // built from the finer level by coarsening all three directions
   float Lc[3] = {1.f, 1.f, 1.f};  // uniform face coefficients (valid when the handle is in uniform mode)
+  // multi-GPU: slab = this level is z-decomposed like level 0; otherwise every rank holds the whole level (coarse levels)
+  bool slab = false;
+  int Ng2 = 0;   // global N[2] of the level
+  int zoffc = 0; // first replicated level only: global coarse plane offset of this rank's restriction (rank·nzl_fine/2)
   Coef coef(bool uni) const {
     Coef k;
     k.L = L;
@@ -122,6 +134,9 @@ struct wl_handle {
   std::vector<int16_t> iters;
   std::vector<float> log;  // rows of (iter, rinf, r2, omega)
   bool logging = false;
+  Dist dist;
+  float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
+  int perz_global = 0;
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
   cudaStream_t st = nullptr;
@@ -159,6 +174,8 @@ static Grid make_grid(int D, const int* N, const int* per) {
   g.s[1] = g.px;
   g.s[2] = (i64)g.px * g.N[1];
   g.sc = (i64)g.px * g.N[1] * g.N[2];
+  g.zopen[0] = g.zopen[1] = g.zstale[0] = g.zstale[1] = 0;
+  g.zoff = 0;
   return g;
 }
 
@@ -198,6 +215,80 @@ static int dalloc(wl_handle* h, float** p, size_t nfloats) {
 
 static const float* dtp(wl_handle* h) { return h->d_dthist + (h->dt_dev_len - 1); }
 
+// ---- z-slab halo exchange and collectives (NCCL over NVLink) ---------------------------------
+// Ghost planes of a field on a slab level: my top interior plane → the upper neighbour's lower ghost plane, my bottom interior
+// plane → the lower neighbour's upper ghost plane.  Sends/receives to one peer are posted in matching order (P = 2 periodic).
+static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
+  if (!h->dist.on() || !l.slab) return 0;
+  const Grid& g = l.g;
+  const size_t cnt = (size_t)g.s[2];
+  const Dist& d = h->dist;
+  prof_begin(h, "halo_exchange");
+  NCK(g_nccl.GroupStart());
+  for (int c = 0; c < ncomp; c++) {
+    float* b = a + (size_t)c * g.sc;
+    if (d.up >= 0) NCK(g_nccl.Send(b + g.s[2] * (g.N[2] - 2), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+    if (d.down >= 0) NCK(g_nccl.Send(b + g.s[2] * 1, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    if (d.down >= 0) NCK(g_nccl.Recv(b, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    if (d.up >= 0) NCK(g_nccl.Recv(b + g.s[2] * (g.N[2] - 1), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+  }
+  NCK(g_nccl.GroupEnd());
+  prof_end(h);
+  return 0;
+}
+// Velocity halo: two planes per side (QUICK reads I-2δ … I+δ, src/Flow.jl:8); the second plane lands in h->uext.
+static int exch_u(wl_handle* h, float* u) {
+  if (!h->dist.on()) return 0;
+  const Grid& g = h->g;
+  const size_t cnt = (size_t)g.s[2];
+  const Dist& d = h->dist;
+  prof_begin(h, "halo_exchange_u");
+  NCK(g_nccl.GroupStart());
+  for (int c = 0; c < 3; c++) {
+    float* b = u + (size_t)c * g.sc;
+    float* elo = h->uext + (size_t)c * g.s[2];
+    float* ehi = h->uext + (size_t)(3 + c) * g.s[2];
+    if (d.up >= 0) {
+      NCK(g_nccl.Send(b + g.s[2] * (g.N[2] - 2), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+      NCK(g_nccl.Send(b + g.s[2] * (g.N[2] - 3), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+    }
+    if (d.down >= 0) {
+      NCK(g_nccl.Send(b + g.s[2] * 1, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+      NCK(g_nccl.Send(b + g.s[2] * 2, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    }
+    if (d.down >= 0) {
+      NCK(g_nccl.Recv(b, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+      NCK(g_nccl.Recv(elo, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    }
+    if (d.up >= 0) {
+      NCK(g_nccl.Recv(b + g.s[2] * (g.N[2] - 1), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+      NCK(g_nccl.Recv(ehi, cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+    }
+  }
+  NCK(g_nccl.GroupEnd());
+  prof_end(h);
+  return 0;
+}
+// In-place all-reduce of one reduction slot (double) across the ranks, on the compute stream.
+static int allreduce_slot(wl_handle* h, int slot, int op) {
+  if (!h->dist.on()) return 0;
+  prof_begin(h, "allreduce");
+  NCK(g_nccl.AllReduce(h->red.out + slot, h->red.out + slot, 1, WL_NCCL_DOUBLE, op, h->dist.comm, h->st));
+  prof_end(h);
+  return 0;
+}
+// Gather the interior planes of a replicated level's field from the ranks that each restricted their own slab into it.
+static int allgather_planes(wl_handle* h, const Level& lc, float* a, int planes_per_rank) {
+  if (!h->dist.on()) return 0;
+  const Grid& g = lc.g;
+  const size_t cnt = (size_t)g.s[2] * planes_per_rank;
+  float* base = a + g.s[2];  // plane 1
+  prof_begin(h, "allgather");
+  NCK(g_nccl.AllGather(base + cnt * h->dist.rank, base, cnt, WL_NCCL_FLOAT, h->dist.comm, h->st));
+  prof_end(h);
+  return 0;
+}
+
 // ---- boundary conditions ------------------------------------------------------------------
 static void launch_bc_vec(wl_handle* h, const Grid& g, float* a, const float* U, int saveexit, const float* keep_src) {
   // planes are at most max(N)² cells; one launch covers all 3·D planes (blockIdx.z)
@@ -220,26 +311,55 @@ static void launch_perbc(wl_handle* h, const Grid& g, float* a) {
   else
     LAUNCH(h, k_perbc<2>, gr, b, g, a);
 }
-static void launch_exitbc(wl_handle* h, float* u, const float* u0, float dt_scale) {
+static int launch_exitbc(wl_handle* h, float* u, const float* u0, float dt_scale) {
   const Grid& g = h->g;
   dim3 b = g.D == 3 ? dim3(16, 16, 1) : dim3(256, 1, 1);
   dim3 gr(cdiv(g.N[1] - 2, b.x), g.D == 3 ? cdiv(g.N[2] - 2, b.y) : 1, 1);
-  for (int stage = 0; stage < 3; stage++) LAUNCH_D(h, k_exitbc, gr, b, g, u, u0, dtp(h), dt_scale, h->red, SLOT_EXIT0, stage);
+  // length(exitR): the whole y-z face, over all slabs
+  const float len = g.D == 3 ? (float)((i64)(g.N[1] - 2) * (h->cfg.n[2])) : (float)(g.N[1] - 2);
+  for (int stage = 0; stage < 3; stage++) {
+    LAUNCH_D(h, k_exitbc, gr, b, g, u, u0, dtp(h), dt_scale, h->red, SLOT_EXIT0, stage, len);
+    if (stage < 2) TRY(allreduce_slot(h, SLOT_EXIT0 + stage, WL_NCCL_SUM));
+  }
+  return 0;
 }
 
 // ---- Poisson hierarchy ---------------------------------------------------------------------
 static inline bool divisible(int N) { return N % 2 == 0 && N > 4; }  // src/MultiLevelPoisson.jl:52
 
+// Local grid of a z-slab level: nz/P interior planes, ghost planes fed by the neighbours (zopen), stale marks on the global
+// periodic boundary, no local wrap in z.
+static Grid slab_grid(const wl_handle* h, const Grid& gg) {
+  const Dist& d = h->dist;
+  const int nzl = (gg.N[2] - 2) / d.P;
+  int N[3] = {gg.N[0], gg.N[1], nzl + 2};
+  int per[3] = {gg.per[0], gg.per[1], 0};
+  Grid g = make_grid(3, N, per);
+  g.zopen[0] = d.down >= 0;
+  g.zopen[1] = d.up >= 0;
+  g.zstale[0] = h->perz_global && d.rank == 0;
+  g.zstale[1] = h->perz_global && d.rank == d.P - 1;
+  g.zoff = d.rank * nzl;
+  return g;
+}
+
 static int build_levels(wl_handle* h) {
-  Level l0;
-  l0.g = h->g;
-  l0.L = h->mu0;
-  l0.z = h->sigma;
-  h->levels.push_back(l0);
+  // the hierarchy of the GLOBAL domain (src/MultiLevelPoisson.jl:68-72) …
+  std::vector<Level> gl;
+  {
+    Level l0;
+    int N[3], per[3];
+    for (int d = 0; d < 3; d++) {
+      N[d] = d < h->D ? h->cfg.n[d] + 2 : 1;
+      per[d] = h->cfg.perdir[d];
+    }
+    l0.g = make_grid(h->D, N, per);
+    gl.push_back(l0);
+  }
   if (h->cfg.pois_kind == WL_POIS_MULTILEVEL) {
     const int maxlevels = 10;
-    while ((int)h->levels.size() <= maxlevels) {  // src/MultiLevelPoisson.jl:70-72
-      const Grid& gf = h->levels.back().g;
+    while ((int)gl.size() <= maxlevels) {
+      const Grid& gf = gl.back().g;
       bool any = false;
       int N[3];
       Level lc;
@@ -253,7 +373,7 @@ static int build_levels(wl_handle* h) {
       lc.g = make_grid(gf.D, N, gf.per);
       lc.ownL = lc.ownz = true;
       lc.fullc = gf.D == 3 && lc.c[0] && lc.c[1] && lc.c[2];
-      const Level& fl = h->levels.back();
+      const Level& fl = gl.back();
       for (int d = 0; d < gf.D; d++) {  // restrictL of a uniform field: Σ over the transverse fine faces, /2 if the normal is coarsened
         float v = fl.Lc[d];
         for (int j = 0; j < gf.D; j++)
@@ -261,14 +381,40 @@ static int build_levels(wl_handle* h) {
         if (lc.c[d]) v /= 2.f;
         lc.Lc[d] = v;
       }
-      h->levels.push_back(lc);
+      gl.push_back(lc);
     }
-    if (h->levels.size() <= 2) return fail("MultiLevelPoisson requires size=a2^n, where n>2");
+    if (gl.size() <= 2) return fail("MultiLevelPoisson requires size=a2^n, where n>2");
+  }
+  // … decomposed into z slabs while a rank keeps at least 4 (and an even number of) planes; coarser levels are replicated
+  const int P = h->dist.P;
+  for (size_t i = 0; i < gl.size(); i++) {
+    Level l = gl[i];
+    l.Ng2 = l.g.N[2];
+    if (P > 1) {
+      const int nz = l.g.N[2] - 2;
+      const bool prev = i == 0 || h->levels[i - 1].slab;
+      l.slab = prev && nz % P == 0 && nz / P >= 4 && (nz / P) % 2 == 0 && (i == 0 || l.c[2]);
+      if (i == 0 && !l.slab) return fail("z-slab decomposition needs dims[3]=%d divisible by %d ranks with an even number (>=4) of planes each", nz, P);
+      if (l.slab) {
+        l.g = slab_grid(h, gl[i].g);
+      } else if (i > 0 && h->levels[i - 1].slab) {
+        if (!l.fullc) return fail("semi-coarsening across the slab/replicated level transition is not supported");
+        l.zoffc = h->dist.rank * ((h->levels[i - 1].g.N[2] - 2) / 2);
+      }
+    }
+    if (i == 0) {
+      l.L = h->mu0;
+      l.z = h->sigma;
+      l.g = h->g;
+      l.g.D = h->D;
+    }
+    h->levels.push_back(l);
   }
   for (size_t i = 0; i < h->levels.size(); i++) {
     Level& l = h->levels[i];
     const size_t n = l.cells();
     l.fast = l.g.D == 3 && (l.g.N[0] - 2) % 4 == 0 && l.g.N[2] > 3;
+    if (l.slab && !l.fast) return fail("z-slab levels need the march kernels: interior x size must be a multiple of 4 (level %zu)", i);
     if (l.ownL) TRY(dalloc(h, &l.L, n * l.g.D));
     if (l.ownz) TRY(dalloc(h, &l.z, n));
     TRY(dalloc(h, &l.Dg, n));
@@ -288,16 +434,29 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
     dim3 b = blk(h->D);
     if (i > 0) {
       const Level& fl = h->levels[i - 1];
-      LAUNCH_D(h, k_restrictL, grd(l.inside(), b), b, l.g, fl.g, l.inside(), l.L, (const float*)fl.L, l.c[0], l.c[1], l.c[2]);
+      Box in = l.inside();
+      const bool transition = h->dist.on() && fl.slab && !l.slab;
+      int planes = 0;
+      if (transition) {  // every rank restricts its own slab into its part of the replicated level, then the parts are gathered
+        planes = (fl.g.N[2] - 2) / 2;
+        in.lo[2] = 1 + l.zoffc;
+        in.n[2] = planes;
+      }
+      LAUNCH_D(h, k_restrictL, grd(in, b), b, l.g, fl.g, in, l.L, (const float*)fl.L, l.c[0], l.c[1], l.c[2], transition ? l.zoffc : 0);
+      if (transition)
+        for (int c = 0; c < h->D; c++) TRY(allgather_planes(h, l, l.L + (size_t)c * l.g.sc, planes));
       launch_bc_vec(h, l.g, l.L, zero, 0, l.L);
     }
+    TRY(exch(h, l, l.L, h->D));
     LAUNCH_D(h, k_set_diag, grd(l.inside(), b), b, l.g, l.inside(), (const float*)l.L, l.Dg, l.iD);
+    TRY(exch(h, l, l.iD, 1));
   }
   // uniform-coefficient specialisation: legal iff no body (μ₀≡1, μ₁≡0, V≡0) and every direction periodic
   h->uni = false;
   const Grid& g = h->g;
-  if (h->D == 3 && g.per[0] && g.per[1] && g.per[2] && !(h->cfg.flags & WL_FLAG_GENERAL_COEFF)) {
+  if (h->D == 3 && g.per[0] && g.per[1] && (g.per[2] || h->perz_global) && !(h->cfg.flags & WL_FLAG_GENERAL_COEFF)) {
     LAUNCH(h, k_check_uniform, dim3(592, 1, 1), dim3(256, 1, 1), (const float*)h->mu0, (const float*)h->mu1, (const float*)h->V, g, h->red, SLOT_UNI);
+    TRY(allreduce_slot(h, SLOT_UNI, WL_NCCL_MAX));
     CK(cudaMemcpyAsync(h->h_out + SLOT_UNI, h->red.out + SLOT_UNI, sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     h->uni = (h->h_out[SLOT_UNI] == 0.0);
@@ -317,33 +476,46 @@ static int read_slot(wl_handle* h, int slot, double* out) {
 }
 
 // GaussSeidelRB!(p;it=4,ω)  src/Poisson.jl:141-148
-static void gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
+static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
   dim3 b = blk(h->D);
   Box in = l.inside();
   if (l.fast && h->fused_gs && (l.g.N[2] - 2) % 2 == 0) {
     // ϵ⁰ + sweep 1, then sweeps 2-4 in place, then increment! (+L₂): five vectorised march launches
     dim3 fb(32, FTY);
     ProlongSrc ps{nullptr, l.g};
+    // (z slabs: the ghost planes of ϵ are refreshed after every half-sweep; across the global periodic boundary the sweeps read
+    //  the stale r·iD from the exchanged ghost plane of r instead)
     if (h->uni) {
       LAUNCH(h, f_gs_a<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, l.zchunk());
-      for (int k0 = 2; k0 <= 4; k0++) LAUNCH(h, f_gs_half<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, k0, l.zchunk());
+      if (exch(h, l, l.eps, 1)) return 1;
+      for (int k0 = 2; k0 <= 4; k0++) {
+        LAUNCH(h, f_gs_half<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, k0, l.zchunk());
+        if (exch(h, l, l.eps, 1)) return 1;
+      }
       LAUNCH(h, (f_increment<true, false>), l.fgrid(), fb, l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2, h->red,
              SLOT_R2);
     } else {
       LAUNCH(h, f_gs_a<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, l.zchunk());
-      for (int k0 = 2; k0 <= 4; k0++) LAUNCH(h, f_gs_half<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, k0, l.zchunk());
+      if (exch(h, l, l.eps, 1)) return 1;
+      for (int k0 = 2; k0 <= 4; k0++) {
+        LAUNCH(h, f_gs_half<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, k0, l.zchunk());
+        if (exch(h, l, l.eps, 1)) return 1;
+      }
       LAUNCH(h, (f_increment<false, false>), l.fgrid(), fb, l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
              h->red, SLOT_R2);
     }
-    return;
+    if (exch(h, l, l.r, 1) || exch(h, l, l.x, 1)) return 1;
+    if (with_l2 && allreduce_slot(h, SLOT_R2, WL_NCCL_SUM)) return 1;
+    return 0;
   }
+  if (l.slab) return fail("z-slab level without the fused Gauss-Seidel path");
   Lvl d = l.dev();
   LAUNCH_D(h, k_gs_init, grd(in, b), b, d, in);
   Box half = in;
   half.n[0] = (in.n[0] + 1) / 2;
   for (int k0 = 1; k0 <= 4; k0++) LAUNCH_D(h, k_gs_sweep, grd(half, b), b, d, in, k0);
   if (l.fast) {
-    ProlongSrc ps{nullptr, l.g};
+    ProlongSrc ps{nullptr, l.g, 0, 0, 0};
     if (h->uni)
       LAUNCH(h, (f_increment<true, false>), l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
              h->red, SLOT_R2);
@@ -352,10 +524,11 @@ static void gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, in
              with_l2, h->red, SLOT_R2);
   } else
     LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, h->red, SLOT_R2);
+  return 0;
 }
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
-// With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; returns true if it was.
-static bool jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse = nullptr) {
+// With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; *fused tells whether it was.
+static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fused_out) {
   dim3 b = blk(h->D);
   Box in = l.inside();
   bool fused = false;
@@ -363,14 +536,27 @@ static bool jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse = nullpt
     fused = coarse && coarse->fullc && l.zchunk() % 2 == 0 && (l.g.N[1] - 2) % 2 == 0 && (l.g.N[2] - 2) % 2 == 0;
     const Grid& gc = fused ? coarse->g : l.g;
     float* rc = fused ? coarse->r : nullptr;
+    const int zoffc = (fused && l.slab && !coarse->slab) ? coarse->zoffc : 0;
     if (h->uni)
-      LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0);
+      LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
+             zoffc);
     else
-      LAUNCH(h, f_jacobi<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0);
-  } else
+      LAUNCH(h, f_jacobi<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
+             zoffc);
+  } else {
+    if (l.slab) return fail("z-slab level without march kernels");
     LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
+  }
   std::swap(l.r, l.r2);
-  return fused;
+  TRY(exch(h, l, l.r, 1));
+  if (fused && h->dist.on()) {
+    if (l.slab && !coarse->slab)
+      TRY(allgather_planes(h, *coarse, coarse->r, (l.g.N[2] - 2) / 2));
+    else
+      TRY(exch(h, *coarse, coarse->r, 1));
+  }
+  if (fused_out) *fused_out = fused;
+  return 0;
 }
 // pcg!(p;it=6)  src/Poisson.jl:166-186 — host-driven (three dots per iteration decide early exits)
 static int pcg(wl_handle* h, Level& l, int it = 6) {
@@ -406,6 +592,7 @@ static int l2_norm(wl_handle* h, Level& l, float* out, int want_max = 0) {
   dim3 b = blk(h->D);
   Box in = l.inside();
   LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, h->red, want_max ? SLOT_LINF : SLOT_R2, want_max);
+  TRY(allreduce_slot(h, want_max ? SLOT_LINF : SLOT_R2, want_max ? WL_NCCL_MAX : WL_NCCL_SUM));
   double v;
   TRY(read_slot(h, want_max ? SLOT_LINF : SLOT_R2, &v));
   *out = (float)v;
@@ -413,10 +600,8 @@ static int l2_norm(wl_handle* h, Level& l, float* out, int want_max = 0) {
 }
 // smooth!(p;ω)  src/MultiLevelPoisson.jl:106
 static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
-  if (h->cfg.smoother == WL_SMOOTH_GSRB) {
-    gs_smooth(h, l, wp, x_is_zero, with_l2);
-    return 0;
-  }
+  if (h->cfg.smoother == WL_SMOOTH_GSRB) return gs_smooth(h, l, wp, x_is_zero, with_l2);
+  if (h->dist.on()) return fail("the pcg smoother is not available with z-slab decomposition");
   if (x_is_zero) CK(cudaMemsetAsync(l.x, 0, l.cells() * sizeof(float), h->st));
   TRY(pcg(h, l));
   if (with_l2) {
@@ -432,22 +617,34 @@ static int vcycle(wl_handle* h, size_t li, const float* wp) {
   Level& coarse = h->levels[li + 1];
   dim3 b = blk(h->D);
   Box cin = coarse.inside();
-  if (!jacobi(h, fine, li > 0, &coarse))
+  bool fused = false;
+  TRY(jacobi(h, fine, li > 0, &coarse, &fused));
+  if (!fused) {
+    if (fine.slab) return fail("z-slab levels need the fused restriction (even sizes, full coarsening)");
     LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
+  }
   const bool last = (li + 2 >= h->levels.size());
   if (!last) TRY(vcycle(h, li + 1, wp));
   TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
   Box fin = fine.inside();
   if (fine.fast && coarse.fullc) {
-    ProlongSrc ps{coarse.x, coarse.g};
+    ProlongSrc ps{coarse.x, coarse.g, 0, 0, 0};
+    if (fine.slab && !coarse.slab) {  // slab level over a replicated level: map local fine planes to global coarse planes
+      ps.zoff = fine.g.zoff;
+      ps.N2g = fine.Ng2;
+      ps.perg = h->perz_global;
+    }
     if (h->uni)
       LAUNCH(h, (f_increment<true, true>), fine.fgrid(), dim3(32, FTY), fine.g, fine.coef(true), (const float*)nullptr, ps, fine.r, fine.x, wp, 0,
              fine.zchunk(), 0, h->red, SLOT_R2);
     else
       LAUNCH(h, (f_increment<false, true>), fine.fgrid(), dim3(32, FTY), fine.g, fine.coef(false), (const float*)nullptr, ps, fine.r, fine.x, wp, 0,
              fine.zchunk(), 0, h->red, SLOT_R2);
-  } else
+  } else {
+    if (fine.slab) return fail("z-slab levels need the march prolongation");
     LAUNCH_D(h, k_prolong_inc, grd(fin, b), b, fine.dev(), coarse.g, (const float*)coarse.x, fin, wp, coarse.c[0], coarse.c[1], coarse.c[2]);
+  }
+  TRY(exch(h, fine, fine.r, 1));
   return 0;
 }
 
@@ -464,7 +661,8 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
   dim3 b = blk(h->D);
   Box in = l.inside();
   float count = 1;
-  for (int d = 0; d < h->D; d++) count *= (float)(l.g.N[d] - 2);
+  for (int d = 0; d < h->D; d++) count *= (float)((d == 2 && l.slab ? l.Ng2 : l.g.N[d]) - 2);
+  if (h->dist.on() && !(l.fast && with_div)) return fail("standalone residual! is not available with z-slab decomposition");
   if (l.fast && with_div) {
     if (h->uni)
       LAUNCH(h, f_div_residual<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
@@ -472,7 +670,10 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
     else
       LAUNCH(h, f_div_residual<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
              l.zchunk(), h->red, SLOT_RSUM);
+    TRY(allreduce_slot(h, SLOT_RSUM, WL_NCCL_SUM));
     LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), h->red, SLOT_RSUM, SLOT_R2);
+    TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
+    TRY(exch(h, l, l.r, 1));
   } else {
     LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
     LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
@@ -555,12 +756,13 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   const int zchunk = std::min(32, ZM);
   dim3 gr(cdiv(XM, 32), cdiv(YM, CTY), cdiv(ZM, zchunk));
   prof_begin(h, "fm_conv");
-  if (g.per[0] && g.per[1] && g.per[2])
+  const bool nowall = g.per[0] && g.per[1] && (g.per[2] || (g.zopen[0] && g.zopen[1]));
+  if (nowall)
     fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                            h->red, SLOT_PHIMAX);
+                                                                            h->red, SLOT_PHIMAX, h->uext);
   else
     fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                             h->red, SLOT_PHIMAX);
+                                                                             h->red, SLOT_PHIMAX, h->uext);
   prof_end(h);
   h->launches++;
 }
@@ -596,6 +798,7 @@ static void momentum(wl_handle* h, int corrector) {
     dim3 pb(32, 8, 1);
     int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
     LAUNCH(h, k_f_lowghost, dim3(cdiv(m0, 32), cdiv(m1, 8), 3), pb, g, (const float*)h->u0, (const float*)h->V, h->f, dtp(h));
+    exch(h, l, h->f, 3);  // BDIM-2 reads f one plane beyond the slab
   } else
     conv_bdim1(h, corrector ? h->u : h->u0, 1);
   LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, corrector);
@@ -606,12 +809,19 @@ static void cfl(wl_handle* h, float* dt_out) {
   Level& l = h->levels[0];
   const Grid& g = h->g;
   if (l.fast) {
+    const int fin = h->dist.on() ? 0 : 1;  // z slabs: the maxima are all-reduced first, then k_cfl_final forms Δt
+    const int sg = h->uni ? SLOT_PHIMAX : SLOT_CFL;
     if (h->uni) {
-      LAUNCH(h, f_cfl<true>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, SLOT_PHIMAX);
+      LAUNCH(h, f_cfl<true>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, sg, fin);
     } else {
       int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
       LAUNCH(h, k_sigma_ghostmax, dim3(cdiv(m0, 32), cdiv(m1, 8), 6), dim3(32, 8, 1), g, (const float*)h->sigma, h->red, SLOT_CFL);
-      LAUNCH(h, f_cfl<false>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, SLOT_CFL);
+      LAUNCH(h, f_cfl<false>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, sg, fin);
+    }
+    if (h->dist.on()) {
+      allreduce_slot(h, SLOT_CFLINT, WL_NCCL_MAX);
+      allreduce_slot(h, sg, WL_NCCL_MAX);
+      LAUNCH(h, k_cfl_final, 1, 1, h->red, SLOT_CFLINT, sg, h->cfg.nu, dt_out);
     }
     return;
   }
@@ -636,6 +846,8 @@ static int project(wl_handle* h, float w) {
   } else
     LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
   launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  TRY(exch_u(h, h->u));
+  TRY(exch(h, l, h->p, 1));
   return 0;
 }
 
@@ -674,11 +886,13 @@ static int mom_step(wl_handle* h) {
   // predictor  src/Flow.jl:190-196
   momentum(h, 0);
   launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u0);
-  if (h->cfg.exitBC) launch_exitbc(h, h->u, h->u0, 1.f);
+  if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
+  TRY(exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
   momentum(h, 1);
   launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  TRY(exch_u(h, h->u));
   TRY(project(h, 0.5f));
   // push!(a.Δt, CFL(a))
   cfl(h, h->d_dthist + h->dt_dev_len);
@@ -728,7 +942,27 @@ int wl_device_count(void) {
   return n;
 }
 
-int wl_create(const wl_config* cfg, wl_handle** out) {
+static int create_impl(const wl_config* cfg, int rank, int nranks, const void* nccl_id, wl_handle** out);
+
+int wl_create(const wl_config* cfg, wl_handle** out) { return create_impl(cfg, 0, 1, nullptr, out); }
+
+int wl_dist_unique_id(void* id128) {
+  if (!id128) return fail("null argument");
+  const char* why = "";
+  if (!g_nccl.load(&why)) return fail("NCCL unavailable: %s", why);
+  ncclUniqueId id;
+  NCK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int wl_create_dist(const wl_config* cfg, int rank, int nranks, const void* nccl_id128, wl_handle** out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
+  if (nranks > 1 && !nccl_id128) return fail("null NCCL id");
+  return create_impl(cfg, rank, nranks, nccl_id128, out);
+}
+
+static int create_impl(const wl_config* cfg, int rank, int nranks, const void* nccl_id, wl_handle** out) {
   if (!cfg || !out) return fail("null argument");
   if (cfg->D != 2 && cfg->D != 3) return fail("D must be 2 or 3 (got %d)", cfg->D);
   for (int d = 0; d < cfg->D; d++)
@@ -749,17 +983,41 @@ int wl_create(const wl_config* cfg, wl_handle** out) {
   int N[3];
   for (int d = 0; d < 3; d++) N[d] = d < cfg->D ? cfg->n[d] + 2 : 1;
   h->g = make_grid(cfg->D, N, cfg->perdir);
+  h->perz_global = cfg->D == 3 && cfg->perdir[2] != 0;
   int rc = 0;
   do {
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
       rc = fail("cudaStreamCreate failed");
       break;
     }
+    if (nranks > 1) {  // z-slab decomposition: one process per GPU, NCCL communicator over all ranks
+      if (cfg->D != 3) { rc = fail("z-slab decomposition needs a 3-D domain"); break; }
+      if (cfg->pois_kind != WL_POIS_MULTILEVEL) { rc = fail("z-slab decomposition supports the MultiLevelPoisson solver only"); break; }
+      const char* why = "";
+      if (!g_nccl.load(&why)) { rc = fail("NCCL unavailable: %s", why); break; }
+      ncclUniqueId id;
+      memcpy(&id, nccl_id, sizeof id);
+      int e = g_nccl.CommInitRank(&h->dist.comm, nranks, id, rank);
+      if (e != 0) { rc = fail("ncclCommInitRank: %s", g_nccl.GetErrorString(e)); break; }
+      h->dist.rank = rank;
+      h->dist.P = nranks;
+      h->dist.up = rank + 1 < nranks ? rank + 1 : (h->perz_global ? 0 : -1);
+      h->dist.down = rank > 0 ? rank - 1 : (h->perz_global ? nranks - 1 : -1);
+      Level tmp;
+      tmp.g = h->g;
+      if ((cfg->n[2] % nranks) != 0 || cfg->n[2] / nranks < 4 || (cfg->n[2] / nranks) % 2) {
+        rc = fail("z-slab decomposition needs dims[3]=%d divisible by %d ranks with an even number (>=4) of planes each", cfg->n[2], nranks);
+        break;
+      }
+      h->g = slab_grid(h, h->g);
+      if ((rc = dalloc(h, &h->uext, (size_t)6 * h->g.s[2]))) break;
+    }
     const size_t n = (size_t)h->g.sc;
     const int D = h->D;
     if ((rc = dalloc(h, &h->u, n * D)) || (rc = dalloc(h, &h->u0, n * D)) || (rc = dalloc(h, &h->f, n * D)) || (rc = dalloc(h, &h->p, n)) ||
         (rc = dalloc(h, &h->sigma, n)) || (rc = dalloc(h, &h->V, n * D)) || (rc = dalloc(h, &h->mu0, n * D)) || (rc = dalloc(h, &h->mu1, n * D * D)))
       break;
+    if (!h->uext && (rc = dalloc(h, &h->uext, 32))) break;
     if ((rc = build_levels(h))) break;
     // reduction buffers
     Box all = h->levels[0].all();
@@ -810,6 +1068,7 @@ int wl_destroy(wl_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->dist.comm) g_nccl.CommDestroy(h->dist.comm);
   for (void* q : h->allocs) cudaFree(q);
   if (h->d_dthist) cudaFree(h->d_dthist);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -824,7 +1083,7 @@ int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
   float* p;
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
-  return copy_in(h, h->g, p, src, nc, src_is_device);
+  return copy_in(h, h->g, p, src, nc, src_is_device);  // z slabs: the caller's slab carries its own ghost planes
 }
 
 int wl_download(wl_handle* h, int field, float* dst, int dst_is_device) {
@@ -841,7 +1100,8 @@ int wl_apply_bc(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
-  launch_exitbc(h, h->u, h->u, 0.f);
+  TRY(launch_exitbc(h, h->u, h->u, 0.f));
+  TRY(exch_u(h, h->u));
   CK(cudaMemcpyAsync(h->u0, h->u, (size_t)h->g.sc * h->D * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
   CK(cudaGetLastError());
   return 0;
@@ -853,6 +1113,9 @@ int wl_measure_bc(wl_handle* h) {
   const float zero[3] = {0, 0, 0};
   launch_bc_vec(h, h->g, h->mu0, zero, 0, h->mu0);
   launch_bc_vec(h, h->g, h->V, zero, h->cfg.exitBC, h->V);
+  TRY(exch(h, h->levels[0], h->mu0, h->D));
+  TRY(exch(h, h->levels[0], h->V, h->D));
+  TRY(exch(h, h->levels[0], h->mu1, h->D * h->D));
   CK(cudaGetLastError());
   return 0;
 }
@@ -908,6 +1171,7 @@ int wl_project(wl_handle* h, float w) {
 
 int wl_conv_diff(wl_handle* h, int from_u0) {
   if (!h) return fail("null handle");
+  if (h->dist.on()) return fail("standalone conv_diff! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
   conv_bdim1(h, from_u0 ? h->u0 : h->u, 0);
   CK(cudaGetLastError());
@@ -925,6 +1189,7 @@ int wl_cfl(wl_handle* h, float* dt_out) {
 
 int wl_pois_mult(wl_handle* h) {
   if (!h) return fail("null handle");
+  if (h->dist.on()) return fail("standalone mult! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
   Level& l = h->levels[0];
   CK(cudaMemsetAsync(l.z, 0, l.cells() * sizeof(float), h->st));
@@ -958,6 +1223,7 @@ int wl_pois_residual(wl_handle* h, float* r2_out) {
 
 int wl_pois_solve(wl_handle* h, int* iters_out) {
   if (!h) return fail("null handle");
+  if (h->dist.on()) return fail("standalone solver! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
   TRY(load_x_from_p(h));
   float r2;
@@ -976,9 +1242,9 @@ int wl_pois_smooth(wl_handle* h, int level, int kind, float omega) {
   Level& l = h->levels[level];
   set_scalar(h, 0, omega);
   if (kind == 0)
-    gs_smooth(h, l, h->d_scal + 0, 0, 0);
+    TRY(gs_smooth(h, l, h->d_scal + 0, 0, 0));
   else if (kind == 1)
-    jacobi(h, l, 0, nullptr);  // reference Jacobi!(p) default ω=1
+    TRY(jacobi(h, l, 0, nullptr, nullptr));  // reference Jacobi!(p) default ω=1
   else
     TRY(pcg(h, l));
   CK(cudaGetLastError());

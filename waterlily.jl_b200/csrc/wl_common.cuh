@@ -21,7 +21,13 @@ struct Grid {
   int xo;      // storage offset of cell i=0 inside a row
   i64 s[3];    // strides in floats: {1, px, px*N1}
   i64 sc;      // component stride = px*N1*N2
-  int per[3];  // periodic flags
+  int per[3];  // periodic flags (LOCAL wrap: in z only when the rank owns the whole periodic extent)
+  // z-slab decomposition (multi-GPU): zopen[side] = the ghost plane of that z face holds the neighbouring rank's interior plane
+  // (refreshed by halo exchange) instead of a wall / local periodic image; zstale[side] = that face is the GLOBAL periodic
+  // boundary, across which GaussSeidelRB! sweeps must see the stale r·iD; zoff = global z index of local plane 0.
+  int zopen[2];
+  int zstale[2];
+  int zoff;
 };
 
 struct Box {

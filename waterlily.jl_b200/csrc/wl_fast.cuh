@@ -208,7 +208,7 @@ __device__ __forceinline__ void march7(const Grid& g, const Frame& f, const SFie
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
-                                                     int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict) {
+                                                     int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
   __shared__ float4 ex[FTY][32];
   const Frame f = make_frame(g, zchunk);
   SField F;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(32 * FTY) f_jacobi(Grid g, Coef c, const float
         acc.y += up.w;
         if (!zlow && f.on) {
           // coarse cell indices: (x0+1)/2, (x0+3)/2 ; (y+1)/2 ; (z+1)/2
-          const i64 oc = (i64)gc.xo + (f.x0 + 1) / 2 + gc.s[1] * ((f.y + 1) / 2) + gc.s[2] * ((z + 1) / 2);
+          const i64 oc = (i64)gc.xo + (f.x0 + 1) / 2 + gc.s[1] * ((f.y + 1) / 2) + gc.s[2] * ((z + 1) / 2 + zoffc);
           rc[oc] = acc.x;
           rc[oc + 1] = acc.y;
         }
@@ -272,6 +272,9 @@ __global__ void __launch_bounds__(32 * FTY) f_jacobi(Grid g, Coef c, const float
 struct ProlongSrc {  // reads ϵ = xc[down(·)] for a fine row segment
   const float* xc;
   Grid gc;
+  // z-slab fine level over a replicated (whole-domain) coarse level: global index of fine plane 0, global fine N2 and whether z is
+  // globally periodic (the replicated level wraps indices itself); all zero when fine and coarse share the decomposition
+  int zoff, N2g, perg;
 };
 
 template <bool UNI, bool PROLONG>
@@ -307,7 +310,14 @@ __global__ void __launch_bounds__(32 * FTY) f_increment(Grid g, Coef c, const fl
     // Prolongation source: a fine group x0..x0+3 (x0 odd) maps to coarse cells cx, cx+1 with cx=(x0+1)/2:
     //   fine x0-1 → cx-1 ; x0,x0+1 → cx ; x0+2,x0+3 → cx+1 ; x0+4 → cx+2   (with the fine periodic wrap applied first)
     const Grid& gc = ps.gc;
-    auto crow = [&](int yf, int zf) -> i64 { return (i64)gc.xo + gc.s[1] * ((yf + 1) / 2) + gc.s[2] * ((zf + 1) / 2); };
+    auto crow = [&](int yf, int zf) -> i64 {
+      int zg = zf + ps.zoff;
+      if (ps.perg) {
+        if (zg == 0) zg = ps.N2g - 2;
+        else if (zg == ps.N2g - 1) zg = 1;
+      }
+      return (i64)gc.xo + gc.s[1] * ((yf + 1) / 2) + gc.s[2] * ((zg + 1) / 2);
+    };
     auto ld2 = [&](i64 rowc) -> float4 {  // ϵ at the lane's 4 fine cells on a coarse row
       const int cx = (f.x0 + 1) / 2;
       const float a = ps.xc[rowc + cx], b = ps.xc[rowc + cx + 1];
@@ -546,10 +556,12 @@ __device__ __forceinline__ float flux_from(float uf, float um2, float um1, float
   return conv - diff;
 }
 
+// PER3 = no walls: every face is periodic (local wrap) or, in z, open to a neighbouring slab.  `uext` holds the second halo
+// planes of ua beyond open z faces: [side][component][plane] (z = -1 and z = N2).
 template <int LAM, bool FUSE, bool PER3>
 __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restrict__ ua, const float* __restrict__ u0, const float* __restrict__ V,
                                                     float* __restrict__ out, float* __restrict__ sigma, const float* __restrict__ dtp, float nu, int zchunk,
-                                                    int corrector, RedBuf R, int slot) {
+                                                    int corrector, RedBuf R, int slot, const float* __restrict__ uext) {
   extern __shared__ float smem_raw[];
   float* const T = smem_raw;  // [CRING][3][CH][CW]
   constexpr int PL = CH * CW;  // one component plane
@@ -585,14 +597,24 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     int slotp = zz % CRING;
     if (slotp < 0) slotp += CRING;
     float* dst = T + slotp * 3 * PL;
-    const i64 pz = g.s[2] * wrap(zz, 2);
+    const float* src = ua;
+    i64 pz = g.s[2] * wrap(zz, 2), cs = g.sc;
+    if (zz < 0 && g.zopen[0]) {  // second halo plane below an open face
+      src = uext;
+      pz = 0;
+      cs = g.s[2];
+    } else if (zz > g.N[2] - 1 && g.zopen[1]) {
+      src = uext + 3 * g.s[2];
+      pz = 0;
+      cs = g.s[2];
+    }
 #pragma unroll
     for (int k = 0; k < NE; k++) {
       if (so[k] >= 0) {
         const i64 o = go[k] + pz;
-        dst[so[k]] = ua[o];
-        dst[PL + so[k]] = ua[o + g.sc];
-        dst[2 * PL + so[k]] = ua[o + 2 * g.sc];
+        dst[so[k]] = src[o];
+        dst[PL + so[k]] = src[o + cs];
+        dst[2 * PL + so[k]] = src[o + 2 * cs];
       }
     }
   };
@@ -607,7 +629,10 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     int variant = 0;
     if (!PER3) {
       const int I[3] = {x + ox, y + oy, zc + oz};
-      if (!g.per[j]) variant = I[j] == 1 ? 1 : (I[j] == g.N[j] - 1 ? 2 : 0);
+      if (!g.per[j]) {
+        const bool walllo = !(j == 2 && g.zopen[0]), wallhi = !(j == 2 && g.zopen[1]);
+        variant = (I[j] == 1 && walllo) ? 1 : ((I[j] == g.N[j] - 1 && wallhi) ? 2 : 0);
+      }
     }
     const int dx = (j == 0), dy = (j == 1), dz = (j == 2);
     const int ix = (i == 0), iy = (i == 1), iz = (i == 2);
@@ -687,15 +712,15 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
       }
       if (FUSE) {
         // periodic images of the stale Φ on upper ghost cells (see header): candidates by T = {k : I_k == 1}
-        const bool t0 = x == 1, t1 = y == 1, t2 = z == 1;
+        const bool t0 = x == 1, t1 = y == 1, t2 = (z + g.zoff) == 1;
         if (t0 || t1) gmax = fmax(gmax, (double)Fz[2]);
         if (t2) gmax = fmax(gmax, (double)F2lo_y);
         if (t2 && t1) gmax = fmax(gmax, (double)Fxlo[2]);
       } else {
-        const bool ghost = x == g.N[0] - 1 || y == g.N[1] - 1 || z == g.N[2] - 1;
+        const bool ghost = x == g.N[0] - 1 || y == g.N[1] - 1 || (z == g.N[2] - 1 && !g.zopen[1]);
         if (ghost) {
           // last Φ written by the reference's (i=D, j) loops: the largest j whose range contains the cell
-          const int lo0 = g.per[0] ? 1 : 2, lo1 = g.per[1] ? 1 : 2, lo2 = g.per[2] ? 1 : 2;
+          const int lo0 = g.per[0] ? 1 : 2, lo1 = g.per[1] ? 1 : 2, lo2 = (g.per[2] || g.zopen[0]) ? 1 : 2;
           if (az && z >= lo2) sigma[o] = Fz[2];
           else if (ay && y >= lo1) sigma[o] = F2lo_y;
           else if (ax && x >= lo0) sigma[o] = Fxlo[2];
@@ -714,6 +739,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
 // f on the lower ghost planes (any index 0): r = 0 there, so f = u⁰ + Δt·0 − V  (src/Flow.jl:178 over CartesianIndices(f))
 __global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f, const float* __restrict__ dtp) {
   const int j = blockIdx.z;  // plane I_j = 0
+  if (j == 2 && g.zopen[0]) return;  // slab-internal face: that plane of f arrives by halo exchange
   const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
   const int t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = blockIdx.y * blockDim.y + threadIdx.y;
   if (t0 >= g.N[da] || t1 >= g.N[db]) return;
@@ -747,7 +773,7 @@ __global__ void __launch_bounds__(256) k_sigma_ghostmax(Grid g, const float* __r
 // combined with the ghost maximum in out[slot_ghost]; the last block stores Δt = min(10, 1/(max+5ν)) to dt_out.
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY) f_cfl(Grid g, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
-                                                  int zchunk, RedBuf R, int slot, int slot_ghost) {
+                                                  int zchunk, RedBuf R, int slot, int slot_ghost, int finalize) {
   const Frame f = make_frame(g, zchunk);
   double m = 0.0;
   for (int z = f.z0; z < f.z1; z++) {
@@ -781,7 +807,7 @@ __global__ void __launch_bounds__(32 * FTY) f_cfl(Grid g, const float* __restric
     }
   }
   double v[1] = {m}, fin[1];
-  if (grid_reduce<RED_MAX, 1>(v, R, slot, fin)) {
+  if (grid_reduce<RED_MAX, 1>(v, R, slot, fin) && finalize) {
     if (threadIdx.x == 0 && threadIdx.y == 0) {
       const float mm = (float)fmax(fin[0], R.out[slot_ghost]);
       *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
@@ -895,9 +921,10 @@ struct Gs {
       if (lane == 0) el = wrapl ? stale1(ro + xl) : eps[ro + xl];
       if (lane == 31 || lastgrp) er = wrapr ? stale1(ro + xr) : eps[ro + xr];
       const bool wym = g.per[1] && y == 1, wyp = g.per[1] && y == g.N[1] - 2;
-      const bool wzm = g.per[2] && z == 1, wzp = g.per[2] && z == g.N[2] - 2;
+      // stale across the global periodic z boundary: a local wrap (per[2]) or, in a z-slab, the exchanged ghost plane of r
+      const bool wzm = (g.per[2] || g.zstale[0]) && z == 1, wzp = (g.per[2] || g.zstale[1]) && z == g.N[2] - 2;
       const i64 oym = off(wym ? g.N[1] - 2 : y - 1, z) + x0, oyp = off(wyp ? 1 : y + 1, z) + x0;
-      const i64 ozm = off(y, wzm ? g.N[2] - 2 : z - 1) + x0, ozp = off(y, wzp ? 1 : z + 1) + x0;
+      const i64 ozm = off(y, (g.per[2] && z == 1) ? g.N[2] - 2 : z - 1) + x0, ozp = off(y, (g.per[2] && z == g.N[2] - 2) ? 1 : z + 1) + x0;
       vym = wym ? stale4(oym) : ld4(eps + oym);
       vyp = wyp ? stale4(oyp) : ld4(eps + oyp);
       vzm = wzm ? stale4(ozm) : ld4(eps + ozm);
@@ -916,8 +943,9 @@ struct Gs {
     auto nb = [&](int d, int dir) -> float {  // stored value of the neighbour, stale across a periodic face
       const int I[3] = {x, y, z};
       const int v = I[d] + dir;
-      const bool w = g.per[d] && (v == 0 || v == g.N[d] - 1);
-      const int vv = w ? (v == 0 ? g.N[d] - 2 : 1) : v;
+      const bool edge = (v == 0 || v == g.N[d] - 1);
+      const bool w = edge && (g.per[d] || (d == 2 && g.zstale[v == 0 ? 0 : 1]));  // stale across a global periodic face
+      const int vv = (edge && g.per[d]) ? (v == 0 ? g.N[d] - 2 : 1) : v;
       const i64 on_ = o + (i64)(vv - I[d]) * g.s[d];
       return w ? stale1(on_) : eps[on_];
     };

@@ -20,7 +20,7 @@ __device__ __forceinline__ float div6(float x) {
   const float r = __fmaf_rn(-6.f, q0, x);
   float q = __fmaf_rn(r, C, q0);
   const float ax = fabsf(x);
-  if (!(ax >= 7.888609052210118e-31f && ax <= 3.0e38f) && ax != 0.f) q = div6_slow(x);  // never taken for physical values
+  if (!(ax >= 7.888609052210118e-31f && ax <= 3.0e38f)) q = (ax == 0.f) ? q0 : div6_slow(x);  // ±0 keeps its sign; the rest is never physical
   return q;
 }
 template <int LAM>
@@ -138,6 +138,10 @@ __global__ void k_bc_vec(Grid g, float* a, const float* keep, float U0, float U1
   const int plane = blockIdx.z;
   const int j = plane / 3, which = plane % 3;
   if (which == 2 && g.per[j]) return;
+  if (D == 3 && j == 2) {  // z faces owned by a neighbouring rank are filled by the halo exchange, not here
+    if ((which == 0 || which == 2) && g.zopen[0]) return;
+    if (which == 1 && g.zopen[1]) return;
+  }
   // plane coordinates: the two (or one) dims other than j
   int I[3] = {0, 0, 0};
   const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +166,9 @@ __global__ void k_bc_vec(Grid g, float* a, const float* keep, float U0, float U1
     bool isconst = false;
 #pragma unroll
     for (int d = D - 1; d >= 0; d--) {
+      if (D == 3 && d == 2 && ((S[2] == 0 && g.zopen[0]) || (S[2] == g.N[2] - 1 && g.zopen[1]) || (S[2] == 1 && g.zopen[0]))) {
+        continue;  // slab-internal z plane: behaves like an interior plane here (its ghost cells arrive by exchange)
+      }
       if (g.per[d]) {
         if (S[d] == 0) S[d] = g.N[d] - 2;
         else if (S[d] == g.N[d] - 1) S[d] = 1;
@@ -222,12 +229,11 @@ __global__ void k_perbc(Grid g, float* __restrict__ a) {
 //  stage 2: u[N-1] −= (mean − U)
 template <int D>
 __global__ void __launch_bounds__(256) k_exitbc(Grid g, float* __restrict__ u, const float* __restrict__ u0, const float* __restrict__ dtp,
-                                                float dt_scale, RedBuf R, int slot, int stage) {
+                                                float dt_scale, RedBuf R, int slot, int stage, float len) {
   int J[3] = {0, 0, 0};
   J[1] = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   J[2] = (D == 3) ? 1 + blockIdx.y * blockDim.y + threadIdx.y : 0;
   const bool ok = J[1] <= g.N[1] - 2 && (D == 2 || J[2] <= g.N[2] - 2);
-  const float len = (D == 3) ? (float)((i64)(g.N[1] - 2) * (g.N[2] - 2)) : (float)(g.N[1] - 2);
   double v[1] = {0.0}, fin[1];
   if (stage == 0) {
     J[0] = 1;
@@ -292,11 +298,12 @@ __global__ void k_set_diag(Grid g, Box box, const float* __restrict__ L, float* 
 
 // restrictL!(a,b,c) interior part (src/MultiLevelPoisson.jl:42-46, :20-26, upL :9-11); BC!(a,0) follows via k_bc_vec.
 template <int D>
-__global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+__global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2, int zoffc) {
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const int c[3] = {c0, c1, c2};
   const i64 o = cell_off(gc, I);
+  if (D == 3) I[2] -= zoffc;  // z slab restricting into a replicated level: local fine planes ↔ global coarse planes
 #pragma unroll
   for (int i = 0; i < D; i++) {
     int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -663,4 +670,10 @@ __global__ void k_selftest_div6(unsigned long long* nbad) {
     if (!same) bad++;
   }
   if (bad) atomicAdd(nbad, bad);
+}
+
+// z slabs: Δt from the all-reduced maxima (the single-GPU path does this in f_cfl's last block)
+__global__ void k_cfl_final(RedBuf R, int slot_a, int slot_b, float nu, float* dt_out) {
+  const float mm = (float)fmax(R.out[slot_a], R.out[slot_b]);
+  *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
 }

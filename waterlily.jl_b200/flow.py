@@ -19,10 +19,18 @@ _FIELDS = {"u": 0, "u0": 1, "f": 2, "p": 3, "sigma": 4, "V": 5, "mu0": 6, "mu1":
 _LVL = {"L": 0, "D": 1, "iD": 2, "x": 3, "eps": 4, "r": 5, "z": 6}
 
 
-def loc_grid(N, i):
+def loc_grid(N, i, zoff=0):
     """loc(i,I) for all cells of a ghost-padded grid (src/core.jl:177): list of D broadcastable coordinate arrays."""
     from .body import _loc
-    return _loc(N, i)
+    return _loc(N, i, zoff)
+
+
+def dist_unique_id(fmad=False):
+    """128-byte NCCL id for wl_create_dist; rank 0 calls this and broadcasts the bytes to the other ranks."""
+    L = _lib.load_library(fmad)
+    buf = C.create_string_buffer(128)
+    _lib.check(L, L.wl_dist_unique_id(buf))
+    return buf.raw
 
 
 class Flow:
@@ -31,7 +39,7 @@ class Flow:
     function u0(i, x) evaluated on the host at the face locations (apply!, src/Flow.jl:81-82; i is 0-based here)."""
 
     def __init__(self, N, uBC, Δt=0.25, ν=0.0, g=None, u0=None, perdir=(), exitBC=False, λ=quick, T=np.float32,
-                 pois="multilevel", smoother="gs", tol=1e-4, itmx=0, device=0, fmad=False, flags=0):
+                 pois="multilevel", smoother="gs", tol=1e-4, itmx=0, device=0, fmad=False, flags=0, dist=None):
         if callable(uBC):
             raise _lib.WLError("function-valued uBC is a host closure: not supported by the B200 C ABI (SURVEY.md §8b)")
         if g is not None:
@@ -41,8 +49,15 @@ class Flow:
         self.L = _lib.load_library(fmad)
         D = len(N)
         self.D = D
-        self.dims = tuple(int(n) for n in N)
+        self.dims = tuple(int(n) for n in N)  # GLOBAL interior size
+        # z-slab decomposition: dist = (rank, world, nccl_id_bytes); arrays seen through this object are the rank's own slab
+        self.rank, self.world = (dist[0], dist[1]) if dist else (0, 1)
         self.N = tuple(n + 2 for n in self.dims)
+        self.zoff = 0
+        if self.world > 1:
+            nzl = self.dims[2] // self.world
+            self.N = self.N[:2] + (nzl + 2,)
+            self.zoff = self.rank * nzl
         self.uBC = tuple(float(v) for v in uBC)
         self.ν = float(ν)
         self.exitBC = bool(exitBC)
@@ -65,12 +80,16 @@ class Flow:
         cfg.device = device
         cfg.flags = flags
         self.h = C.c_void_p()
-        _lib.check(self.L, self.L.wl_create(C.byref(cfg), C.byref(self.h)))
+        if self.world > 1:
+            idb = C.create_string_buffer(bytes(dist[2]), 128)
+            _lib.check(self.L, self.L.wl_create_dist(C.byref(cfg), self.rank, self.world, idb, C.byref(self.h)))
+        else:
+            _lib.check(self.L, self.L.wl_create(C.byref(cfg), C.byref(self.h)))
         if u0 is not None:
             arr = np.empty((D,) + tuple(reversed(self.N)), F)
             if callable(u0):
                 for i in range(D):
-                    arr[i] = np.asarray(u0(i, loc_grid(self.N, i)), F)
+                    arr[i] = np.asarray(u0(i, loc_grid(self.N, i, self.zoff)), F)
             else:
                 for i in range(D):
                     arr[i] = F(u0[i])

@@ -99,6 +99,8 @@ def load_library(fmad=False):
         "wl_stream": [H, C.POINTER(C.c_void_p)],
     }
     sig["wl_selftest_div6"] = [C.POINTER(C.c_uint64)]
+    sig["wl_dist_unique_id"] = [C.c_void_p]
+    sig["wl_create_dist"] = [C.POINTER(Config), C.c_int, C.c_int, C.c_void_p, C.POINTER(H)]
     for name, args in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
         fn.argtypes = args

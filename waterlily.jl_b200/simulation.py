@@ -44,7 +44,7 @@ def measure(sim, t=None):
     if isinstance(sim.body, NoBody):
         return
     fl = sim.flow
-    mu0, mu1, V, sigma = measure_body(fl.N, sim.body, sim.ϵ)
+    mu0, mu1, V, sigma = measure_body(fl.N, sim.body, sim.ϵ, fl.zoff)
     fl.upload("mu0", mu0)
     fl.upload("mu1", mu1)
     fl.upload("V", V)
