@@ -72,9 +72,20 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def tgv_u0(n):
-    from util import tgv3d_u0
-    return tgv3d_u0((n + 2,) * 3, n)
+def tgv_u0(n, z0=0, nzl=None):
+    """TGV initial condition on the ghost-padded planes z0 … z0+nzl+1 (the whole domain by default)."""
+    F = np.float32
+    nzl = n if nzl is None else nzl
+    k = F(2 * np.pi / n)
+    u = np.zeros((3, nzl + 2, n + 2, n + 2), F)
+    idx = np.arange(1, n + 3, dtype=F)
+    idz = np.arange(1 + z0, z0 + nzl + 3, dtype=F)
+    for i in range(2):
+        x = (idx - F(1.5) - (F(0.5) if i == 0 else F(0)))[None, None, :]
+        y = (idx - F(1.5) - (F(0.5) if i == 1 else F(0)))[None, :, None]
+        z = (idz - F(1.5))[:, None, None]
+        u[i] = (-np.sin(k * x) * np.cos(k * y) * np.cos(k * z) if i == 0 else np.cos(k * x) * np.sin(k * y) * np.cos(k * z)).astype(F)
+    return u
 
 
 def make_case(name):
@@ -90,14 +101,15 @@ def make_case(name):
     return dict(dims=d, uBC=(1.0, 0.0, 0.0), L=2 * R, nu=2 * R / 3700, perdir=(), exitBC=True, body=((c, c, c), R), u0=None)
 
 
-def build_sim(case, u0_host=None):
+def build_sim(case, u0_host=None, dist=None, device=0):
     import wl_b200 as wl
     body = wl.Sphere(*case["body"]) if case["body"] else None
     u0 = None
     if u0_host is not None:
         def u0(i, x):
             return u0_host[i]
-    return wl.Simulation(case["dims"], case["uBC"], case["L"], ν=case["nu"], perdir=case["perdir"], exitBC=case["exitBC"], body=body, u0=u0)
+    return wl.Simulation(case["dims"], case["uBC"], case["L"], ν=case["nu"], perdir=case["perdir"], exitBC=case["exitBC"], body=body, u0=u0,
+                         dist=dist, device=device)
 
 
 class ClockSampler:
@@ -204,10 +216,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     case = make_case(args.workload)
     cells = int(np.prod(case["dims"]))
-    u0_host = tgv_u0(case["u0"][1]) if case["u0"] else None
+    nzl = case["dims"][2] // world
+
+    def new_dist():
+        """z-slab decomposition: rank 0 creates the NCCL id of the library's own communicator, torch broadcasts it (one id per handle)"""
+        if world == 1:
+            return None
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(wl.dist_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        return (rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+    distarg = new_dist()
+    u0_host = tgv_u0(case["u0"][1], rank * nzl, nzl) if case["u0"] else None
 
     # ---- device-resident throughput --------------------------------------------------------------
-    sim = build_sim(case, u0_host)
+    sim = build_sim(case, u0_host, distarg, local)
     fl = sim.flow
     check = wl.lib.check
     check(fl.L, fl.L.wl_sim_step_n(fl.h, args.warmup))
@@ -287,19 +312,23 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "dims": list(case["dims"]), "periodic": list(case["perdir"]), "body": bool(case["body"]),
                        "poisson_iters_per_step": round(n_v, 3), "l2_flush": "state (%.1f GB) exceeds L2" % (padded * 32 * 4 / 1e9),
-                       "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient"},
+                       "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient",
+                       "parallelism": "single GPU" if world == 1 else "z-slab x%d (NCCL halo planes + all-reduce; coarse levels replicated)" % world},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "kernel_times": ksum}
 
     # ---- end to end through the host API: host u0 → Simulation → K × sim_step (+Δt readback) → u,p to host ----
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         sim.close()
         del sim
         pinned = None
         if u0_host is not None:
             pinned = torch.from_numpy(u0_host).pin_memory().numpy()
         torch.cuda.synchronize()
+        distarg2 = new_dist()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        sim2 = build_sim(case, pinned)
+        sim2 = build_sim(case, pinned, distarg2, local)
         h2d = (pinned.nbytes if pinned is not None else 0)
         if case["body"]:
             h2d += 4 * padded * (3 + 9 + 3 + 1)
@@ -316,10 +345,16 @@ def main():
         p = sim2.flow.p
         t2 = time.perf_counter()
         e2e_s = (t2 - t1) + t_setup
-        d2h = u.nbytes + p.nbytes
+        d2h = (u.nbytes + p.nbytes) * world
+        h2d *= world
+        if world > 1:
+            tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
         line["e2e"] = {"value": round(e2e_s * 1e9 / args.steps / cells, 5), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
                        "d2h_bytes_per_step": int(d2h / args.steps + 4 * len(sim2.flow.Δt)),
-                       "what": "Simulation(host u0) set-up + K×sim_step with Δt read back each step + u,p downloaded to host, all timed",
+                       "what": "Simulation(host u0) set-up + K×sim_step with Δt read back each step + u,p downloaded to host, all timed "
+                               "(max over ranks; every rank moves its own z slab)",
                        "setup_s": round(t_setup, 3), "last_dt": last_dt}
         sim2.close()
 

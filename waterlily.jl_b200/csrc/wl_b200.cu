@@ -137,6 +137,7 @@ struct wl_handle {
   Dist dist;
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
+  int slab_min_planes = 16;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
   cudaStream_t st = nullptr;
@@ -227,6 +228,26 @@ static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
   NCK(g_nccl.GroupStart());
   for (int c = 0; c < ncomp; c++) {
     float* b = a + (size_t)c * g.sc;
+    if (d.up >= 0) NCK(g_nccl.Send(b + g.s[2] * (g.N[2] - 2), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+    if (d.down >= 0) NCK(g_nccl.Send(b + g.s[2] * 1, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    if (d.down >= 0) NCK(g_nccl.Recv(b, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
+    if (d.up >= 0) NCK(g_nccl.Recv(b + g.s[2] * (g.N[2] - 1), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
+  }
+  NCK(g_nccl.GroupEnd());
+  prof_end(h);
+  return 0;
+}
+// Two scalar fields in one NCCL group (r and x after increment!)
+static int exch2(wl_handle* h, const Level& l, float* a0, float* a1) {
+  if (!h->dist.on() || !l.slab) return 0;
+  const Grid& g = l.g;
+  const size_t cnt = (size_t)g.s[2];
+  const Dist& d = h->dist;
+  float* f[2] = {a0, a1};
+  prof_begin(h, "halo_exchange");
+  NCK(g_nccl.GroupStart());
+  for (int c = 0; c < 2; c++) {
+    float* b = f[c];
     if (d.up >= 0) NCK(g_nccl.Send(b + g.s[2] * (g.N[2] - 2), cnt, WL_NCCL_FLOAT, d.up, d.comm, h->st));
     if (d.down >= 0) NCK(g_nccl.Send(b + g.s[2] * 1, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
     if (d.down >= 0) NCK(g_nccl.Recv(b, cnt, WL_NCCL_FLOAT, d.down, d.comm, h->st));
@@ -393,7 +414,7 @@ static int build_levels(wl_handle* h) {
     if (P > 1) {
       const int nz = l.g.N[2] - 2;
       const bool prev = i == 0 || h->levels[i - 1].slab;
-      l.slab = prev && nz % P == 0 && nz / P >= 4 && (nz / P) % 2 == 0 && (i == 0 || l.c[2]);
+      l.slab = prev && nz % P == 0 && nz / P >= (i == 0 ? 4 : h->slab_min_planes) && (nz / P) % 2 == 0 && (i == 0 || l.c[2]);
       if (i == 0 && !l.slab) return fail("z-slab decomposition needs dims[3]=%d divisible by %d ranks with an even number (>=4) of planes each", nz, P);
       if (l.slab) {
         l.g = slab_grid(h, gl[i].g);
@@ -504,7 +525,7 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
       LAUNCH(h, (f_increment<false, false>), l.fgrid(), fb, l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
              h->red, SLOT_R2);
     }
-    if (exch(h, l, l.r, 1) || exch(h, l, l.x, 1)) return 1;
+    if (exch2(h, l, l.r, l.x)) return 1;
     if (with_l2 && allreduce_slot(h, SLOT_R2, WL_NCCL_SUM)) return 1;
     return 0;
   }
