@@ -19,6 +19,7 @@
 #include "wl_kernels.cuh"
 
 #define FTY 8
+#define MARCH_MINB 6  // ≤40 registers ⇒ 6 blocks (48 warps) per SM: measured +10% on every march kernel over the compiler's default
 #define FULLMASK 0xffffffffu
 
 struct Coef {
@@ -207,7 +208,7 @@ __device__ __forceinline__ void march7(const Grid& g, const Frame& f, const SFie
 // The y pair of a coarse cell sits in two adjacent warps: r' is exchanged through shared memory once per plane.
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
                                                      int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
   __shared__ float4 ex[FTY][32];
   const Frame f = make_frame(g, zchunk);
@@ -278,7 +279,7 @@ struct ProlongSrc {  // reads ϵ = xc[down(·)] for a fine row segment
 };
 
 template <bool UNI, bool PROLONG>
-__global__ void __launch_bounds__(32 * FTY) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
                                                         float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
                                                         RedBuf R, int slot) {
   const Frame f = make_frame(g, zchunk);
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(32 * FTY) f_increment(Grid g, Coef c, const fl
 // σ (=z) is not stored in UNI mode (it is pure scratch there; CFL rewrites the interior every step).
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
                                                            float* __restrict__ r, float* __restrict__ zarr, const float* __restrict__ dtp, float wdt,
                                                            int zchunk, RedBuf R, int slot) {
   const Frame f = make_frame(g, zchunk);
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(32 * FTY) f_div_residual(Grid g, Coef c, const
 }
 
 // residual! part 2 + L₂ (src/Poisson.jl:95-97,189): s = Σr/|inside|; |s|>2eps ⇒ r −= s; Σr² → out[slot_out]
-__global__ void __launch_bounds__(32 * FTY) f_resid_fix(Grid g, float* __restrict__ r, float count, int zchunk, RedBuf R, int slot_in, int slot_out) {
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_resid_fix(Grid g, float* __restrict__ r, float count, int zchunk, RedBuf R, int slot_in, int slot_out) {
   const Frame f = make_frame(g, zchunk);
   const float s = (float)R.out[slot_in] / count;
   const bool fix = fabsf(s) > 2.f * 1.1920929e-7f;
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(32 * FTY) f_resid_fix(Grid g, float* __restric
 //   u_d[I] −= L[I,d]·(x[I] − x[I−δ_d]);  p = x/dt
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
                                                       const float* __restrict__ dtp, float wdt, int zchunk) {
   const Frame f = make_frame(g, zchunk);
   const float dt = wdt * (*dtp);
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(256) k_sigma_ghostmax(Grid g, const float* __r
 // CFL (src/Flow.jl:234-244) on the interior with the march geometry: σ = flux_out(I,u) (stored unless UNI), max-reduced,
 // combined with the ghost maximum in out[slot_ghost]; the last block stores Δt = min(10, 1/(max+5ν)) to dt_out.
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_cfl(Grid g, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_cfl(Grid g, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
                                                   int zchunk, RedBuf R, int slot, int slot_ghost, int finalize) {
   const Frame f = make_frame(g, zchunk);
   double m = 0.0;
@@ -962,7 +963,7 @@ struct Gs {
 
 // f_gs_a: ϵ⁰ = r·iD everywhere; A cells take sweep 1 (their neighbours are ϵ⁰, stale and fresh coincide).
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                    float* __restrict__ eps, int zchunk) {
   const Frame f = make_frame(g, zchunk);
   const Gs<UNI> G(g, c, eps, r, f);
@@ -984,7 +985,7 @@ __global__ void __launch_bounds__(32 * FTY) f_gs_a(const __grid_constant__ Grid 
 // a moving cell reads only cells of the other colour (or stale r·iD across periodic faces), which nobody writes in this launch; the
 // vector store rewrites the other colour's lanes with the values just loaded.
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                       float* eps, int k0, int zchunk) {
   const Frame f = make_frame(g, zchunk);
   const Gs<UNI> G(g, c, eps, r, f);
