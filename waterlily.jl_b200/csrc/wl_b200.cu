@@ -779,10 +779,10 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   prof_begin(h, "fm_conv");
   const bool nowall = g.per[0] && g.per[1] && (g.per[2] || (g.zopen[0] && g.zopen[1]));
   if (nowall)
-    fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
+    fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
                                                                             h->red, SLOT_PHIMAX, h->uext);
   else
-    fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
+    fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
                                                                              h->red, SLOT_PHIMAX, h->uext);
   prof_end(h);
   h->launches++;

@@ -645,31 +645,63 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     return flux_from<LAM>(uf, um2, um1, u0c, up1, nu, variant);
   };
 
+  // runtime-component x flux at the cell `ox` columns to the right (the one extra face a warp needs, computed by 3 lanes at once)
+  auto flux_x_rt = [&](int i, int ox) -> float {
+    int variant = 0;
+    if (!PER3 && !g.per[0]) variant = (x + ox == 1) ? 1 : ((x + ox == g.N[0] - 1) ? 2 : 0);
+    const int pc = po[2] + ox;
+    const int pn = (i == 2 ? po[1] : po[2]) + ox - (i == 0) - (i == 1) * CW;  // I − δ_i
+    const float uf = (T[pc] + T[pn]) / 2.f;
+    const int pi = pc + i * PL;
+    return flux_from<LAM>(uf, T[pi - 2], T[pi - 1], T[pi], T[pi + 1], nu, variant);
+  };
+  auto set_planes = [&](int z) {
+    zc = z;
+    int sl = (z - 2) % CRING;
+    if (sl < 0) sl += CRING;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      po[k] = sl * 3 * PL + colbase;
+      sl = (sl + 1 == CRING) ? 0 : sl + 1;
+    }
+  };
+  // lower y fluxes are computed one plane ahead and shared between the rows (warps) of the block through shared memory
+  float* const Fy = T + CRING * 3 * PL;  // [2][3][CTY][32]
+  auto fy_at = [&](int buf, int i, int row) -> float& { return Fy[((buf * 3 + i) * CTY + row) * 32 + lane]; };
+
   for (int zz = z0 - 2; zz <= z0 + 1; zz++) load_plane(zz);
+  __syncthreads();
+  set_planes(z0);
+  float Fyl[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Fyl[i] = flux(i, 1, 0, 0, 0);
+    fy_at(z0 & 1, i, ty) = Fyl[i];
+  }
   float Fz[3] = {0.f, 0.f, 0.f};
   bool haveFz = false;
   double gmax = 0.0;
   for (int z = z0; z < z1; z++) {
     load_plane(z + 2);
-    zc = z;
-    {
-      int sl = (z - 2) % CRING;
-      if (sl < 0) sl += CRING;
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        po[k] = sl * 3 * PL + colbase;
-        sl = (sl + 1 == CRING) ? 0 : sl + 1;
-      }
-    }
+    set_planes(z);
     __syncthreads();
     // which directions contribute to this cell (all for interior cells; upper ghost rows only get the others)
     const bool ax = FUSE || x <= g.N[0] - 2, ay = FUSE || y <= g.N[1] - 2, az = FUSE || z <= g.N[2] - 2;
     float Fxlo[3], Fxhi[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) Fxlo[i] = flux(i, 0, 0, 0, 0);
+    {
+      // the face beyond the warp's last cell: lanes 0-2 compute one component each, lane 31 collects them
+      float fex = 0.f;
+      if (lane < 3) fex = flux_x_rt(lane, 32 - lane);
 #pragma unroll
-    for (int i = 0; i < 3; i++) Fxhi[i] = __shfl_down_sync(FULLMASK, Fxlo[i], 1);
-    if (lane == 31 || x == XM) {
+      for (int i = 0; i < 3; i++) {
+        const float e = __shfl_sync(FULLMASK, fex, i);
+        Fxhi[i] = __shfl_down_sync(FULLMASK, Fxlo[i], 1);
+        if (lane == 31) Fxhi[i] = e;
+      }
+    }
+    if (x == XM && lane != 31) {  // partial warp at the end of a row
 #pragma unroll
       for (int i = 0; i < 3; i++) Fxhi[i] = (FUSE || x + 1 <= g.N[0] - 1) ? flux(i, 0, 1, 0, 0) : 0.f;
     }
@@ -683,13 +715,21 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
 #pragma unroll
       for (int i = 0; i < 3; i++) Fzhi[i] = flux(i, 2, 0, 0, 1);
     }
+    // upper y flux = the next row's lower flux (shared); the last row of the block computes its own
+    float Fyhi[3], Fyn[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Fyhi[i] = (ty + 1 < CTY) ? fy_at(z & 1, i, ty + 1) : flux(i, 1, 0, 1, 0);
+      Fyn[i] = flux(i, 1, 0, 0, 1);  // lower y flux of plane z+1, for the next step
+      fy_at((z + 1) & 1, i, ty) = Fyn[i];
+    }
     float F2lo_y = 0.f;
     if (on) {
       const i64 o = (i64)g.xo + x + g.s[1] * y + g.s[2] * z;
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         float r = 0.f;
-        const float Fylo = flux(i, 1, 0, 0, 0);
+        const float Fylo = Fyl[i];
         if (i == 2) F2lo_y = Fylo;
         if (ax) {
           r += Fxlo[i];
@@ -697,7 +737,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
         }
         if (ay) {
           r += Fylo;
-          r -= flux(i, 1, 0, 1, 0);
+          r -= Fyhi[i];
         }
         if (az) {
           r += Fz[i];
@@ -729,7 +769,10 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
       }
     }
 #pragma unroll
-    for (int i = 0; i < 3; i++) Fz[i] = Fzhi[i];
+    for (int i = 0; i < 3; i++) {
+      Fz[i] = Fzhi[i];
+      Fyl[i] = Fyn[i];
+    }
   }
   if (FUSE) {
     double v[1] = {gmax}, fin[1];
