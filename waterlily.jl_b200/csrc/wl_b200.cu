@@ -75,7 +75,14 @@ struct Level {
     (void)uni;
     return k;
   }
-  int zchunk() const { return std::max(2, std::min(16, (g.N[2] - 2 + 1) / 2 * 2)); }
+  // planes a block marches over: 16 when that still gives every SM several blocks, fewer (even, ≥2) on small grids and thin slabs
+  int zchunk() const {
+    const int nz = g.N[2] - 2;
+    int zc = std::max(2, std::min(16, (nz + 1) / 2 * 2));
+    const long xy = (long)cdiv(g.N[0] - 2, 128) * cdiv(g.N[1] - 2, FTY);
+    while (zc > 2 && xy * cdiv(nz, zc) < 4 * 148) zc = std::max(2, (zc / 2 + 1) / 2 * 2);
+    return zc;
+  }
   dim3 fgrid() const { return dim3(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, FTY), cdiv(g.N[2] - 2, zchunk())); }
   Lvl dev() const {
     Lvl l;
@@ -137,7 +144,13 @@ struct wl_handle {
   Dist dist;
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
-  int slab_min_planes = 16;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
+  int slab_min_planes = 16;
+  // persistent coarse-level kernel: levels >= small_from run inside one cooperative launch per V-cycle (0 = disabled)
+  int small_from = 0;
+  int small_grid = 0;
+  SmallOp* d_ops = nullptr;
+  SmallOp* h_ops = nullptr;  // pinned
+  std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
   cudaStream_t st = nullptr;
@@ -632,6 +645,111 @@ static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int wi
   }
   return 0;
 }
+// ---- flattening of the coarse end of the V-cycle for k_small_levels ----------------------------------------------------
+static SmallOp op_base(const wl_handle* h, const Level& l, int type) {
+  SmallOp o;
+  memset(&o, 0, sizeof o);
+  o.type = type;
+  o.g = l.g;
+  o.c = l.coef(h->uni);
+  o.gc = l.g;
+  o.lvl = l.dev();
+  o.box = l.inside();
+  o.zchunk = l.zchunk();
+  if (type <= OP_F_PROLONG) {
+    dim3 fg = l.fgrid();
+    o.vg[0] = fg.x;
+    o.vg[1] = fg.y;
+    o.vg[2] = fg.z;
+  } else {  // general bodies with a 32×8×1 block
+    o.vg[0] = cdiv(o.box.n[0], 32);
+    o.vg[1] = cdiv(o.box.n[1], FTY);
+    o.vg[2] = o.box.n[2];
+  }
+  return o;
+}
+static bool gs_fusable(const wl_handle* h, const Level& l) { return l.fast && h->fused_gs && (l.g.N[2] - 2) % 2 == 0; }
+static void emit_gs(wl_handle* h, Level& l, int x_is_zero) {
+  if (gs_fusable(h, l)) {
+    h->ops.push_back(op_base(h, l, OP_F_GSA));
+    for (int k0 = 2; k0 <= 4; k0++) {
+      SmallOp o = op_base(h, l, OP_F_GSHALF);
+      o.k0 = k0;
+      h->ops.push_back(o);
+    }
+  } else {
+    h->ops.push_back(op_base(h, l, OP_K_GSINIT));
+    for (int k0 = 1; k0 <= 4; k0++) {
+      SmallOp o = op_base(h, l, OP_K_GSSWEEP);
+      o.k0 = k0;
+      o.vg[0] = cdiv((o.box.n[0] + 1) / 2, 32);
+      h->ops.push_back(o);
+    }
+  }
+  SmallOp o = op_base(h, l, l.fast ? OP_F_INC : OP_K_INC);
+  o.x_is_zero = x_is_zero;
+  h->ops.push_back(o);
+}
+static void emit_vcycle(wl_handle* h, size_t li) {
+  Level& fine = h->levels[li];
+  Level& coarse = h->levels[li + 1];
+  // Jacobi! (+ restrict!)
+  const bool fused = fine.fast && coarse.fullc && fine.zchunk() % 2 == 0 && (fine.g.N[1] - 2) % 2 == 0 && (fine.g.N[2] - 2) % 2 == 0;
+  {
+    SmallOp o = op_base(h, fine, fine.fast ? OP_F_JACOBI : OP_K_JACOBI);
+    o.x_is_zero = li > 0;
+    o.do_restrict = fused;
+    o.gc = fused ? coarse.g : fine.g;
+    o.other = fused ? coarse.r : nullptr;
+    h->ops.push_back(o);
+    std::swap(fine.r, fine.r2);
+  }
+  if (!fused) {
+    SmallOp o = op_base(h, fine, OP_K_RESTRICT);
+    o.gc = coarse.g;
+    o.box = coarse.inside();
+    o.vg[0] = cdiv(o.box.n[0], 32);
+    o.vg[1] = cdiv(o.box.n[1], FTY);
+    o.vg[2] = o.box.n[2];
+    o.other = coarse.r;
+    for (int d = 0; d < 3; d++) o.cm[d] = coarse.c[d];
+    h->ops.push_back(o);
+  }
+  const bool last = (li + 2 >= h->levels.size());
+  if (!last) emit_vcycle(h, li + 1);
+  emit_gs(h, coarse, last ? 1 : 0);
+  {
+    const bool fp = fine.fast && coarse.fullc;
+    SmallOp o = op_base(h, fine, fp ? OP_F_PROLONG : OP_K_PROLONG);
+    o.gc = coarse.g;
+    o.other = coarse.x;
+    for (int d = 0; d < 3; d++) o.cm[d] = coarse.c[d];
+    h->ops.push_back(o);
+  }
+}
+// Runs "Vcycle!(ml; l=small_from) ; smooth!(levels[small_from])" — everything a V-cycle does at and below level small_from.
+static int run_small_levels(wl_handle* h, const float* wp) {
+  const size_t ls = (size_t)h->small_from;
+  h->ops.clear();
+  const bool last = (ls + 1 >= h->levels.size());
+  if (!last) emit_vcycle(h, ls);
+  emit_gs(h, h->levels[ls], last ? 1 : 0);
+  const int nops = (int)h->ops.size();
+  if (nops > 256) return fail("too many coarse-level operations (%d)", nops);
+  memcpy(h->h_ops, h->ops.data(), nops * sizeof(SmallOp));
+  CK(cudaMemcpyAsync(h->d_ops, h->h_ops, nops * sizeof(SmallOp), cudaMemcpyHostToDevice, h->st));
+  const SmallOp* dops = h->d_ops;
+  int n = nops;
+  void* args[] = {(void*)&dops, (void*)&n, (void*)&wp};
+  prof_begin(h, "k_small_levels");
+  cudaError_t e = h->uni ? cudaLaunchCooperativeKernel((void*)k_small_levels<true>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st)
+                         : cudaLaunchCooperativeKernel((void*)k_small_levels<false>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st);
+  prof_end(h);
+  h->launches++;
+  if (e != cudaSuccess) return fail("cooperative launch of k_small_levels: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // Vcycle!(ml;l,ω)  src/MultiLevelPoisson.jl:88-101
 static int vcycle(wl_handle* h, size_t li, const float* wp) {
   Level& fine = h->levels[li];
@@ -645,8 +763,12 @@ static int vcycle(wl_handle* h, size_t li, const float* wp) {
     LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
   }
   const bool last = (li + 2 >= h->levels.size());
-  if (!last) TRY(vcycle(h, li + 1, wp));
-  TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
+  if (h->small_from > 0 && (int)li + 1 == h->small_from) {
+    TRY(run_small_levels(h, wp));  // the whole coarse end in one cooperative launch
+  } else {
+    if (!last) TRY(vcycle(h, li + 1, wp));
+    TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
+  }
   Box fin = fine.inside();
   if (fine.fast && coarse.fullc) {
     ProlongSrc ps{coarse.x, coarse.g, 0, 0, 0};
@@ -1040,6 +1162,36 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       break;
     if (!h->uext && (rc = dalloc(h, &h->uext, 32))) break;
     if ((rc = build_levels(h))) break;
+    if (h->D == 3 && h->cfg.pois_kind == WL_POIS_MULTILEVEL && h->cfg.smoother == WL_SMOOTH_GSRB && !(cfg->flags & WL_FLAG_NO_PERSISTENT)) {
+      // levels of at most ~0.6 M cells (and, with z slabs, only replicated ones) go to the persistent coarse-level kernel
+      for (size_t i = 1; i < h->levels.size(); i++) {
+        const Level& l = h->levels[i];
+        if (!l.slab && (i64)l.g.N[0] * l.g.N[1] * l.g.N[2] <= 600000) {
+          h->small_from = (int)i;
+          break;
+        }
+      }
+      if (h->small_from > 0) {
+        int dev = 0, nsm = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_small_levels<true>, 32 * FTY, 0);
+        int per_sm2 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_small_levels<false>, 32 * FTY, 0);
+        per_sm = std::min(per_sm, per_sm2);
+        if (!coop || per_sm < 1) {
+          h->small_from = 0;
+        } else {
+          h->small_grid = nsm * std::min(per_sm, 2);
+          void* q = nullptr;
+          if (cudaMalloc(&q, 256 * sizeof(SmallOp)) != cudaSuccess) { rc = fail("cudaMalloc ops"); break; }
+          h->d_ops = (SmallOp*)q;
+          h->allocs.push_back(q);
+          if (cudaMallocHost((void**)&h->h_ops, 256 * sizeof(SmallOp)) != cudaSuccess) { rc = fail("cudaMallocHost ops"); break; }
+        }
+      }
+    }
     // reduction buffers
     Box all = h->levels[0].all();
     const size_t nb = std::max(nblocks(all, blk(D)), (size_t)1024) + 4096;
@@ -1093,6 +1245,7 @@ int wl_destroy(wl_handle* h) {
   for (void* q : h->allocs) cudaFree(q);
   if (h->d_dthist) cudaFree(h->d_dthist);
   if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_ops) cudaFreeHost(h->h_ops);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;

@@ -37,14 +37,22 @@ struct Box {
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// `vb` is the block index a kernel body works for: blockIdx for an ordinary launch, a virtual block index when the persistent
+// coarse-level kernel (k_small_levels) loops the same body over the blocks of a small grid.
+__device__ __forceinline__ int3 real_block() { return make_int3(blockIdx.x, blockIdx.y, blockIdx.z); }
+
 template <int D>
-__device__ __forceinline__ bool thread_cell(const Box& b, int I[3]) {
-  I[0] = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
-  I[1] = b.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-  I[2] = (D == 3) ? b.lo[2] + blockIdx.z * blockDim.z + threadIdx.z : 0;
+__device__ __forceinline__ bool thread_cell(const Box& b, int I[3], const int3 vb) {
+  I[0] = b.lo[0] + vb.x * blockDim.x + threadIdx.x;
+  I[1] = b.lo[1] + vb.y * blockDim.y + threadIdx.y;
+  I[2] = (D == 3) ? b.lo[2] + vb.z * blockDim.z + threadIdx.z : 0;
   bool ok = I[0] < b.lo[0] + b.n[0] && I[1] < b.lo[1] + b.n[1];
   if (D == 3) ok = ok && I[2] < b.lo[2] + b.n[2];
   return ok;
+}
+template <int D>
+__device__ __forceinline__ bool thread_cell(const Box& b, int I[3]) {
+  return thread_cell<D>(b, I, real_block());
 }
 
 __device__ __forceinline__ i64 cell_off(const Grid& g, const int I[3]) { return (i64)(g.xo + I[0]) + g.s[1] * I[1] + g.s[2] * I[2]; }

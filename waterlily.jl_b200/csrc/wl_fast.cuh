@@ -55,12 +55,12 @@ struct Frame {
   i64 rowm, rowp;           // same for rows ym, yp
 };
 
-__device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk) {
+__device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk, const int3 vb) {
   Frame f;
   f.lane = threadIdx.x;
-  f.x0 = 1 + 4 * (32 * blockIdx.x + threadIdx.x);
-  f.y = 1 + FTY * blockIdx.y + threadIdx.y;
-  f.z0 = 1 + zchunk * blockIdx.z;
+  f.x0 = 1 + 4 * (32 * vb.x + threadIdx.x);
+  f.y = 1 + FTY * vb.y + threadIdx.y;
+  f.z0 = 1 + zchunk * vb.z;
   f.z1 = min(f.z0 + zchunk, g.N[2] - 1);
   f.on = f.x0 <= g.N[0] - 2 && f.y <= g.N[1] - 2;
   f.lastgrp = f.x0 + 4 > g.N[0] - 2;
@@ -74,6 +74,7 @@ __device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk) {
   f.rowp = (i64)g.xo + g.s[1] * f.yp;
   return f;
 }
+__device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk) { return make_frame(g, zchunk, real_block()); }
 __device__ __forceinline__ int zwrap_lo(const Grid& g, int z) { return (g.per[2] && z == 1) ? g.N[2] - 2 : z - 1; }
 __device__ __forceinline__ int zwrap_hi(const Grid& g, int z) { return (g.per[2] && z == g.N[2] - 2) ? 1 : z + 1; }
 
@@ -208,10 +209,10 @@ __device__ __forceinline__ void march7(const Grid& g, const Frame& f, const SFie
 // The y pair of a coarse cell sits in two adjacent warps: r' is exchanged through shared memory once per plane.
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
-                                                     int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
+__device__ __forceinline__ void b_f_jacobi(const Grid& g, const Coef& c, const float* r, float* r2, float* x,
+                                                     int x_is_zero, int zchunk, Grid gc, float* rc, int do_restrict, int zoffc, const int3 vb) {
   __shared__ float4 ex[FTY][32];
-  const Frame f = make_frame(g, zchunk);
+  const Frame f = make_frame(g, zchunk, vb);
   SField F;
   F.q = r;
   F.w = c.iD;
@@ -264,6 +265,11 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_jacobi(Grid g, Coef c,
     }
   });
 }
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
+                                                     int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
+  b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
+}
 
 // ------------------------------------------------------------------------------------------------
 // increment!(p;ω) (src/Poisson.jl:100-104) with the ϵ source either the level's own ϵ array (after GaussSeidelRB!) or
@@ -279,10 +285,10 @@ struct ProlongSrc {  // reads ϵ = xc[down(·)] for a fine row segment
 };
 
 template <bool UNI, bool PROLONG>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
-                                                        float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
-                                                        RedBuf R, int slot) {
-  const Frame f = make_frame(g, zchunk);
+__device__ __forceinline__ void b_f_increment(const Grid& g, const Coef& c, const float* eps, ProlongSrc ps, float* r,
+                                                        float* x, const float* wp, int x_is_zero, int zchunk, int with_l2,
+                                                        RedBuf R, int slot, const int3 vb) {
+  const Frame f = make_frame(g, zchunk, vb);
   const float w = *wp;
   double l2 = 0.0;
   if (!PROLONG) {
@@ -346,6 +352,12 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef
     double v[1] = {l2}, fin[1];
     grid_reduce<RED_SUM, 1>(v, R, slot, fin);
   }
+}
+template <bool UNI, bool PROLONG>
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
+                                                        float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
+                                                        RedBuf R, int slot) {
+  b_f_increment<UNI, PROLONG>(g, c, eps, ps, r, x, wp, x_is_zero, zchunk, with_l2, R, slot, real_block());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1006,9 +1018,9 @@ struct Gs {
 
 // f_gs_a: ϵ⁰ = r·iD everywhere; A cells take sweep 1 (their neighbours are ϵ⁰, stale and fresh coincide).
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
-                                                   float* __restrict__ eps, int zchunk) {
-  const Frame f = make_frame(g, zchunk);
+__device__ __forceinline__ void b_f_gs_a(const Grid& g, const Coef& c, const float* r,
+                                                   float* eps, int zchunk, const int3 vb) {
+  const Frame f = make_frame(g, zchunk, vb);
   const Gs<UNI> G(g, c, eps, r, f);
   SField F;
   F.q = r;
@@ -1023,14 +1035,19 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_cons
     }
   });
 }
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+                                                   float* __restrict__ eps, int zchunk) {
+  b_f_gs_a<UNI>(g, c, r, eps, zchunk, real_block());
+}
 
 // f_gs_half: one red/black half-sweep (src/Poisson.jl:145) in place: the cells with (x+y+z) ≡ k₀ (mod 2) move.  In-place is race-free:
 // a moving cell reads only cells of the other colour (or stale r·iD across periodic faces), which nobody writes in this launch; the
 // vector store rewrites the other colour's lanes with the values just loaded.
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
-                                                      float* eps, int k0, int zchunk) {
-  const Frame f = make_frame(g, zchunk);
+__device__ __forceinline__ void b_f_gs_half(const Grid& g, const Coef& c, const float* r,
+                                                      float* eps, int k0, int zchunk, const int3 vb) {
+  const Frame f = make_frame(g, zchunk, vb);
   const Gs<UNI> G(g, c, eps, r, f);
   const int y = min(f.y, g.N[1] - 2);
   const bool moveA = (k0 & 1) != 0;
@@ -1042,5 +1059,94 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_half(const __grid_c
       // select_A(firstA, a, b): A lanes from a, B lanes from b
       st4(eps + G.off(y, z) + f.x0, moveA ? select_A(firstA, up, st) : select_A(firstA, st, up));
     }
+  }
+}
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+                                                      float* eps, int k0, int zchunk) {
+  b_f_gs_half<UNI>(g, c, r, eps, k0, zchunk, real_block());
+}
+
+// ================================================================================================
+// k_small_levels — the coarse end of a V-cycle in ONE cooperative launch.
+// Levels of a few hundred thousand cells and fewer are launch-latency bound: nine launches per level per V-cycle, each a few
+// microseconds of work.  This kernel runs the same kernel BODIES (b_f_jacobi, b_f_gs_a, … — identical arithmetic, identical
+// bits) over the virtual blocks of each small grid and separates the operations with grid-wide barriers instead of launches.
+// The host flattens the recursion of Vcycle! (src/MultiLevelPoisson.jl:88-101) into a list of SmallOp.
+// ================================================================================================
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+enum { OP_F_JACOBI = 0, OP_F_GSA, OP_F_GSHALF, OP_F_INC, OP_F_PROLONG, OP_K_JACOBI, OP_K_RESTRICT, OP_K_GSINIT, OP_K_GSSWEEP, OP_K_INC, OP_K_PROLONG };
+
+struct SmallOp {
+  int type, k0, x_is_zero, do_restrict, zoffc, zchunk;
+  int vg[3];  // virtual grid of 32×8(×1)-thread blocks
+  int cm[3];  // coarsening mask towards `gc`
+  Grid g;     // the level the op runs on
+  Coef c;
+  Grid gc;    // the other level of a restriction / prolongation
+  Lvl lvl;    // pointer bundle for the general bodies
+  Box box;
+  float* other;  // coarse r (restriction target) or coarse x (prolongation source)
+};
+
+template <bool UNI>
+__global__ void __launch_bounds__(32 * FTY, 4) k_small_levels(const SmallOp* __restrict__ ops, int nops, const float* wp) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ SmallOp op;
+  const int tid = threadIdx.x + 32 * threadIdx.y;
+  RedBuf nored{nullptr, nullptr, nullptr};
+  for (int o = 0; o < nops; o++) {
+    __syncthreads();
+    {  // stage the descriptor in shared memory
+      const int* src = reinterpret_cast<const int*>(ops + o);
+      int* dst = reinterpret_cast<int*>(&op);
+      for (int q = tid; q < (int)(sizeof(SmallOp) / sizeof(int)); q += 32 * FTY) dst[q] = src[q];
+    }
+    __syncthreads();
+    const int nvb = op.vg[0] * op.vg[1] * op.vg[2];
+    for (int v = blockIdx.x; v < nvb; v += gridDim.x) {
+      const int3 vb = make_int3(v % op.vg[0], (v / op.vg[0]) % op.vg[1], v / (op.vg[0] * op.vg[1]));
+      switch (op.type) {
+        case OP_F_JACOBI:
+          b_f_jacobi<UNI>(op.g, op.c, op.lvl.r, op.lvl.r2, op.lvl.x, op.x_is_zero, op.zchunk, op.gc, op.other, op.do_restrict, op.zoffc, vb);
+          break;
+        case OP_F_GSA:
+          b_f_gs_a<UNI>(op.g, op.c, op.lvl.r, op.lvl.eps, op.zchunk, vb);
+          break;
+        case OP_F_GSHALF:
+          b_f_gs_half<UNI>(op.g, op.c, op.lvl.r, op.lvl.eps, op.k0, op.zchunk, vb);
+          break;
+        case OP_F_INC: {
+          ProlongSrc ps{nullptr, op.g, 0, 0, 0};
+          b_f_increment<UNI, false>(op.g, op.c, op.lvl.eps, ps, op.lvl.r, op.lvl.x, wp, op.x_is_zero, op.zchunk, 0, nored, 0, vb);
+        } break;
+        case OP_F_PROLONG: {
+          ProlongSrc ps{op.other, op.gc, 0, 0, 0};
+          b_f_increment<UNI, true>(op.g, op.c, nullptr, ps, op.lvl.r, op.lvl.x, wp, 0, op.zchunk, 0, nored, 0, vb);
+        } break;
+        case OP_K_JACOBI:
+          b_k_jacobi<3>(op.lvl, op.box, op.x_is_zero, vb);
+          break;
+        case OP_K_RESTRICT:
+          b_k_restrict<3>(op.gc, op.g, op.box, op.other, op.lvl.r, op.cm[0], op.cm[1], op.cm[2], vb);
+          break;
+        case OP_K_GSINIT:
+          b_k_gs_init<3>(op.lvl, op.box, vb);
+          break;
+        case OP_K_GSSWEEP:
+          b_k_gs_sweep<3>(op.lvl, op.box, op.k0, vb);
+          break;
+        case OP_K_INC:
+          b_k_increment<3>(op.lvl, op.box, wp, op.x_is_zero, 0, nored, 0, vb);
+          break;
+        case OP_K_PROLONG:
+          b_k_prolong_inc<3>(op.lvl, op.gc, op.other, op.box, wp, op.cm[0], op.cm[1], op.cm[2], vb);
+          break;
+      }
+      __syncthreads();
+    }
+    grid.sync();
   }
 }

@@ -387,10 +387,10 @@ __global__ void __launch_bounds__(512) k_resid_fix(Lvl l, Box box, float count, 
 //   ϵ = r·iD (neighbours recomputed on the fly, periodic wrap = perBC!(ϵ));  r' = r − Aϵ;  x (+)= ϵ
 // r' goes to the ping-pong buffer r2 because neighbours still need the old r.
 template <int D>
-__global__ void __launch_bounds__(512) k_jacobi(Lvl l, Box box, int x_is_zero) {
+__device__ __forceinline__ void b_k_jacobi(Lvl l, Box box, int x_is_zero, const int3 vb) {
   const Grid& g = l.g;
   int I[3];
-  if (!thread_cell<D>(box, I)) return;
+  if (!thread_cell<D>(box, I, vb)) return;
   const i64 o = cell_off(g, I);
   i64 lo[3], hi[3];
   nbr_offsets<D>(g, I, lo, hi);
@@ -402,12 +402,16 @@ __global__ void __launch_bounds__(512) k_jacobi(Lvl l, Box box, int x_is_zero) {
   l.r2[o] = l.r[o] - 1.f * s;
   l.x[o] = x_is_zero ? e : l.x[o] + 1.f * e;
 }
+template <int D>
+__global__ void __launch_bounds__(512) k_jacobi(Lvl l, Box box, int x_is_zero) {
+  b_k_jacobi<D>(l, box, x_is_zero, real_block());
+}
 
 // restrict!(a,b,c) (src/MultiLevelPoisson.jl:49, :13-19): coarse r = Σ fine r over up(I,c), x fastest.
 template <int D>
-__global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+__device__ __forceinline__ void b_k_restrict(Grid gc, Grid gf, Box box, float* a, const float* b, int c0, int c1, int c2, const int3 vb) {
   int I[3];
-  if (!thread_cell<D>(box, I)) return;
+  if (!thread_cell<D>(box, I, vb)) return;
   const int c[3] = {c0, c1, c2};
   int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
@@ -421,29 +425,37 @@ __global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, con
       for (int ii = lo[0]; ii <= hi[0]; ii++) s += b[(i64)(gf.xo + ii) + gf.s[1] * jj + gf.s[2] * k];
   a[cell_off(gc, I)] = s;
 }
+template <int D>
+__global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+  b_k_restrict<D>(gc, gf, box, a, b, c0, c1, c2, real_block());
+}
 
 // GaussSeidelRB! line 1: @inside ϵ = r·iD (src/Poisson.jl:142).  perBC!(ϵ) is NOT materialised: the sweeps
 // below read r·iD of the wrapped cell across periodic faces, which is exactly the stale ghost the reference sees.
 template <int D>
-__global__ void k_gs_init(Lvl l, Box box) {
+__device__ __forceinline__ void b_k_gs_init(Lvl l, Box box, const int3 vb) {
   int I[3];
-  if (!thread_cell<D>(box, I)) return;
+  if (!thread_cell<D>(box, I, vb)) return;
   const i64 o = cell_off(l.g, I);
   l.eps[o] = l.r[o] * l.iD[o];
+}
+template <int D>
+__global__ void k_gs_init(Lvl l, Box box) {
+  b_k_gs_init<D>(l, box, real_block());
 }
 
 // One red/black half-sweep gauss_rb(ϵ,r,L,iD,k₀,·) (src/Poisson.jl:116-132,145).  Thread t along x handles the cell
 // x = 1 + 2t + shift of the sweep's colour: Σ(1-based idx) ≡ 1+k₀ (mod 2).  The reference's half_rangek only reaches
 // last-dim indices k with Iv=(k+1+p)/2 ≤ N_d÷2 (matters for odd N_d).
 template <int D>
-__global__ void __launch_bounds__(512) k_gs_sweep(Lvl l, Box box, int k0) {
+__device__ __forceinline__ void b_k_gs_sweep(Lvl l, Box box, int k0, const int3 vb) {
   const Grid& g = l.g;
   int I[3];
-  I[1] = box.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-  I[2] = (D == 3) ? box.lo[2] + blockIdx.z * blockDim.z + threadIdx.z : 0;
+  I[1] = box.lo[1] + vb.y * blockDim.y + threadIdx.y;
+  I[2] = (D == 3) ? box.lo[2] + vb.z * blockDim.z + threadIdx.z : 0;
   if (I[1] >= box.lo[1] + box.n[1]) return;
   if (D == 3 && I[2] >= box.lo[2] + box.n[2]) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = vb.x * blockDim.x + threadIdx.x;
   // 1-based index sum parity must equal (1+k0)&1 :  (Σ0 + D) & 1 == (1+k0) & 1
   const int rest = I[1] + I[2] + D + 1 + k0;  // x0 must make (x0 + rest) even
   I[0] = 1 + 2 * t + ((1 + rest) & 1);
@@ -477,14 +489,18 @@ __global__ void __launch_bounds__(512) k_gs_sweep(Lvl l, Box box, int k0) {
   }
   l.eps[o] = s * l.iD[o];
 }
+template <int D>
+__global__ void __launch_bounds__(512) k_gs_sweep(Lvl l, Box box, int k0) {
+  b_k_gs_sweep<D>(l, box, k0, real_block());
+}
 
 // increment!(p;ω) (src/Poisson.jl:100-104): r −= ω·Aϵ; x += ω·ϵ (periodic wrap = perBC!(ϵ)), optionally fused with
 // L₂(p) = r⋅r (src/Poisson.jl:189) → out[slot].
 template <int D>
-__global__ void __launch_bounds__(512) k_increment(Lvl l, Box box, const float* __restrict__ wp, int x_is_zero, int with_l2, RedBuf R, int slot) {
+__device__ __forceinline__ void b_k_increment(Lvl l, Box box, const float* wp, int x_is_zero, int with_l2, RedBuf R, int slot, const int3 vb) {
   const Grid& g = l.g;
   int I[3];
-  const bool ok = thread_cell<D>(box, I);
+  const bool ok = thread_cell<D>(box, I, vb);
   double v[1] = {0.0}, fin[1];
   if (ok) {
     const float w = *wp;
@@ -500,15 +516,19 @@ __global__ void __launch_bounds__(512) k_increment(Lvl l, Box box, const float* 
   }
   if (with_l2) grid_reduce<RED_SUM, 1>(v, R, slot, fin);
 }
+template <int D>
+__global__ void __launch_bounds__(512) k_increment(Lvl l, Box box, const float* __restrict__ wp, int x_is_zero, int with_l2, RedBuf R, int slot) {
+  b_k_increment<D>(l, box, wp, x_is_zero, with_l2, R, slot, real_block());
+}
 
 // prolongate!(fine.ϵ,coarse.x,c) + increment!(fine;ω) (src/MultiLevelPoisson.jl:50,99-100) without materialising ϵ:
 // ϵ[I] = x_c[down(I,c)], down = (I+2)÷2 (1-based) ↔ (I0+1)/2 (0-based) in coarsened dims.
 template <int D>
-__global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float* __restrict__ xc, Box box, const float* __restrict__ wp, int c0, int c1,
-                                                     int c2) {
+__device__ __forceinline__ void b_k_prolong_inc(Lvl l, Grid gc, const float* xc, Box box, const float* wp, int c0, int c1,
+                                                     int c2, const int3 vb) {
   const Grid& g = l.g;
   int I[3];
-  if (!thread_cell<D>(box, I)) return;
+  if (!thread_cell<D>(box, I, vb)) return;
   const int c[3] = {c0, c1, c2};
   const float w = *wp;
   const i64 o = cell_off(g, I);
@@ -535,6 +555,11 @@ __global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float
   }
   l.r[o] = l.r[o] - w * s;
   l.x[o] = l.x[o] + w * e;
+}
+template <int D>
+__global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float* __restrict__ xc, Box box, const float* __restrict__ wp, int c0, int c1,
+                                                     int c2) {
+  b_k_prolong_inc<D>(l, gc, xc, box, wp, c0, c1, c2, real_block());
 }
 
 // Velocity correction and pressure unscale of mom_project! (src/Flow.jl:227-230):
