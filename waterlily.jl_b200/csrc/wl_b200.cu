@@ -148,6 +148,7 @@ struct wl_handle {
   // persistent coarse-level kernel: levels >= small_from run inside one cooperative launch per V-cycle (0 = disabled)
   int small_from = 0;
   int small_grid = 0;
+  int* d_flags = nullptr;  // [0]: a flux kernel met a value outside the proven range of its division-free x/6 (non-finite or < 8e-31)
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
@@ -902,10 +903,10 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   const bool nowall = g.per[0] && g.per[1] && (g.per[2] || (g.zopen[0] && g.zopen[1]));
   if (nowall)
     fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                            h->red, SLOT_PHIMAX, h->uext);
+                                                                            h->red, SLOT_PHIMAX, h->uext, h->d_flags);
   else
     fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                             h->red, SLOT_PHIMAX, h->uext);
+                                                                             h->red, SLOT_PHIMAX, h->uext, h->d_flags);
   prof_end(h);
   h->launches++;
 }
@@ -1006,6 +1007,13 @@ static int ensure_dt_capacity(wl_handle* h, size_t need) {
   }
   h->d_dthist = q;
   h->dt_cap = cap;
+  return 0;
+}
+static int check_flags(wl_handle* h) {
+  int f = 0;
+  CK(cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (f) return fail("the flux kernel met a non-finite or denormal-range (<8e-31) value: the velocity field has diverged");
   return 0;
 }
 static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vector
@@ -1161,6 +1169,11 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         (rc = dalloc(h, &h->sigma, n)) || (rc = dalloc(h, &h->V, n * D)) || (rc = dalloc(h, &h->mu0, n * D)) || (rc = dalloc(h, &h->mu1, n * D * D)))
       break;
     if (!h->uext && (rc = dalloc(h, &h->uext, 32))) break;
+    {
+      float* q = nullptr;
+      if ((rc = dalloc(h, &q, 8))) break;
+      h->d_flags = (int*)q;
+    }
     if ((rc = build_levels(h))) break;
     if (h->D == 3 && h->cfg.pois_kind == WL_POIS_MULTILEVEL && h->cfg.smoother == WL_SMOOTH_GSRB && !(cfg->flags & WL_FLAG_NO_PERSISTENT)) {
       // levels of at most ~0.6 M cells (and, with z slabs, only replicated ones) go to the persistent coarse-level kernel
@@ -1534,7 +1547,7 @@ int wl_sync(wl_handle* h) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
-  return 0;
+  return check_flags(h);
 }
 
 int wl_launch_count(wl_handle* h, int64_t* count) {

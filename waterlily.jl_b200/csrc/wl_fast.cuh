@@ -555,17 +555,17 @@ struct ConvTile {
 };
 
 template <int LAM>
-__device__ __forceinline__ float flux_from(float uf, float um2, float um1, float u0c, float up1, float nu, int variant) {
+__device__ __forceinline__ float flux_from(float uf, float um2, float um1, float u0c, float up1, float nu, int variant, int* flag) {
   // variant 0: ϕu (inner / periodic), 1: ϕuL (lower non-periodic boundary), 2: ϕuR (upper non-periodic boundary)
   const float diff = nu * (u0c - um1);
   const bool pos = uf > 0.f;
   float conv;
   if (variant == 1)
-    conv = pos ? uf * ((u0c + um1) / 2.f) : uf * limiter<LAM>(up1, u0c, um1);
+    conv = pos ? uf * ((u0c + um1) / 2.f) : uf * limiter_f<LAM>(up1, u0c, um1, flag);
   else if (variant == 2)
-    conv = uf < 0.f ? uf * ((u0c + um1) / 2.f) : uf * limiter<LAM>(um2, um1, u0c);
+    conv = uf < 0.f ? uf * ((u0c + um1) / 2.f) : uf * limiter_f<LAM>(um2, um1, u0c, flag);
   else
-    conv = uf * limiter<LAM>(pos ? um2 : up1, pos ? um1 : u0c, pos ? u0c : um1);
+    conv = uf * limiter_f<LAM>(pos ? um2 : up1, pos ? um1 : u0c, pos ? u0c : um1, flag);
   return conv - diff;
 }
 
@@ -574,7 +574,7 @@ __device__ __forceinline__ float flux_from(float uf, float um2, float um1, float
 template <int LAM, bool FUSE, bool PER3>
 __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restrict__ ua, const float* __restrict__ u0, const float* __restrict__ V,
                                                     float* __restrict__ out, float* __restrict__ sigma, const float* __restrict__ dtp, float nu, int zchunk,
-                                                    int corrector, RedBuf R, int slot, const float* __restrict__ uext) {
+                                                    int corrector, RedBuf R, int slot, const float* __restrict__ uext, int* __restrict__ flag) {
   extern __shared__ float smem_raw[];
   float* const T = smem_raw;  // [CRING][3][CH][CW]
   constexpr int PL = CH * CW;  // one component plane
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     const float um1 = U(i, ox - dx, oy - dy, oz - dz);
     const float u0c = U(i, ox, oy, oz);
     const float up1 = U(i, ox + dx, oy + dy, oz + dz);
-    return flux_from<LAM>(uf, um2, um1, u0c, up1, nu, variant);
+    return flux_from<LAM>(uf, um2, um1, u0c, up1, nu, variant, flag);
   };
 
   // runtime-component x flux at the cell `ox` columns to the right (the one extra face a warp needs, computed by 3 lanes at once)
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     const int pn = (i == 2 ? po[1] : po[2]) + ox - (i == 0) - (i == 1) * CW;  // I − δ_i
     const float uf = (T[pc] + T[pn]) / 2.f;
     const int pi = pc + i * PL;
-    return flux_from<LAM>(uf, T[pi - 2], T[pi - 1], T[pi], T[pi + 1], nu, variant);
+    return flux_from<LAM>(uf, T[pi - 2], T[pi - 1], T[pi], T[pi + 1], nu, variant, flag);
   };
   auto set_planes = [&](int z) {
     zc = z;

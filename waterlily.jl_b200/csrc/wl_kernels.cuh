@@ -23,6 +23,24 @@ __device__ __forceinline__ float div6(float x) {
   if (!(ax >= 7.888609052210118e-31f && ax <= 3.0e38f)) q = (ax == 0.f) ? q0 : div6_slow(x);  // ±0 keeps its sign; the rest is never physical
   return q;
 }
+// Branch-free variant for the flux kernel: outside the proven range (never for physical values) it raises *flag instead of taking
+// the slow path; the host turns a raised flag into an error, so a result is either exact or reported.
+__device__ __forceinline__ float div6_flag(float x, int* flag) {
+  const float C = 0.16666667163372039794921875f;
+  const float q0 = x * C;
+  const float r = __fmaf_rn(-6.f, q0, x);
+  const float q = __fmaf_rn(r, C, q0);
+  const float ax = fabsf(x);
+  const bool inr = ax >= 7.888609052210118e-31f && ax <= 3.0e38f;
+  if (!inr && ax != 0.f) *flag = 1;
+  return inr ? q : q0;  // ±0 → ±0 (= q0)
+}
+template <int LAM>
+__device__ __forceinline__ float limiter_f(float u, float c, float d, int* flag) {
+  if (LAM == 0) return median3(div6_flag(5.f * c + 2.f * d - u, flag), c, median3(10.f * c - 9.f * u, c, d));  // quick
+  if (LAM == 1) return (c + d) / 2.f;                                                                          // cds
+  return (c <= fminf(u, d) || c >= fmaxf(u, d)) ? c : c + (d - c) * (c - u) / (d - u);                        // vanLeer
+}
 template <int LAM>
 __device__ __forceinline__ float limiter(float u, float c, float d) {
   if (LAM == 0) return median3(div6(5.f * c + 2.f * d - u), c, median3(10.f * c - 9.f * u, c, d));  // quick
