@@ -63,6 +63,7 @@ typedef struct wl_config {
 enum {
   WL_FLAG_GENERAL_COEFF = 1, /* never use the constant-coefficient (NoBody) kernel variants */
   WL_FLAG_NO_PERSISTENT = 4, /* launch every coarse-level operation separately instead of the one cooperative coarse-level kernel */
+  WL_FLAG_NCCL_HALO = 8,     /* multi-GPU: exchange halo planes with ncclSend/ncclRecv instead of the peer-to-peer NVLink kernel */
   WL_FLAG_UNFUSED_GS = 2,    /* run GaussSeidelRB! as six separate launches like the reference (debugging aid) */
 };
 

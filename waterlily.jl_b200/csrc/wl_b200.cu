@@ -116,6 +116,11 @@ struct Level {
   size_t cells() const { return (size_t)g.sc; }
 };
 
+struct Chunk {
+  char* base;
+  size_t size, used;
+};
+
 struct ProfRec {
   const char* name;
   cudaEvent_t a, b;
@@ -142,6 +147,12 @@ struct wl_handle {
   std::vector<float> log;  // rows of (iter, rinf, r2, omega)
   bool logging = false;
   Dist dist;
+  std::vector<Chunk> chunks;
+  // peer-to-peer halo exchange over NVLink (CUDA IPC): mappings of the neighbours' chunks and a mailbox of flags
+  bool p2p = false;
+  std::vector<char*> peer_base[2];  // [0] lower neighbour, [1] upper neighbour
+  int* mbox = nullptr;              // ready[2], arrived[2], block counter, error
+  int halo_seq = 0;
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
   int slab_min_planes = 16;
@@ -217,13 +228,26 @@ static inline size_t nblocks(const Box& b, dim3 t) {
       LAUNCH(h, kern<2>, grid, block, __VA_ARGS__);               \
   } while (0)
 
+// Field memory comes from a few big chunks (bump allocation, identical on every rank), so that a neighbouring rank can address
+// any field of this rank through one CUDA-IPC mapping per chunk: peer pointer = peer chunk base + (local pointer − local chunk base).
 static int dalloc(wl_handle* h, float** p, size_t nfloats) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, nfloats * sizeof(float));
-  if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", nfloats * sizeof(float), cudaGetErrorString(e));
-  e = cudaMemsetAsync(q, 0, nfloats * sizeof(float), h->st);
+  const size_t bytes = (nfloats * sizeof(float) + 511) / 512 * 512;
+  if (h->chunks.empty() || h->chunks.back().used + bytes > h->chunks.back().size) {
+    Chunk c;
+    c.size = std::max(bytes, (size_t)256 << 20);
+    c.used = 0;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, c.size);
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", c.size, cudaGetErrorString(e));
+    c.base = (char*)q;
+    h->chunks.push_back(c);
+    h->allocs.push_back(q);
+  }
+  Chunk& c = h->chunks.back();
+  void* q = c.base + c.used;
+  c.used += bytes;
+  cudaError_t e = cudaMemsetAsync(q, 0, bytes, h->st);
   if (e != cudaSuccess) return fail("cudaMemset: %s", cudaGetErrorString(e));
-  h->allocs.push_back(q);
   *p = (float*)q;
   return 0;
 }
@@ -233,11 +257,68 @@ static const float* dtp(wl_handle* h) { return h->d_dthist + (h->dt_dev_len - 1)
 // ---- z-slab halo exchange and collectives (NCCL over NVLink) ---------------------------------
 // Ghost planes of a field on a slab level: my top interior plane → the upper neighbour's lower ghost plane, my bottom interior
 // plane → the lower neighbour's upper ghost plane.  Sends/receives to one peer are posted in matching order (P = 2 periodic).
+// Peer pointer of a local field address on the lower (0) / upper (1) neighbour.
+static float* peer_ptr(const wl_handle* h, int side, const float* local) {
+  const char* q = (const char*)local;
+  for (size_t k = 0; k < h->chunks.size(); k++) {
+    const Chunk& c = h->chunks[k];
+    if (q >= c.base && q < c.base + c.size) return (float*)(h->peer_base[side][k] + (q - c.base));
+  }
+  return nullptr;
+}
+// P2P exchange of up to 16 planes: planes[i] = {local source plane, side (0 lower / 1 upper), local address of the DESTINATION
+// plane as it is laid out on the neighbour (same layout on every rank)}.
+struct PlaneMove {
+  const float* src;
+  int side;
+  const float* dst_local;
+};
+static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n) {
+  HaloSegs segs;
+  memset(&segs, 0, sizeof segs);
+  const Dist& d = h->dist;
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const int peer = mv[i].side ? d.up : d.down;
+    if (peer < 0) continue;
+    segs.src[m] = mv[i].src;
+    segs.dst[m] = peer_ptr(h, mv[i].side, mv[i].dst_local);
+    if (!segs.dst[m]) return fail("halo plane outside the IPC-mapped chunks");
+    m++;
+  }
+  segs.nseg = m;
+  const int cnt4 = (int)(g.s[2] / 4);
+  int* plo = d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)h->mbox) : nullptr;
+  int* phi = d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)h->mbox) : nullptr;
+  const int seq = ++h->halo_seq;
+  const long long total4 = (long long)m * cnt4;
+  const int nb = (int)std::max<long long>(1, std::min<long long>(128, (total4 + 2047) / 2048));
+  prof_begin(h, "halo_exchange_p2p");
+  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 4000000000LL);
+  prof_end(h);
+  h->launches++;
+  return 0;
+}
+
 static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
   if (!h->dist.on() || !l.slab) return 0;
   const Grid& g = l.g;
   const size_t cnt = (size_t)g.s[2];
   const Dist& d = h->dist;
+  if (h->p2p && ncomp <= 8) {
+    PlaneMove mv[16];
+    int n = 0;
+    for (int c = 0; c < ncomp; c++) {
+      float* b = a + (size_t)c * g.sc;
+      mv[n++] = {b + g.s[2] * (g.N[2] - 2), 1, b};                      // my top interior plane → upper neighbour's lower ghost
+      mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};         // my bottom interior plane → lower neighbour's upper ghost
+    }
+    return p2p_push(h, g, mv, n);
+  }
+  if (h->p2p) {  // more than 8 components (μ₁): in two batches
+    TRY(exch(h, l, a, 8));
+    return exch(h, l, a + (size_t)8 * g.sc, ncomp - 8);
+  }
   prof_begin(h, "halo_exchange");
   NCK(g_nccl.GroupStart());
   for (int c = 0; c < ncomp; c++) {
@@ -258,6 +339,16 @@ static int exch2(wl_handle* h, const Level& l, float* a0, float* a1) {
   const size_t cnt = (size_t)g.s[2];
   const Dist& d = h->dist;
   float* f[2] = {a0, a1};
+  if (h->p2p) {
+    PlaneMove mv[4];
+    int n = 0;
+    for (int c = 0; c < 2; c++) {
+      float* b = f[c];
+      mv[n++] = {b + g.s[2] * (g.N[2] - 2), 1, b};
+      mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};
+    }
+    return p2p_push(h, g, mv, n);
+  }
   prof_begin(h, "halo_exchange");
   NCK(g_nccl.GroupStart());
   for (int c = 0; c < 2; c++) {
@@ -277,6 +368,20 @@ static int exch_u(wl_handle* h, float* u) {
   const Grid& g = h->g;
   const size_t cnt = (size_t)g.s[2];
   const Dist& d = h->dist;
+  if (h->p2p) {
+    PlaneMove mv[12];
+    int n = 0;
+    for (int c = 0; c < 3; c++) {
+      float* b = u + (size_t)c * g.sc;
+      float* elo = h->uext + (size_t)c * g.s[2];
+      float* ehi = h->uext + (size_t)(3 + c) * g.s[2];
+      mv[n++] = {b + g.s[2] * (g.N[2] - 2), 1, b};
+      mv[n++] = {b + g.s[2] * (g.N[2] - 3), 1, elo};
+      mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};
+      mv[n++] = {b + g.s[2] * 2, 0, ehi};
+    }
+    return p2p_push(h, g, mv, n);
+  }
   prof_begin(h, "halo_exchange_u");
   NCK(g_nccl.GroupStart());
   for (int c = 0; c < 3; c++) {
@@ -1014,6 +1119,12 @@ static int check_flags(wl_handle* h) {
   CK(cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   if (f) return fail("the flux kernel met a non-finite or denormal-range (<8e-31) value: the velocity field has diverged");
+  if (h->mbox) {
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, h->mbox + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (e) return fail("peer-to-peer halo exchange timed out waiting for a neighbouring rank");
+  }
   return 0;
 }
 static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vector
@@ -1095,6 +1206,48 @@ int wl_device_count(void) {
 
 static int create_impl(const wl_config* cfg, int rank, int nranks, const void* nccl_id, wl_handle** out);
 
+// Map the neighbours' field chunks (CUDA IPC over NVLink).  The handles travel through an NCCL all-gather.
+static int setup_p2p(wl_handle* h) {
+  const Dist& d = h->dist;
+  const int nch = (int)h->chunks.size();
+  // all ranks must have made the same allocations
+  const size_t rec = sizeof(cudaIpcMemHandle_t);
+  std::vector<char> mine((size_t)nch * rec);
+  for (int k = 0; k < nch; k++) {
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h->chunks[k].base));
+    memcpy(mine.data() + (size_t)k * rec, &hd, rec);
+  }
+  char* dbuf = nullptr;
+  const size_t per = (size_t)nch * rec;
+  CK(cudaMalloc((void**)&dbuf, per * d.P));
+  CK(cudaMemcpyAsync(dbuf + per * d.rank, mine.data(), per, cudaMemcpyHostToDevice, h->st));
+  NCK(g_nccl.AllGather(dbuf + per * d.rank, dbuf, per, 0 /*ncclInt8*/, d.comm, h->st));
+  std::vector<char> all(per * d.P);
+  CK(cudaMemcpyAsync(all.data(), dbuf, per * d.P, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaFree(dbuf));
+  const int nb[2] = {d.down, d.up};
+  for (int side = 0; side < 2; side++) {
+    h->peer_base[side].assign(nch, nullptr);
+    if (nb[side] < 0) continue;
+    if (side == 1 && d.up == d.down) {  // two ranks, periodic: one neighbour on both sides
+      h->peer_base[1] = h->peer_base[0];
+      continue;
+    }
+    for (int k = 0; k < nch; k++) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, all.data() + per * nb[side] + (size_t)k * rec, rec);
+      void* q = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle (rank %d chunk %d): %s", nb[side], k, cudaGetErrorString(e));
+      h->peer_base[side][k] = (char*)q;
+    }
+  }
+  h->p2p = true;
+  return 0;
+}
+
 int wl_create(const wl_config* cfg, wl_handle** out) { return create_impl(cfg, 0, 1, nullptr, out); }
 
 int wl_dist_unique_id(void* id128) {
@@ -1162,6 +1315,11 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       }
       h->g = slab_grid(h, h->g);
       if ((rc = dalloc(h, &h->uext, (size_t)6 * h->g.s[2]))) break;
+      {
+        float* q = nullptr;
+        if ((rc = dalloc(h, &q, 64))) break;
+        h->mbox = (int*)q;
+      }
     }
     const size_t n = (size_t)h->g.sc;
     const int D = h->D;
@@ -1223,6 +1381,10 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
     if (cudaMallocHost((void**)&h->h_out, NSLOTS * sizeof(double)) != cudaSuccess) { rc = fail("cudaMallocHost"); break; }
     if ((rc = dalloc(h, &h->d_scal, 16))) break;
     if ((rc = ensure_dt_capacity(h, 1024))) break;
+    if (h->dist.on() && !(cfg->flags & WL_FLAG_NCCL_HALO)) {
+      if (cudaStreamSynchronize(h->st) != cudaSuccess) { rc = fail("init sync"); break; }
+      if ((rc = setup_p2p(h))) break;
+    }
     // Flow ctor: Δt=[dt0]; u = uBC everywhere; BC!; exitBC!(u,u,0); u⁰=copy(u); μ₀=1; BC!(μ₀,0)
     h->dt.assign(1, cfg->dt0);
     if (cudaMemcpyAsync(h->d_dthist, h->dt.data(), sizeof(float), cudaMemcpyHostToDevice, h->st) != cudaSuccess) { rc = fail("memcpy dt"); break; }
@@ -1254,6 +1416,13 @@ int wl_destroy(wl_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->p2p) {
+    for (int side = 0; side < 2; side++) {
+      if (side == 1 && h->dist.up == h->dist.down) break;
+      for (char* q : h->peer_base[side])
+        if (q) cudaIpcCloseMemHandle(q);
+    }
+  }
   if (h->dist.comm) g_nccl.CommDestroy(h->dist.comm);
   for (void* q : h->allocs) cudaFree(q);
   if (h->d_dthist) cudaFree(h->d_dthist);

@@ -720,3 +720,74 @@ __global__ void k_cfl_final(RedBuf R, int slot_a, int slot_b, float nu, float* d
   const float mm = (float)fmax(R.out[slot_a], R.out[slot_b]);
   *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
 }
+
+// ------------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange (z slabs): one launch pushes this rank's boundary planes straight into the neighbours' ghost planes
+// with NVLink stores and returns only when the neighbours' planes have arrived here.  Flags live in each rank's `mbox`
+// (ints: [0] ready-from-lower, [1] ready-from-upper, [2] arrived-from-lower, [3] arrived-from-upper, [4] block counter,
+// [5] error) and carry the exchange's sequence number, identical on every rank.
+//   A. tell both neighbours "my ghost planes may be overwritten" (everything that read them is earlier in this stream);
+//   B. wait until both neighbours said so;            C. copy;            D. fence, tell them "arrived", wait for theirs.
+// Every wait is bounded (≈2 s): a lost partner raises the error flag instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+struct HaloSegs {
+  int nseg;
+  const float* src[16];
+  float* dst[16];
+};
+
+__device__ __forceinline__ int ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_flag_sys(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int seq, int* my, int* peer_lo, int* peer_hi, long long timeout) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      if (peer_lo) st_flag_sys(peer_lo + 1, seq);  // I am the upper neighbour of my lower neighbour
+      if (peer_hi) st_flag_sys(peer_hi + 0, seq);
+    }
+    const long long t0 = clock64();
+    int good = 1;
+    while ((peer_lo && ld_flag(my + 0) < seq) || (peer_hi && ld_flag(my + 1) < seq)) {
+      if (clock64() - t0 > timeout) {
+        good = 0;
+        st_flag_sys(my + 5, 1);
+        break;
+      }
+    }
+    ok = good;
+  }
+  __syncthreads();
+  if (ok) {
+    const long long total = (long long)segs.nseg * cnt4;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+      const int sgi = (int)(q / cnt4);
+      const int e = (int)(q - (long long)sgi * cnt4);
+      reinterpret_cast<float4*>(segs.dst[sgi])[e] = reinterpret_cast<const float4*>(segs.src[sgi])[e];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(my + 4, 1);
+    if (t == (int)gridDim.x - 1) {
+      atomicExch(my + 4, 0);
+      __threadfence_system();
+      if (peer_lo) st_flag_sys(peer_lo + 3, seq);
+      if (peer_hi) st_flag_sys(peer_hi + 2, seq);
+      const long long t0 = clock64();
+      while ((peer_lo && ld_flag(my + 2) < seq) || (peer_hi && ld_flag(my + 3) < seq)) {
+        if (clock64() - t0 > timeout) {
+          st_flag_sys(my + 5, 1);
+          break;
+        }
+      }
+      __threadfence_system();
+    }
+  }
+}
