@@ -165,6 +165,9 @@ struct wl_handle {
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
+  // Uniform mode on one GPU never reads the periodic ghost cells of u (every reader wraps its indices), so the BC! launches of
+  // mom_step! are deferred until something outside the step loop looks at u (flush_ghosts).
+  bool ghosts_dirty = false;
   cudaStream_t st = nullptr;
   int64_t launches = 0;
   double tol;
@@ -465,6 +468,21 @@ static int launch_exitbc(wl_handle* h, float* u, const float* u0, float dt_scale
 }
 
 // ---- Poisson hierarchy ---------------------------------------------------------------------
+static inline bool lazy_bc(const wl_handle* h) { return h->uni && h->D == 3 && !h->dist.on() && !h->cfg.exitBC; }
+// BC!(u) of mom_step! (src/Flow.jl:194,209,230): deferred in uniform mode, see wl_handle::ghosts_dirty
+static void step_bc(wl_handle* h, const float* keep) {
+  if (lazy_bc(h)) {
+    h->ghosts_dirty = true;
+    return;
+  }
+  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, keep);
+}
+static void flush_ghosts(wl_handle* h) {
+  if (!h->ghosts_dirty) return;
+  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  launch_bc_vec(h, h->g, h->u0, h->cfg.uBC, h->cfg.exitBC, h->u0);
+  h->ghosts_dirty = false;
+}
 static inline bool divisible(int N) { return N % 2 == 0 && N > 4; }  // src/MultiLevelPoisson.jl:52
 
 // Local grid of a z-slab level: nz/P interior planes, ghost planes fed by the neighbours (zopen), stale marks on the global
@@ -920,9 +938,21 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
       LAUNCH(h, f_div_residual<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
              l.zchunk(), h->red, SLOT_RSUM);
     TRY(allreduce_slot(h, SLOT_RSUM, WL_NCCL_SUM));
-    LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), h->red, SLOT_RSUM, SLOT_R2);
     TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
-    TRY(exch(h, l, l.r, 1));
+    // residual! subtracts the mean only when |s| > 2eps (src/Poisson.jl:96); otherwise r is final and the Σr² of the same pass is L₂
+    static_assert(SLOT_R2 == SLOT_RSUM + 1, "f_div_residual reduces Σr and Σr² into adjacent slots");
+    CK(cudaMemcpyAsync(h->h_out + SLOT_RSUM, h->red.out + SLOT_RSUM, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    const float s = (float)h->h_out[SLOT_RSUM] / count;
+    if (std::fabs(s) > 2.f * 1.1920929e-7f) {
+      LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), h->red, SLOT_RSUM, SLOT_R2);
+      TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
+      TRY(exch(h, l, l.r, 1));
+    } else {
+      TRY(exch(h, l, l.r, 1));
+      *r2 = (float)h->h_out[SLOT_R2];
+      return 0;
+    }
   } else {
     LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
     LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
@@ -1094,7 +1124,7 @@ static int project(wl_handle* h, float w) {
       LAUNCH(h, f_correct<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.x, h->u, h->p, dtp(h), w, l.zchunk());
   } else
     LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
-  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  step_bc(h, h->u);
   TRY(exch_u(h, h->u));
   TRY(exch(h, l, h->p, 1));
   return 0;
@@ -1147,13 +1177,13 @@ static int mom_step(wl_handle* h) {
   std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
   // predictor  src/Flow.jl:190-196
   momentum(h, 0);
-  launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u0);
+  step_bc(h, h->u0);
   if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
   TRY(exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
   momentum(h, 1);
-  launch_bc_vec(h, g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
+  step_bc(h, h->u);
   TRY(exch_u(h, h->u));
   TRY(project(h, 0.5f));
   // push!(a.Δt, CFL(a))
@@ -1436,6 +1466,7 @@ int wl_destroy(wl_handle* h) {
 int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
   if (!h || !src) return fail("null argument");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   float* p;
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
@@ -1445,6 +1476,7 @@ int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
 int wl_download(wl_handle* h, int field, float* dst, int dst_is_device) {
   if (!h || !dst) return fail("null argument");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   float* p;
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
@@ -1455,6 +1487,7 @@ int wl_download(wl_handle* h, int field, float* dst, int dst_is_device) {
 int wl_apply_bc(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
   TRY(launch_exitbc(h, h->u, h->u, 0.f));
   TRY(exch_u(h, h->u));
@@ -1466,6 +1499,7 @@ int wl_apply_bc(wl_handle* h) {
 int wl_measure_bc(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   const float zero[3] = {0, 0, 0};
   launch_bc_vec(h, h->g, h->mu0, zero, 0, h->mu0);
   launch_bc_vec(h, h->g, h->V, zero, h->cfg.exitBC, h->V);
@@ -1479,6 +1513,7 @@ int wl_measure_bc(wl_handle* h) {
 int wl_update(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   return update_levels(h);
 }
 
@@ -1522,6 +1557,7 @@ int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t ma
 int wl_project(wl_handle* h, float w) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   return project(h, w);
 }
 
@@ -1529,6 +1565,7 @@ int wl_conv_diff(wl_handle* h, int from_u0) {
   if (!h) return fail("null handle");
   if (h->dist.on()) return fail("standalone conv_diff! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   conv_bdim1(h, from_u0 ? h->u0 : h->u, 0);
   CK(cudaGetLastError());
   return 0;
@@ -1537,6 +1574,7 @@ int wl_conv_diff(wl_handle* h, int from_u0) {
 int wl_cfl(wl_handle* h, float* dt_out) {
   if (!h || !dt_out) return fail("null argument");
   CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
   cfl(h, h->d_scal + 4);
   CK(cudaMemcpyAsync(dt_out, h->d_scal + 4, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));

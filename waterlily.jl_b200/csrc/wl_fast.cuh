@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef
 
 // ------------------------------------------------------------------------------------------------
 // div + x.*=dt + residual! part 1 (src/Flow.jl:225, src/Poisson.jl:93-95):
-//   z = Σ_d (u_d[I+δ_d] − u_d[I]);  x = p·dt;  r = iD==0 ? 0 : z − A x;   Σr → out[slot], Σr² → out[slot+1]
+//   z = Σ_d (u_d[I+δ_d] − u_d[I]);  x = p·dt;  r = iD==0 ? 0 : z − A x;   Σr → out[slot], Σr² → out[slot+1]  (slot+1 must be SLOT_R2)
 // σ (=z) is not stored in UNI mode (it is pure scratch there; CFL rewrites the interior every step).
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_div_residual(Grid g, C
   F.w = nullptr;
   F.s = dt;
   F.kind = 1;
-  double sum = 0.0;
+  double sum = 0.0, l2 = 0.0;  // Σr and, for the case that residual! leaves r alone (|mean| ≤ 2eps), Σr² = L₂
   march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& xs, float left, float right, const float4& ym, const float4& yp, const float4& zm,
                       const float4& zp) {
     // u_x needs the value one cell to the right of the group
@@ -384,13 +384,14 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_div_residual(Grid g, C
     float uxr_edge = 0.f;
     if (f.on) {
       ux = ld4(u + o);
-      if (f.lane == 31 || f.lastgrp) uxr_edge = u[o + 4];
+      if (f.lane == 31 || f.lastgrp) uxr_edge = u[f.row + pz + f.xr];
     }
     float uxr = __shfl_down_sync(FULLMASK, ux.x, 1);
     if (f.lane == 31 || f.lastgrp) uxr = uxr_edge;
     if (f.on) {
-      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + o + g.s[1]);
-      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + o + g.s[2]);
+      // upper neighbours through the periodic wrap (= the ghost value after BC!), so u's periodic ghosts need not be current
+      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + f.rowp + pz + f.x0);
+      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + f.row + g.s[2] * zwrap_hi(g, z) + f.x0);
       float4 dv;
       dv.x = 0.f + (ux.y - ux.x);
       dv.x += uyp.x - uy.x;
@@ -417,10 +418,11 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_div_residual(Grid g, C
       st4(x + o, xs);
       st4(r + o, rr);
       sum += (double)rr.x + (double)rr.y + (double)rr.z + (double)rr.w;
+      l2 += (double)rr.x * rr.x + (double)rr.y * rr.y + (double)rr.z * rr.z + (double)rr.w * rr.w;
     }
   });
-  double v[1] = {sum}, fin[1];
-  grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+  double v[2] = {sum, l2}, fin[2];
+  grid_reduce<RED_SUM, 2>(v, R, slot, fin);
 }
 
 // residual! part 2 + L₂ (src/Poisson.jl:95-97,189): s = Σr/|inside|; |s|>2eps ⇒ r −= s; Σr² → out[slot_out]
@@ -590,8 +592,11 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
   auto wrap = [&](int v, int d) -> int {  // periodic image inside [0, N-1]; clamp otherwise (clamped values are never used)
     const int N = g.N[d];
     if (g.per[d]) {
-      if (v < 0) v += N - 2;
-      else if (v > N - 1) v -= N - 2;
+      // FUSE (uniform mode) also maps the ghost cells themselves to their interior images, so the tile never depends on the
+      // periodic ghosts of u being current (deferred BC!); otherwise a ghost is read as stored: with exitBC! it legitimately
+      // differs from its image (the exit plane is rewritten after BC!, src/Flow.jl:194-195)
+      if (v < (FUSE ? 1 : 0)) v += N - 2;
+      else if (v > N - (FUSE ? 2 : 1)) v -= N - 2;
     }
     return max(0, min(N - 1, v));
   };
@@ -833,18 +838,20 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_cfl(Grid g, const floa
   const Frame f = make_frame(g, zchunk);
   double m = 0.0;
   for (int z = f.z0; z < f.z1; z++) {
-    const i64 o = f.row + g.s[2] * z + f.x0;
+    const i64 pz = g.s[2] * z;
+    const i64 o = f.row + pz + f.x0;
     float4 ux = f4zero();
     float e = 0.f;
     if (f.on) {
       ux = ld4(u + o);
-      if (f.lane == 31 || f.lastgrp) e = u[o + 4];
+      if (f.lane == 31 || f.lastgrp) e = u[f.row + pz + f.xr];
     }
     float uxr = __shfl_down_sync(FULLMASK, ux.x, 1);
     if (f.lane == 31 || f.lastgrp) uxr = e;
     if (f.on) {
-      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + o + g.s[1]);
-      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + o + g.s[2]);
+      // upper neighbours through the periodic wrap (see f_div_residual)
+      const float4 uy = ld4(u + g.sc + o), uyp = ld4(u + g.sc + f.rowp + pz + f.x0);
+      const float4 uz = ld4(u + 2 * g.sc + o), uzp = ld4(u + 2 * g.sc + f.row + g.s[2] * zwrap_hi(g, z) + f.x0);
       float4 s;
       s.x = 0.f + (fmaxf(0.f, ux.y) + fmaxf(0.f, -ux.x));
       s.x += fmaxf(0.f, uyp.x) + fmaxf(0.f, -uy.x);
