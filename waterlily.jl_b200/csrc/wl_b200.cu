@@ -16,6 +16,7 @@
 #include "../../include/wl_b200.h"
 #include "wl_dist.h"
 #include "wl_fast.cuh"
+#include "wl_conv4.cuh"
 
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -165,6 +166,8 @@ struct wl_handle {
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
+  bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
+  int conv4_zchunk = 32;
   // Uniform mode on one GPU never reads the periodic ghost cells of u (every reader wraps its indices), so the BC! launches of
   // mom_step! are deferred until something outside the step loop looks at u (flush_ghosts).
   bool ghosts_dirty = false;
@@ -1034,8 +1037,22 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   const int XM = FUSE ? g.N[0] - 2 : g.N[0] - 1, YM = FUSE ? g.N[1] - 2 : g.N[1] - 1, ZM = FUSE ? g.N[2] - 2 : g.N[2] - 1;
   const int zchunk = std::min(32, ZM);
   dim3 gr(cdiv(XM, 32), cdiv(YM, CTY), cdiv(ZM, zchunk));
-  prof_begin(h, "fm_conv");
   const bool nowall = g.per[0] && g.per[1] && (g.per[2] || (g.zopen[0] && g.zopen[1]));
+  if (FUSE && nowall && h->conv4 && (g.N[0] - 2) % 4 == 0) {  // uniform mode: four cells per thread
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(fm_conv4<LAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
+      attr = true;
+    }
+    const int zc = std::min(h->conv4_zchunk, g.N[2] - 2);
+    dim3 g4(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, C4TY), cdiv(g.N[2] - 2, zc));
+    prof_begin(h, "fm_conv4");
+    fm_conv4<LAM><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags);
+    prof_end(h);
+    h->launches++;
+    return;
+  }
+  prof_begin(h, "fm_conv");
   if (nowall)
     fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
                                                                             h->red, SLOT_PHIMAX, h->uext, h->d_flags);
@@ -1312,6 +1329,8 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->D = cfg->D;
   h->tol = cfg->tol > 0 ? (double)cfg->tol : 1e-4;
   h->fused_gs = !(cfg->flags & WL_FLAG_UNFUSED_GS);
+  if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
+  if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
   int N[3];

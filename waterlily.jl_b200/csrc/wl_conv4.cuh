@@ -1,0 +1,313 @@
+// wl_conv4.cuh — fm_conv4: the momentum flux kernel of uniform mode (no body, no walls), four cells per thread.
+//
+// Same arithmetic, same association order and same results as fm_conv<LAM, FUSE=true, PER3=true> (wl_fast.cuh), i.e.
+// conv_diff! in gather form with shared face fluxes (src/Flow.jl:38-62) fused with BDIM! for μ₀≡1, μ₁≡0, V≡0
+// (src/Flow.jl:176-180) and scale_u! (src/Flow.jl:211-214).  fm_conv is issue-bound (713 instructions per cell, half of them
+// shared-memory loads, integer and control overhead of a one-cell-per-thread tile); here a lane owns one aligned float4 of x,
+// so a stencil row is one LDS.128 instead of four LDS.32 and all index arithmetic is amortised over four cells.
+//
+// Geometry: blockDim = (32, C4TY); a warp owns a 128-cell row segment, a block a 128 × C4TY tile, marching over a z chunk.
+// Shared memory holds the three velocity components of planes z, z+1, z+2 (and the plane being fetched with cp.async) with
+// an in-plane halo of 2, loaded through the periodic wrap so the ghost cells of u are never read.  Plane z-1 of a lane's own
+// column lives in registers.  Face fluxes are evaluated once: the lower z flux is carried from the previous plane, the upper
+// x flux of a lane's last cell comes from the next lane by shuffle, the lower y fluxes are computed one plane ahead and shared
+// between the rows (warps) of a block through shared memory.
+#pragma once
+#include "wl_fast.cuh"
+
+#define C4TY 8
+#define C4RING 4
+#define C4W 136                // row pitch: 4 + 128 + 4 floats, the x halo of 2 sits inside the pads
+#define C4H (C4TY + 4)         // rows incl. the y halo of 2
+#define C4CS (C4H * C4W)       // one component plane
+#define C4PS (3 * C4CS)        // one ring slot
+#define C4Q (C4W / 4)          // float4 per row
+#define C4FILL ((C4H * C4Q + 32 * C4TY - 1) / (32 * C4TY))
+#define C4SMEM ((C4RING * C4PS + 2 * 3 * (C4TY + 1) * 32 * 4) * 4)
+
+// x/6, exact as div6_flag (wl_kernels.cuh); a non-zero input outside the proven range lands in `bad` (tested once per thread)
+__device__ __forceinline__ float div6_bad(float x, unsigned& bad) {
+  const float C = 0.16666667163372039794921875f;
+  const float q0 = x * C;
+  const float r = __fmaf_rn(-6.f, q0, x);
+  const float q = __fmaf_rn(r, C, q0);
+  const unsigned b = __float_as_uint(x) & 0x7fffffffu;
+  const unsigned LO = 0x0D800000u;  // 2^-100 = 7.888609052210118e-31f
+  const unsigned HI = 0x7F61B1E6u;  // 3.0e38f
+  const bool inr = (b - LO) <= (HI - LO);
+  bad |= inr ? 0u : b;
+  return inr ? q : q0;  // ±0 → ±0 (= q0)
+}
+template <int LAM>
+__device__ __forceinline__ float limiter_b(float u, float c, float d, unsigned& bad) {
+  if (LAM == 0) return median3(div6_bad(5.f * c + 2.f * d - u, bad), c, median3(10.f * c - 9.f * u, c, d));  // quick
+  if (LAM == 1) return (c + d) / 2.f;                                                                          // cds
+  return (c <= fminf(u, d) || c >= fmaxf(u, d)) ? c : c + (d - c) * (c - u) / (d - u);                        // vanLeer
+}
+// ϕu(j, CI(I,i), u, û, λ) − ν ∂(j, CI(I,i), u) for an inner / periodic face (src/Flow.jl:8-11,52)
+template <int LAM>
+__device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, unsigned& bad) {
+  const float diff = nu * (u0c - um1);
+  const bool pos = uf > 0.f;
+  const float conv = uf * limiter_b<LAM>(pos ? um2 : up1, pos ? um1 : u0c, pos ? u0c : um1, bad);
+  return conv - diff;
+}
+template <int LAM>
+__device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, float nu,
+                                          unsigned& bad) {
+  return make_float4(flux_p<LAM>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
+                     flux_p<LAM>(uf.z, um2.z, um1.z, u0c.z, up1.z, nu, bad), flux_p<LAM>(uf.w, um2.w, um1.w, u0c.w, up1.w, nu, bad));
+}
+__device__ __forceinline__ float4 avg4(const float4& a, const float4& b) {
+  return make_float4((a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f, (a.w + b.w) / 2.f);
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+
+template <int LAM>
+__global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__ Grid g, const float* __restrict__ ua, const float* __restrict__ u0,
+                                                         float* __restrict__ out, const float* __restrict__ dtp, float nu, int zchunk, int corrector, RedBuf R,
+                                                         int slot, const float* __restrict__ uext, int* __restrict__ flag) {
+  extern __shared__ float4 smem4[];
+  float* const T = reinterpret_cast<float*>(smem4);      // [C4RING][3][C4H][C4W]
+  float* const Fy = T + C4RING * C4PS;                    // [2][3][C4TY+1][32] float4: lower y fluxes of planes z, z+1 (row C4TY: the block's upper edge)
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int tid = lane + 32 * ty;
+  const int xb = 1 + 128 * blockIdx.x, yb = 1 + C4TY * blockIdx.y;
+  const int x0 = xb + 4 * lane, y = yb + ty;
+  const int z0 = 1 + zchunk * blockIdx.z, z1 = min(z0 + zchunk, g.N[2] - 1);
+  const bool on = x0 <= g.N[0] - 2 && y <= g.N[1] - 2;
+  const float dt = *dtp;
+  unsigned bad = 0u;
+
+  // ---- tile fill: every plane is fetched with the same per-thread float4 elements ----
+  int gof[C4FILL], sof[C4FILL];  // in-plane global offset / offset inside a component plane of the tile (-1: none)
+#pragma unroll
+  for (int k = 0; k < C4FILL; k++) {
+    const int e = tid + k * 32 * C4TY;
+    const int row = e / C4Q, q = e - row * C4Q;
+    int xx = xb - 4 + 4 * q;  // first cell of the float4; interior extents are multiples of 4, so a float4 never straddles the wrap
+    if (xx < 1) xx += g.N[0] - 2;
+    else if (xx > g.N[0] - 2) xx -= g.N[0] - 2;
+    xx = max(1, min(g.N[0] - 5, xx));
+    int yy = yb - 2 + row;
+    if (yy < 1) yy += g.N[1] - 2;
+    else if (yy > g.N[1] - 2) yy -= g.N[1] - 2;
+    yy = max(1, min(g.N[1] - 2, yy));
+    sof[k] = e < C4H * C4Q ? row * C4W + 4 * q : -1;
+    gof[k] = g.xo + xx + g.px * yy;
+  }
+  // global source of plane zz: periodic wrap, or (z slabs) the exchanged ghost plane / the second halo plane in uext
+  auto plane_src = [&](int zz, const float*& src, i64& cs) {
+    if (zz < 0 && g.zopen[0]) {
+      src = uext;
+      cs = g.s[2];
+    } else if (zz > g.N[2] - 1 && g.zopen[1]) {
+      src = uext + 3 * g.s[2];
+      cs = g.s[2];
+    } else {
+      if (g.per[2]) {
+        if (zz < 1) zz += g.N[2] - 2;
+        else if (zz > g.N[2] - 2) zz -= g.N[2] - 2;
+      }
+      zz = max(0, min(g.N[2] - 1, zz));
+      src = ua + g.s[2] * zz;
+      cs = g.sc;
+    }
+  };
+  auto fill = [&](int zz) {
+    const float* src;
+    i64 cs;
+    plane_src(zz, src, cs);
+    float* dst = T + ((zz + 1024) & (C4RING - 1)) * C4PS;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+      for (int k = 0; k < C4FILL; k++)
+        if (sof[k] >= 0) cp_async16(dst + c * C4CS + sof[k], src + c * cs + gof[k]);
+    }
+  };
+  // own column of plane zz straight from global memory (prologue only)
+  auto own_global = [&](int zz, int c) -> float4 {
+    const float* src;
+    i64 cs;
+    plane_src(zz, src, cs);
+    const int xx = min(x0, g.N[0] - 5), yy = min(y, g.N[1] - 2);
+    return ld4(src + c * cs + g.xo + xx + (i64)g.px * yy);
+  };
+
+  const int col = (ty + 2) * C4W + 4 + 4 * lane;  // own float4 inside a component plane of the tile
+  auto P = [&](int zz) -> const float* { return T + ((zz + 1024) & (C4RING - 1)) * C4PS + col; };
+  auto fy4 = [&](int buf, int c, int row) -> float4* { return reinterpret_cast<float4*>(Fy) + ((buf * 3 + c) * (C4TY + 1) + row) * 32 + lane; };
+
+  // prologue: planes z0-1, z0, z0+1 in the ring, plane z0-2 of the own column in registers; the loop starts one plane early
+  // (z = z0-1, nothing stored) to produce the carried fluxes of plane z0
+  fill(z0 - 1);
+  fill(z0);
+  fill(z0 + 1);
+  float4 m1[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) m1[c] = own_global(z0 - 2, c);
+  cp_async_wait_all();
+  __syncthreads();
+
+  float4 Fz[3] = {f4zero(), f4zero(), f4zero()};  // lower z fluxes of the current plane
+  float gmax = 0.f;
+  const bool lastrow = ty == C4TY - 1;
+  for (int z = z0 - 1; z < z1; z++) {
+    const bool live = z >= z0;
+    if (z + 1 < z1) fill(z + 3);  // into the slot plane z-1 left; read as plane z+2 of the next step
+    const float* p0 = P(z);
+    const float* p1 = P(z + 1);
+    const float* p2 = P(z + 2);
+    float4 r[3], own[3];
+    float4 Fx2lo = f4zero();
+    // ---- x fluxes on plane z (only needed for stored planes) ----
+    if (live) {
+      const float4 a0 = ld4(p0);                      // u_x on the own cells
+      const float4 b1 = ld4(p0 - C4W);                // u_x one row down   (û of the y-momentum flux)
+      float fex = 0.f;                                // the face beyond the warp's last cell: lanes 0-2 compute one component each
+      if (lane < 3) {
+        const float* e = T + ((z + 1024) & (C4RING - 1)) * C4PS + (ty + 2) * C4W + 4 + 128;  // cell xb+128 of u_x
+        float other;
+        if (lane == 0) other = e[-1];
+        else if (lane == 1) other = e[-C4W];
+        else {  // plane z-1 is not in the ring any more: one scalar from global memory
+          const float* src;
+          i64 cs;
+          plane_src(z - 1, src, cs);
+          int xx = xb + 128;
+          if (xx > g.N[0] - 2) xx -= g.N[0] - 2;
+          other = src[g.xo + min(xx, g.N[0] - 2) + (i64)g.px * min(y, g.N[1] - 2)];
+        }
+        const float* ei = e + lane * C4CS;
+        fex = flux_p<LAM>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu, bad);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 a = c == 0 ? a0 : ld4(p0 + c * C4CS);
+        const float2 l2 = *reinterpret_cast<const float2*>(p0 + c * C4CS - 2);
+        const float rr = p0[c * C4CS + 4];
+        own[c] = a;
+        float4 uf;
+        if (c == 0) uf = make_float4((a0.x + l2.y) / 2.f, (a0.y + a0.x) / 2.f, (a0.z + a0.y) / 2.f, (a0.w + a0.z) / 2.f);
+        else if (c == 1) uf = avg4(a0, b1);
+        else uf = avg4(a0, m1[0]);
+        const float4 lo = flux_p4<LAM>(uf, make_float4(l2.x, l2.y, a.x, a.y), make_float4(l2.y, a.x, a.y, a.z), a, make_float4(a.y, a.z, a.w, rr), nu, bad);
+        float hi = __shfl_down_sync(FULLMASK, lo.x, 1);
+        const float e = __shfl_sync(FULLMASK, fex, c);
+        if (lane == 31) hi = e;
+        r[c] = make_float4(0.f + lo.x, 0.f + lo.y, 0.f + lo.z, 0.f + lo.w);
+        r[c].x -= lo.y;
+        r[c].y -= lo.z;
+        r[c].z -= lo.w;
+        r[c].w -= hi;
+        if (c == 2) Fx2lo = lo;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; c++) own[c] = ld4(p0 + c * C4CS);
+    }
+    // ---- y fluxes: lower flux of the own row from the previous step, upper flux = next row's lower flux ----
+    float4 Fy2lo = f4zero();
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 lo = *fy4(z & 1, c, ty);
+        const float4 hi = *fy4(z & 1, c, lastrow ? C4TY : ty + 1);
+        r[c].x += lo.x;
+        r[c].y += lo.y;
+        r[c].z += lo.z;
+        r[c].w += lo.w;
+        r[c].x -= hi.x;
+        r[c].y -= hi.y;
+        r[c].z -= hi.z;
+        r[c].w -= hi.w;
+        if (c == 2) Fy2lo = lo;
+      }
+    }
+    // ---- z fluxes: lower flux carried, upper flux = lower flux of plane z+1 ----
+    {
+      const float4 w1 = ld4(p1 + 2 * C4CS);           // u_z on plane z+1
+      const float wl = p1[2 * C4CS - 1];              //   … and one cell to the left
+      const float4 wd = ld4(p1 + 2 * C4CS - C4W);     //   … one row down
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 a1 = c == 2 ? w1 : ld4(p1 + c * C4CS);
+        const float4 a2 = ld4(p2 + c * C4CS);
+        float4 uf;
+        if (c == 0) uf = make_float4((w1.x + wl) / 2.f, (w1.y + w1.x) / 2.f, (w1.z + w1.y) / 2.f, (w1.w + w1.z) / 2.f);
+        else if (c == 1) uf = avg4(w1, wd);
+        else uf = avg4(w1, own[2]);
+        const float4 hi = flux_p4<LAM>(uf, m1[c], own[c], a1, a2, nu, bad);
+        if (live) {
+          r[c].x += Fz[c].x;
+          r[c].y += Fz[c].y;
+          r[c].z += Fz[c].z;
+          r[c].w += Fz[c].w;
+          r[c].x -= hi.x;
+          r[c].y -= hi.y;
+          r[c].z -= hi.z;
+          r[c].w -= hi.w;
+        }
+        if (live && c == 2) {
+          // periodic images of the stale Φ the reference leaves on the upper ghost cells of σ (they enter maximum(σ) in CFL,
+          // SURVEY App. A.9-1), see fm_conv: candidates by {k : I_k == 1}
+          if (on) {
+            const bool t1 = y == 1, t2 = (z + g.zoff) == 1;
+            const float4 fz = Fz[2];
+            if (t1) gmax = fmaxf(gmax, fmaxf(fmaxf(fz.x, fz.y), fmaxf(fz.z, fz.w)));
+            else if (x0 == 1) gmax = fmaxf(gmax, fz.x);
+            if (t2) gmax = fmaxf(gmax, fmaxf(fmaxf(Fy2lo.x, Fy2lo.y), fmaxf(Fy2lo.z, Fy2lo.w)));
+            if (t2 && t1) gmax = fmaxf(gmax, fmaxf(fmaxf(Fx2lo.x, Fx2lo.y), fmaxf(Fx2lo.z, Fx2lo.w)));
+          }
+        }
+        Fz[c] = hi;
+      }
+    }
+    // ---- u_new = u⁰ + Δt·r  (predictor)  or  (u + u⁰ + Δt·r)/2  (corrector) ----
+    if (live && on) {
+      const i64 o = (i64)g.xo + x0 + g.s[1] * y + g.s[2] * z;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4 b = ld4(u0 + o + c * g.sc);
+        float4 f = make_float4(b.x + dt * r[c].x, b.y + dt * r[c].y, b.z + dt * r[c].z, b.w + dt * r[c].w);
+        if (corrector) f = make_float4((own[c].x + f.x) * 0.5f, (own[c].y + f.y) * 0.5f, (own[c].z + f.z) * 0.5f, (own[c].w + f.w) * 0.5f);
+        st4(out + o + c * g.sc, f);
+      }
+    }
+    // ---- lower y fluxes of plane z+1 for the next step (the block's last row also computes its upper flux) ----
+    if (z + 1 < z1) {
+      const int nrow = lastrow ? 2 : 1;
+      for (int k = 0; k < nrow; k++) {
+        const float* q1 = p1 + k * C4W;
+        const float* q0 = p0 + k * C4W;
+        const float4 v1 = ld4(q1 + C4CS);             // u_y on plane z+1, row y+k
+        const float vl = q1[C4CS - 1];                //   … one cell to the left
+        const float4 vd = ld4(q1 + C4CS - C4W);       //   … one row down
+        const float4 vz = ld4(q0 + C4CS);             //   … one plane down (plane z)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float4 s2 = ld4(q1 + c * C4CS - 2 * C4W);
+          const float4 s1 = c == 1 ? vd : ld4(q1 + c * C4CS - C4W);
+          const float4 s0 = c == 1 ? v1 : ld4(q1 + c * C4CS);
+          const float4 sp = ld4(q1 + c * C4CS + C4W);
+          float4 uf;
+          if (c == 0) uf = make_float4((v1.x + vl) / 2.f, (v1.y + v1.x) / 2.f, (v1.z + v1.y) / 2.f, (v1.w + v1.z) / 2.f);
+          else if (c == 1) uf = avg4(v1, vd);
+          else uf = avg4(v1, vz);
+          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM>(uf, s2, s1, s0, sp, nu, bad);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) m1[c] = own[c];
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  if (bad) *flag = 1;
+  double v[1] = {(double)gmax}, fin[1];
+  grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+}
