@@ -251,3 +251,49 @@ def test_div6_is_ieee_division_for_all_floats():
     n = C.c_uint64(1)
     wl.lib.check(L, L.wl_selftest_div6(C.byref(n)))
     assert n.value == 0
+
+
+def _tgv_pair(dims, oracle_too=True):
+    n = dims[0]
+    u0 = tgv3d_u0(tuple(d + 2 for d in dims), n)
+    # break the symmetry a little so that every direction carries a different signal
+    u0[2] = (0.1 * np.roll(u0[0], 3, axis=0)).astype(F)
+    nu = float(F(1 / (2 * np.pi / n * 1600)))
+    return make_pair(dims, (0.0, 0.0, 0.0), nu=nu, perdir=(1, 2, 3), u0=u0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,nz", [((64, 64, 64), 0), ((128, 96, 64), 2)])
+def test_fused_upstroke_matches_oracle(dims, nz, monkeypatch):
+    """f_vsmooth (prolongation + GaussSeidelRB! + increments in one pass, wl_vsmooth.cuh) and fm_conv4 on grids large enough to
+    take those paths, with several tiles per direction and (nz=2) several z chunks: bit-identical to the oracle."""
+    if nz:
+        monkeypatch.setenv("WL_VS_NZ", str(nz))
+    o, s = _tgv_pair(dims)
+    for _ in range(4):
+        o.mom_step()
+        s.flow.L.wl_mom_step(s.flow.h)
+    assert np.array_equal(s.flow.u, o.field("u"))
+    assert np.array_equal(s.flow.p, o.field("p"))
+    assert list(np.asarray(o.iters)) == list(np.asarray(s.pois.n))
+    assert np.array_equal(np.asarray(o.dt, F), np.asarray(s.flow.Δt, F))
+
+
+@pytest.mark.gpu
+def test_fused_kernels_equal_unfused_kernels(monkeypatch):
+    """128³ (two levels take f_vsmooth): the fused uniform-mode kernels against the separate march kernels, bit for bit."""
+    import wl_b200 as wl
+    outs = []
+    for flags in ({"WL_VSMOOTH": "1", "WL_CONV4": "1"}, {"WL_VSMOOTH": "0", "WL_CONV4": "0"}):
+        for k, v in flags.items():
+            monkeypatch.setenv(k, v)
+        n = 128
+        u0 = tgv3d_u0((n + 2,) * 3, n)
+        u0[2] = (0.1 * np.roll(u0[0], 3, axis=0)).astype(F)
+        nu = float(F(1 / (2 * np.pi / n * 1600)))
+        s = wl.Simulation((n,) * 3, (0.0, 0.0, 0.0), float(n), ν=nu, perdir=(1, 2, 3), u0=lambda i, x: u0[i])
+        wl.lib.check(s.flow.L, s.flow.L.wl_sim_step_n(s.flow.h, 3))
+        outs.append((s.flow.u.copy(), s.flow.p.copy(), list(s.pois.n), np.asarray(s.flow.Δt).copy()))
+    a, b = outs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[2] == b[2] and np.array_equal(a[3], b[3])

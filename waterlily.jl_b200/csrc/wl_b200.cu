@@ -17,6 +17,7 @@
 #include "wl_dist.h"
 #include "wl_fast.cuh"
 #include "wl_conv4.cuh"
+#include "wl_vsmooth.cuh"
 
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -166,8 +167,10 @@ struct wl_handle {
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
+  bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
   int conv4_zchunk = 32;
+  int vs_nz = 0;           // WL_VS_NZ: force the number of z chunks of f_vsmooth
   // Uniform mode on one GPU never reads the periodic ghost cells of u (every reader wraps its indices), so the BC! launches of
   // mom_step! are deferred until something outside the step loop looks at u (flush_ghosts).
   bool ghosts_dirty = false;
@@ -772,6 +775,70 @@ static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int wi
   }
   return 0;
 }
+// f_vsmooth applies to level li: uniform mode on one GPU, a fully coarsened level below it that is not part of the persistent
+// coarse-level kernel's range, sizes that fit the kernel's 8-cell groups and red/black planes, enough planes to fill the pipeline
+static bool vs_fusable(const wl_handle* h, size_t li) {
+  if (!h->vsmooth || !h->uni || h->dist.on() || h->D != 3 || h->cfg.smoother != WL_SMOOTH_GSRB) return false;
+  if (li + 1 >= h->levels.size()) return false;
+  if (h->small_from > 0 && (int)li >= h->small_from) return false;
+  const Level& f = h->levels[li];
+  const Level& c = h->levels[li + 1];
+  const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
+  return f.fast && c.fullc && !f.slab && n0 % 8 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && n0 >= 64 && n1 >= 32 && n2 >= 64;
+}
+// prolongate! + increment! + GaussSeidelRB! + increment! (+ L₂) of level li in one launch (wl_vsmooth.cuh)
+static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
+  Level& f = h->levels[li];
+  Level& c = h->levels[li + 1];
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(f_vsmooth<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    attr = true;
+  }
+  const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
+  const int tiles = cdiv(n0, VS_CX) * cdiv(n1, VS_CY);
+  // z chunks: every chunk pays 12 planes of pipeline fill; pick the count that minimises waves × (planes per chunk + 12)
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+  int best = 1;
+  long bestcost = -1;
+  for (int nz = 1; nz <= std::max(1, n2 / 16); nz++) {
+    const long cost = (long)cdiv(tiles * nz, nsm) * (cdiv(n2, nz) + 12);
+    if (bestcost < 0 || cost < bestcost) {
+      bestcost = cost;
+      best = nz;
+    }
+  }
+  if (h->vs_nz > 0) best = h->vs_nz;
+  const int zc = cdiv(n2, best);
+  const Coef k = f.coef(true);
+  VsArgs a;
+  a.g = f.g;
+  a.gc = c.g;
+  a.xc = c.x;
+  a.r = f.r;
+  a.r2 = f.r2;
+  a.x = f.x;
+  a.wp = wp;
+  a.L0 = k.Lc[0];
+  a.L1 = k.Lc[1];
+  a.L2 = k.Lc[2];
+  a.D = k.Dc;
+  a.iD = k.iDc;
+  a.zchunk = zc;
+  dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
+  prof_begin(h, "f_vsmooth");
+  if (with_l2)
+    f_vsmooth<true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  else
+    f_vsmooth<false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  prof_end(h);
+  h->launches++;
+  std::swap(f.r, f.r2);
+  CK(cudaGetLastError());
+  return 0;
+}
 // ---- flattening of the coarse end of the V-cycle for k_small_levels ----------------------------------------------------
 static SmallOp op_base(const wl_handle* h, const Level& l, int type) {
   SmallOp o;
@@ -878,7 +945,8 @@ static int run_small_levels(wl_handle* h, const float* wp) {
 }
 
 // Vcycle!(ml;l,ω)  src/MultiLevelPoisson.jl:88-101
-static int vcycle(wl_handle* h, size_t li, const float* wp) {
+// `defer_up`: the caller runs level li's prolongation + increment! fused with its smoother (vsmooth) instead of here
+static int vcycle(wl_handle* h, size_t li, const float* wp, bool defer_up = false) {
   Level& fine = h->levels[li];
   Level& coarse = h->levels[li + 1];
   dim3 b = blk(h->D);
@@ -893,9 +961,14 @@ static int vcycle(wl_handle* h, size_t li, const float* wp) {
   if (h->small_from > 0 && (int)li + 1 == h->small_from) {
     TRY(run_small_levels(h, wp));  // the whole coarse end in one cooperative launch
   } else {
-    if (!last) TRY(vcycle(h, li + 1, wp));
-    TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
+    const bool fu = !last && vs_fusable(h, li + 1);
+    if (!last) TRY(vcycle(h, li + 1, wp, fu));
+    if (fu)
+      TRY(vsmooth(h, li + 1, wp, 0));
+    else
+      TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
   }
+  if (defer_up) return 0;
   Box fin = fine.inside();
   if (fine.fast && coarse.fullc) {
     ProlongSrc ps{coarse.x, coarse.g, 0, 0, 0};
@@ -977,8 +1050,13 @@ static int solve_after_residual(wl_handle* h, float r2, int* iters_out) {
     log_row(h, np, rinf, r2, w);
     while (np < h->itmx) {
       set_scalar(h, 0, w);
-      TRY(vcycle(h, 0, h->d_scal + 0));
-      TRY(smooth(h, p, h->d_scal + 0, 0, 1));
+      if (vs_fusable(h, 0)) {
+        TRY(vcycle(h, 0, h->d_scal + 0, true));
+        TRY(vsmooth(h, 0, h->d_scal + 0, 1));
+      } else {
+        TRY(vcycle(h, 0, h->d_scal + 0));
+        TRY(smooth(h, p, h->d_scal + 0, 0, 1));
+      }
       double v;
       TRY(read_slot(h, SLOT_R2, &v));
       const float rnew = (float)v;
@@ -1329,7 +1407,9 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->D = cfg->D;
   h->tol = cfg->tol > 0 ? (double)cfg->tol : 1e-4;
   h->fused_gs = !(cfg->flags & WL_FLAG_UNFUSED_GS);
+  if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
+  if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
   if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);

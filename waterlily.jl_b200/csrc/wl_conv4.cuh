@@ -25,36 +25,49 @@
 #define C4FILL ((C4H * C4Q + 32 * C4TY - 1) / (32 * C4TY))
 #define C4SMEM ((C4RING * C4PS + 2 * 3 * (C4TY + 1) * 32 * 4) * 4)
 
-// x/6, exact as div6_flag (wl_kernels.cuh); a non-zero input outside the proven range lands in `bad` (tested once per thread)
-__device__ __forceinline__ float div6_bad(float x, unsigned& bad) {
+// x/6, exact as div6_flag (wl_kernels.cuh).  The proven range of the two-FMA form is 2^-100 ≤ |x| ≤ 3e38: the lower bound is tested
+// here (a non-zero input below it raises `bad`, tested once per thread), the upper bound follows from the kernel's per-cell test
+// |u| ≤ 1e37 (|5c+2d−u| ≤ 8e37).
+__device__ __forceinline__ float div6_chk(float x, bool& bad) {
   const float C = 0.16666667163372039794921875f;
   const float q0 = x * C;
   const float r = __fmaf_rn(-6.f, q0, x);
   const float q = __fmaf_rn(r, C, q0);
-  const unsigned b = __float_as_uint(x) & 0x7fffffffu;
-  const unsigned LO = 0x0D800000u;  // 2^-100 = 7.888609052210118e-31f
-  const unsigned HI = 0x7F61B1E6u;  // 3.0e38f
-  const bool inr = (b - LO) <= (HI - LO);
-  bad |= inr ? 0u : b;
+  const bool inr = fabsf(x) >= 7.888609052210118e-31f;
+  bad = bad || (!inr && x != 0.f);
   return inr ? q : q0;  // ±0 → ±0 (= q0)
 }
-template <int LAM>
-__device__ __forceinline__ float limiter_b(float u, float c, float d, unsigned& bad) {
-  if (LAM == 0) return median3(div6_bad(5.f * c + 2.f * d - u, bad), c, median3(10.f * c - 9.f * u, c, d));  // quick
-  if (LAM == 1) return (c + d) / 2.f;                                                                          // cds
-  return (c <= fminf(u, d) || c >= fmaxf(u, d)) ? c : c + (d - c) * (c - u) / (d - u);                        // vanLeer
-}
 // ϕu(j, CI(I,i), u, û, λ) − ν ∂(j, CI(I,i), u) for an inner / periodic face (src/Flow.jl:8-11,52)
+//
+// quick(u,c,d) = median((5c+2d−u)/6, c, median(10c−9u, c, d))  (src/Flow.jl:6) is evaluated as a clamp: with a = (5c+2d−u)/6 and
+// b = 10c−9u the nested median equals min(max(min(a,b), c), d) when c ≤ d and max(min(max(a,b), c), d) when d ≤ c (lattice
+// identities on ordered values: same value, three min/max instead of eight).  The second case is the first one mirrored, and
+// mirroring (multiplying the three inputs by s = −1) is exact in IEEE arithmetic, so one code path serves both:
+// λ = s·min(max(min(a',b'), s·c), s·d) with s = sign(d−c).  d−c is ±(u[I]−u[I−δ]) with the sign of û, so s = sign(t·û).
+// (û = 0 gives conv = 0·λ = 0 whatever s is.)  min/max run on the half-rate ALU pipe, the multiplications on the FMA pipe.
 template <int LAM>
-__device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, unsigned& bad) {
-  const float diff = nu * (u0c - um1);
+__device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, bool& bad) {
+  const float t = u0c - um1;
+  const float diff = nu * t;
   const bool pos = uf > 0.f;
-  const float conv = uf * limiter_b<LAM>(pos ? um2 : up1, pos ? um1 : u0c, pos ? u0c : um1, bad);
-  return conv - diff;
+  const float u = pos ? um2 : up1, c = pos ? um1 : u0c, d = pos ? u0c : um1;
+  float lam;
+  if (LAM == 0) {
+    const float s = __uint_as_float((__float_as_uint(t * uf) & 0x80000000u) | 0x3f800000u);
+    const float cs = c * s, ds = d * s, us = u * s;
+    const float a = div6_chk(5.f * cs + 2.f * ds - us, bad);
+    const float b = 10.f * cs - 9.f * us;
+    lam = s * fminf(fmaxf(fminf(a, b), cs), ds);
+  } else if (LAM == 1) {
+    lam = (c + d) / 2.f;  // cds
+  } else {
+    lam = (c <= fminf(u, d) || c >= fmaxf(u, d)) ? c : c + (d - c) * (c - u) / (d - u);  // vanLeer
+  }
+  return uf * lam - diff;
 }
 template <int LAM>
 __device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, float nu,
-                                          unsigned& bad) {
+                                          bool& bad) {
   return make_float4(flux_p<LAM>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
                      flux_p<LAM>(uf.z, um2.z, um1.z, u0c.z, up1.z, nu, bad), flux_p<LAM>(uf.w, um2.w, um1.w, u0c.w, up1.w, nu, bad));
 }
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
   const int z0 = 1 + zchunk * blockIdx.z, z1 = min(z0 + zchunk, g.N[2] - 1);
   const bool on = x0 <= g.N[0] - 2 && y <= g.N[1] - 2;
   const float dt = *dtp;
-  unsigned bad = 0u;
+  bool bad = false;
 
   // ---- tile fill: every plane is fetched with the same per-thread float4 elements ----
   int gof[C4FILL], sof[C4FILL];  // in-plane global offset / offset inside a component plane of the tile (-1: none)
@@ -210,6 +223,9 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 3; c++) own[c] = ld4(p0 + c * C4CS);
     }
+#pragma unroll
+    for (int c = 0; c < 3; c++)  // the range test behind div6_chk; catches NaN and Inf too
+      bad = bad || !(fabsf(own[c].x) <= 1e37f) || !(fabsf(own[c].y) <= 1e37f) || !(fabsf(own[c].z) <= 1e37f) || !(fabsf(own[c].w) <= 1e37f);
     // ---- y fluxes: lower flux of the own row from the previous step, upper flux = next row's lower flux ----
     float4 Fy2lo = f4zero();
     if (live) {

@@ -1,0 +1,294 @@
+// wl_vsmooth.cuh — f_vsmooth: the up-stroke of one multigrid level in ONE pass over the level's fields (uniform mode).
+//
+// Fuses, for a level with a coarser level below it (src/MultiLevelPoisson.jl:99-100,106; src/Poisson.jl:100-104,141-148):
+//     prolongate!(fine.ϵ, coarse.x); increment!(fine; ω)            r¹ = r − ω·A ϵc ,  x¹ = x + ω·ϵc
+//     GaussSeidelRB!(fine; it=4, ω):  ϵ⁰ = r¹·iD ; four red/black half-sweeps ; increment!   r² = r¹ − ω·A ϵ⁴ ,  x² = x¹ + ω·ϵ⁴
+//     (level 1 only) L₂ = Σ r²·r²
+// which the march kernels run as six launches moving 80.5 B/cell (f_increment<PROLONG>, f_gs_a, 3 × f_gs_half, f_increment);
+// here r and x are read once and written once: 16 B/cell (+ ⅛ cell of the coarse solution).
+//
+// Temporal blocking: a block owns an x-y tile, marches over a z chunk and keeps a ring of planes of ϵ and r¹ in shared memory.
+// The six stages run as a software pipeline on different planes of the ring (newest first):
+//     step t, phase α:  P (r¹, ϵ⁰) on plane t      sweep 2 on plane t−3      sweep 4 on plane t−6
+//             phase β:  sweep 1 on plane t−1       sweep 3 on plane t−4      increment on plane t−7
+// (two block barriers per plane; a stage reads planes q−1, q, q+1 of the previous stage).  r² depends on r within a distance
+// of 5 cells, so a tile is loaded and processed with a halo of 5 rows in y and 5 planes in z — 8 cells in x, the granule of the
+// layout below — and only its core is stored; the values computed in the halo get progressively wrong towards the tile edge,
+// exactly one cell per stage, and never reach the core.  r² goes to a second array (neighbouring tiles still read r).
+//
+// Layout of a plane in the ring: cells are split by the parity of their x position into two arrays; a thread owns a group of
+// 8 consecutive cells of a row = one float4 in each array.  A red/black half-sweep on row y moves the cells of ONE of the two
+// arrays (which one alternates with y+z), reading the other array for the x neighbours and the same array one row / one plane
+// away for the y / z neighbours, so every lane does useful work on full float4 vectors and the update is race-free in place.
+// Warps are made of rows of equal parity, so the choice of the array is warp-uniform.
+//
+// The reference's periodic-ghost quirk (App. A.9-4: perBC! runs once before the sweeps, so across a periodic face a sweep sees
+// the stale ϵ⁰ = r¹·iD of the wrapped cell; increment! refreshes the ghosts) is reproduced: a neighbour across the domain's
+// periodic face is read from the r¹ ring and multiplied by iD during the sweeps, from the ϵ ring in the increment.
+// Arithmetic and association order are those of mult_uni / Gs::gauss4 (wl_fast.cuh): results are bit-identical to the unfused path.
+#pragma once
+#include "wl_fast.cuh"
+
+#define VS_NGX 10                      // groups of 8 cells per tile row: 8 core groups + one halo group on each side
+#define VS_CX ((VS_NGX - 2) * 8)       // core width  (64)
+#define VS_CY 32                       // core height
+#define VS_HALO 5
+#define VS_TH (VS_CY + 2 * VS_HALO)    // tile rows (42)
+#define VS_DE 9                        // ring depth of ϵ   (planes t … t−8)
+#define VS_DR 8                        // ring depth of r¹  (planes t … t−7)
+#define VS_AF (VS_TH * VS_NGX * 4)     // floats of one parity array of a plane
+#define VS_PF (2 * VS_AF)              // floats of one plane (both arrays)
+#define VS_NW (2 * ((VS_TH / 2 * VS_NGX + 31) / 32))  // warps: the rows of each parity are spread over NW/2 warps
+#define VS_NT (32 * VS_NW)
+#define VS_SMEM ((VS_DE + VS_DR) * VS_PF * 4)
+
+struct VsArgs {
+  Grid g, gc;
+  const float* xc;   // coarse solution
+  const float* r;    // residual in
+  float* r2;         // residual out
+  float* x;          // solution, updated in place
+  const float* wp;   // ω
+  float L0, L1, L2, D, iD;
+  int zchunk;
+};
+
+__device__ __forceinline__ float4 mul4s(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// One red/black half-sweep of the thread's 4 target cells on plane q.  TE: the target is the array of even positions (its left
+// x neighbours are (S, V.x, V.y, V.z), right V); otherwise odd positions (left V, right (V.y, V.z, V.w, S)), V = the other array.
+template <bool TE>
+__device__ __forceinline__ void vs_sweep(float* Eq, const float* Eqm, const float* Eqp, const float* Rq, const float* Rqm, const float* Rqp, int e4, int oS,
+                                         int oYm, int oYp, bool stS, bool stYm, bool stYp, bool stZm, bool stZp, const VsArgs& a) {
+  const int tg = TE ? 0 : VS_AF, ot = TE ? VS_AF : 0;
+  const float iD = a.iD;
+  const float4 V = ld4(Eq + ot + e4);
+  float S = stS ? Rq[ot + e4 + oS] * iD : Eq[ot + e4 + oS];
+  float4 ym, yp, zm, zp;
+  if (stYm) ym = mul4s(ld4(Rq + tg + e4 + oYm), iD);
+  else ym = ld4(Eq + tg + e4 + oYm);
+  if (stYp) yp = mul4s(ld4(Rq + tg + e4 + oYp), iD);
+  else yp = ld4(Eq + tg + e4 + oYp);
+  if (stZm) zm = mul4s(ld4(Rqm + tg + e4), iD);
+  else zm = ld4(Eqm + tg + e4);
+  if (stZp) zp = mul4s(ld4(Rqp + tg + e4), iD);
+  else zp = ld4(Eqp + tg + e4);
+  float4 s = ld4(Rq + tg + e4);
+  const float L0 = a.L0, L1 = a.L1, L2 = a.L2;
+  float4 lf, rt;
+  if (TE) {
+    lf = make_float4(S, V.x, V.y, V.z);
+    rt = V;
+  } else {
+    lf = V;
+    rt = make_float4(V.y, V.z, V.w, S);
+  }
+  s.x -= lf.x * L0 + rt.x * L0;
+  s.x -= ym.x * L1 + yp.x * L1;
+  s.x -= zm.x * L2 + zp.x * L2;
+  s.y -= lf.y * L0 + rt.y * L0;
+  s.y -= ym.y * L1 + yp.y * L1;
+  s.y -= zm.y * L2 + zp.y * L2;
+  s.z -= lf.z * L0 + rt.z * L0;
+  s.z -= ym.z * L1 + yp.z * L1;
+  s.z -= zm.z * L2 + zp.z * L2;
+  s.w -= lf.w * L0 + rt.w * L0;
+  s.w -= ym.w * L1 + yp.w * L1;
+  s.w -= zm.w * L2 + zp.w * L2;
+  st4(Eq + tg + e4, mul4s(s, iD));
+}
+
+// A ϵ at the 4 cells of one parity array (mult_uni order: ϵ·D, + x pair, + y pair, + z pair)
+__device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, const float4& rt, const float4& ym, const float4& yp, const float4& zm,
+                                          const float4& zp, const VsArgs& a) {
+  const float L0 = a.L0, L1 = a.L1, L2 = a.L2, D = a.D;
+  float4 s;
+  s.x = c.x * D;
+  s.x += lf.x * L0 + rt.x * L0;
+  s.x += ym.x * L1 + yp.x * L1;
+  s.x += zm.x * L2 + zp.x * L2;
+  s.y = c.y * D;
+  s.y += lf.y * L0 + rt.y * L0;
+  s.y += ym.y * L1 + yp.y * L1;
+  s.y += zm.y * L2 + zp.y * L2;
+  s.z = c.z * D;
+  s.z += lf.z * L0 + rt.z * L0;
+  s.z += ym.z * L1 + yp.z * L1;
+  s.z += zm.z * L2 + zp.z * L2;
+  s.w = c.w * D;
+  s.w += lf.w * L0 + rt.w * L0;
+  s.w += ym.w * L1 + yp.w * L1;
+  s.w += zm.w * L2 + zp.w * L2;
+  return s;
+}
+
+template <bool WITH_L2>
+__global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
+  extern __shared__ float4 vs_smem4[];
+  float* const ER = reinterpret_cast<float*>(vs_smem4);  // [VS_DE][2][VS_TH][VS_NGX] float4
+  float* const RR = ER + VS_DE * VS_PF;                  // [VS_DR][2][VS_TH][VS_NGX] float4
+  const Grid& g = a.g;
+  const Grid& gc = a.gc;
+  const int n0 = g.N[0] - 2, n1 = g.N[1] - 2, n2 = g.N[2] - 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int par = warp & 1;  // parity class of this warp's rows
+  const int qi = (warp >> 1) * 32 + lane;
+  const int rc = qi / VS_NGX, gx = qi - rc * VS_NGX;
+  const int ry = min(2 * rc + par, VS_TH - 1);
+  const bool act = 2 * rc + par < VS_TH;
+  const int xb = 1 + VS_CX * blockIdx.x, yb = 1 + VS_CY * blockIdx.y;
+  const int z0 = 1 + a.zchunk * blockIdx.z, z1 = min(z0 + a.zchunk, n2 + 1);
+  const int xu = xb - 8 + 8 * gx, yu = yb - VS_HALO + ry;  // unwrapped coordinates of the group's first cell / of the row
+  const int ypar = yu & 1;
+  auto wrap = [](int v, int n) -> int {
+    if (v < 1) v += n;
+    else if (v > n) v -= n;
+    return v;
+  };
+  const int xs = max(1, min(n0 - 7, wrap(xu, n0)));
+  const int yr = max(1, min(n1, wrap(yu, n1)));
+  // neighbours across the domain's periodic faces (see header): the group's left / right x neighbour, the rows below / above
+  const bool stL = xu == 1 || xu == n0 + 1, stR = xu + 8 == 1 || xu + 8 == n0 + 1;
+  const bool stYm = yu == 1 || yu == n1 + 1, stYp = yu == 0 || yu == n1;
+  const int e4 = (ry * VS_NGX + gx) * 4;
+  const int oYm = ry > 0 ? -VS_NGX * 4 : 0, oYp = ry < VS_TH - 1 ? VS_NGX * 4 : 0;
+  const int oSl = gx > 0 ? -1 : 3, oSr = gx < VS_NGX - 1 ? 4 : 0;  // last cell of the group to the left / first cell of the group to the right
+  const bool core = act && gx >= 1 && gx <= VS_NGX - 2 && ry >= VS_HALO && ry < VS_TH - VS_HALO && xu <= n0 && yu <= n1;
+  // global offsets (in-plane)
+  const int gin = g.xo + xs + g.px * yr;
+  const int cy = (yr + 1) >> 1;
+  const int cyo = (wrap((yr & 1) ? yr - 1 : yr + 1, n1) + 1) >> 1;  // coarse row of the fine y neighbour that is not in the own coarse cell
+  const int cx = (xs + 1) >> 1;
+  const int cinx = gc.xo + cx;
+  const int dcl = ((wrap(xs - 1, n0) + 1) >> 1) - cx, dcr = ((wrap(xs + 8, n0) + 1) >> 1) - cx;
+  const float w = *a.wp;
+  const float iD = a.iD;
+  double l2 = 0.0;
+
+  int se = 0, sr = 0;  // ring slots of plane t
+  for (int t = z0 - VS_HALO; t <= z1 + 6; t++) {
+    auto Es = [&](int k) -> float* {  // ϵ ring slot of plane t−k
+      int s = se - k;
+      if (s < 0) s += VS_DE;
+      return ER + s * VS_PF;
+    };
+    auto Rs = [&](int k) -> float* {
+      int s = sr - k;
+      if (s < 0) s += VS_DR;
+      return RR + s * VS_PF;
+    };
+    // =============== phase α ===============
+    if (act && t <= z1 + 4) {
+      // ---- P: r¹ = r − ω·A ϵc with ϵc = coarse.x[down(·)], ϵ⁰ = r¹·iD, all 8 cells of the group on plane t ----
+      const int zr = wrap(t, n2);
+      const int cz = (zr + 1) >> 1, czo = (wrap((zr & 1) ? zr - 1 : zr + 1, n2) + 1) >> 1;
+      const float* rp = a.r + g.s[2] * zr + gin;
+      const float4 f0 = ld4(rp), f1 = ld4(rp + 4);
+      const float* cp = a.xc + gc.s[2] * cz + cinx;
+      const float4 C = ld4(cp + gc.px * cy);
+      const float cl = cp[gc.px * cy + dcl], cr = cp[gc.px * cy + dcr];
+      const float4 Cy = ld4(cp + gc.px * cyo);
+      const float4 Cz = ld4(a.xc + gc.s[2] * czo + cinx + gc.px * cy);
+      const float L0 = a.L0, L1 = a.L1, L2 = a.L2, D = a.D;
+      // fine cell j of the group sits in coarse cell j/2; its x neighbour outside that coarse cell is on the left for even j
+      auto Aec = [&](float c0, float xo, float yo, float zo) -> float {
+        float s = c0 * D;
+        s += c0 * L0 + xo * L0;
+        s += c0 * L1 + yo * L1;
+        s += c0 * L2 + zo * L2;
+        return s;
+      };
+      float4 re, ro;  // r¹ at even / odd positions
+      re.x = f0.x - w * Aec(C.x, cl, Cy.x, Cz.x);
+      ro.x = f0.y - w * Aec(C.x, C.y, Cy.x, Cz.x);
+      re.y = f0.z - w * Aec(C.y, C.x, Cy.y, Cz.y);
+      ro.y = f0.w - w * Aec(C.y, C.z, Cy.y, Cz.y);
+      re.z = f1.x - w * Aec(C.z, C.y, Cy.z, Cz.z);
+      ro.z = f1.y - w * Aec(C.z, C.w, Cy.z, Cz.z);
+      re.w = f1.z - w * Aec(C.w, C.z, Cy.w, Cz.w);
+      ro.w = f1.w - w * Aec(C.w, cr, Cy.w, Cz.w);
+      float* Rt = Rs(0);
+      float* Et = Es(0);
+      st4(Rt + e4, re);
+      st4(Rt + VS_AF + e4, ro);
+      st4(Et + e4, mul4s(re, iD));
+      st4(Et + VS_AF + e4, mul4s(ro, iD));
+    }
+    // ---- sweeps 2 and 4 move the even cells ((x+y+z) even; the array of even positions holds odd x) ----
+#pragma unroll
+    for (int k = 3; k <= 6; k += 3) {
+      const int q = t - k;
+      const int h = k == 3 ? 3 : 1;  // sweep 2 is valid on planes z0−3 … z1+2, sweep 4 on z0−1 … z1
+      if (act && q >= z0 - h && q <= z1 - 1 + h) {
+        const int zr = wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == n2;
+        const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
+        if (te)
+          vs_sweep<true>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSl, oYm, oYp, stL, stYm, stYp, zsm, zsp, a);
+        else
+          vs_sweep<false>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSr, oYm, oYp, stR, stYm, stYp, zsm, zsp, a);
+      }
+    }
+    __syncthreads();
+    // =============== phase β ===============
+    // ---- sweeps 1 and 3 move the odd cells ----
+#pragma unroll
+    for (int k = 1; k <= 4; k += 3) {
+      const int q = t - k;
+      const int h = k == 1 ? 4 : 2;  // sweep 1 is valid on planes z0−4 … z1+3, sweep 3 on z0−2 … z1+1
+      if (act && q >= z0 - h && q <= z1 - 1 + h) {
+        const int zr = wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == n2;
+        const bool te = ((1 + ypar + q) & 1) == 1;
+        if (te)
+          vs_sweep<true>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSl, oYm, oYp, stL, stYm, stYp, zsm, zsp, a);
+        else
+          vs_sweep<false>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSr, oYm, oYp, stR, stYm, stYp, zsm, zsp, a);
+      }
+    }
+    // ---- increment!: r² = r¹ − ω·A ϵ⁴ ; x² = (x + ω·ϵc) + ω·ϵ⁴ on plane t−7, core cells only ----
+    {
+      const int q = t - 7;
+      if (q >= z0 && q <= z1 - 1 && core) {
+        const float* Eq = Es(7);
+        const float* Eqm = Es(8);
+        const float* Eqp = Es(6);
+        const float* Rq = Rs(7);
+        const float4 ce = ld4(Eq + e4), co = ld4(Eq + VS_AF + e4);
+        const float sl = Eq[VS_AF + e4 + oSl], sr_ = Eq[e4 + oSr];
+        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, ld4(Eq + e4 + oYm), ld4(Eq + e4 + oYp), ld4(Eqm + e4), ld4(Eqp + e4), a);
+        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ld4(Eq + VS_AF + e4 + oYm), ld4(Eq + VS_AF + e4 + oYp), ld4(Eqm + VS_AF + e4),
+                                  ld4(Eqp + VS_AF + e4), a);
+        const float4 re = ld4(Rq + e4), ro = ld4(Rq + VS_AF + e4);
+        const float4 ne = make_float4(re.x - w * Ae.x, re.y - w * Ae.y, re.z - w * Ae.z, re.w - w * Ae.w);
+        const float4 no = make_float4(ro.x - w * Ao.x, ro.y - w * Ao.y, ro.z - w * Ao.z, ro.w - w * Ao.w);
+        const i64 o = g.s[2] * q + gin;  // core rows and planes are inside the domain: no wrap
+        st4(a.r2 + o, make_float4(ne.x, no.x, ne.y, no.y));
+        st4(a.r2 + o + 4, make_float4(ne.z, no.z, ne.w, no.w));
+        const float4 C = ld4(a.xc + gc.s[2] * ((q + 1) >> 1) + cinx + gc.px * cy);
+        float4 x0 = ld4(a.x + o), x1 = ld4(a.x + o + 4);
+        x0.x = (x0.x + w * C.x) + w * ce.x;
+        x0.y = (x0.y + w * C.x) + w * co.x;
+        x0.z = (x0.z + w * C.y) + w * ce.y;
+        x0.w = (x0.w + w * C.y) + w * co.y;
+        x1.x = (x1.x + w * C.z) + w * ce.z;
+        x1.y = (x1.y + w * C.z) + w * co.z;
+        x1.z = (x1.z + w * C.w) + w * ce.w;
+        x1.w = (x1.w + w * C.w) + w * co.w;
+        st4(a.x + o, x0);
+        st4(a.x + o + 4, x1);
+        if (WITH_L2) {
+          l2 += (double)ne.x * ne.x + (double)no.x * no.x + (double)ne.y * ne.y + (double)no.y * no.y;
+          l2 += (double)ne.z * ne.z + (double)no.z * no.z + (double)ne.w * ne.w + (double)no.w * no.w;
+        }
+      }
+    }
+    __syncthreads();
+    se = se + 1 == VS_DE ? 0 : se + 1;
+    sr = sr + 1 == VS_DR ? 0 : sr + 1;
+  }
+  if (WITH_L2) {
+    double v[1] = {l2}, fin[1];
+    grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+  }
+}
