@@ -29,18 +29,19 @@
 #pragma once
 #include "wl_fast.cuh"
 
-#define VS_NGX 10                      // groups of 8 cells per tile row: 8 core groups + one halo group on each side
-#define VS_CX ((VS_NGX - 2) * 8)       // core width  (64)
-#define VS_CY 32                       // core height
+#define VS_NGX 8                       // groups of 8 cells per tile row: 6 core groups + one halo group on each side (8 float4 = one quarter-warp: row breaks cause no bank conflicts)
+#define VS_CX ((VS_NGX - 2) * 8)       // core width  (48)
+#define VS_CY 42                       // core height
 #define VS_HALO 5
-#define VS_TH (VS_CY + 2 * VS_HALO)    // tile rows (42)
+#define VS_TH (VS_CY + 2 * VS_HALO)    // tile rows (52)
 #define VS_DE 9                        // ring depth of ϵ   (planes t … t−8)
 #define VS_DR 8                        // ring depth of r¹  (planes t … t−7)
 #define VS_AF (VS_TH * VS_NGX * 4)     // floats of one parity array of a plane
 #define VS_PF (2 * VS_AF)              // floats of one plane (both arrays)
 #define VS_NW (2 * ((VS_TH / 2 * VS_NGX + 31) / 32))  // warps: the rows of each parity are spread over NW/2 warps
 #define VS_NT (32 * VS_NW)
-#define VS_SMEM ((VS_DE + VS_DR) * VS_PF * 4)
+#define VS_PAD 64                       // floats of padding before and after the rings (edge elements read neighbours out of the tile)
+#define VS_SMEM (((VS_DE + VS_DR) * VS_PF + 2 * VS_PAD) * 4)
 
 struct VsArgs {
   Grid g, gc;
@@ -55,25 +56,50 @@ struct VsArgs {
 
 __device__ __forceinline__ float4 mul4s(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
-// One red/black half-sweep of the thread's 4 target cells on plane q.  TE: the target is the array of even positions (its left
-// x neighbours are (S, V.x, V.y, V.z), right V); otherwise odd positions (left V, right (V.y, V.z, V.w, S)), V = the other array.
+// Ring slot offsets (floats from the start of the ϵ ring) by (slot of plane t, planes back): a constant-bank lookup instead
+// of modular arithmetic at every use.
+struct VsLut {
+  int e[VS_DE][VS_DE];
+  int r[VS_DR][VS_DR];
+};
+constexpr VsLut vs_make_lut() {
+  VsLut l{};
+  for (int s = 0; s < VS_DE; s++)
+    for (int k = 0; k < VS_DE; k++) l.e[s][k] = ((s - k + VS_DE) % VS_DE) * VS_PF;
+  for (int s = 0; s < VS_DR; s++)
+    for (int k = 0; k < VS_DR; k++) l.r[s][k] = VS_DE * VS_PF + ((s - k + VS_DR) % VS_DR) * VS_PF;
+  return l;
+}
+__constant__ VsLut vs_lut = vs_make_lut();
+
+// One red/black half-sweep of the thread's 4 target cells on plane q.  `sb` = ring base + the thread's element; eq/eqm/eqp and
+// rq/rqm/rqp = slot offsets of planes q, q−1, q+1 in the ϵ and r¹ rings.  TE: the target is the array of even positions (its
+// left x neighbours are (S, V.x, V.y, V.z), right V); otherwise odd positions (left V, right (V.y, V.z, V.w, S)), V = the other
+// array.  The neighbour offsets are immediates: the rings are padded so that the tile's edge elements read garbage in bounds.
+// stS/mS: the x neighbour S lies across the periodic face (read r¹, times mS = iD; mS = 1 otherwise); anyYZ: some y or z
+// neighbour does (rare: one branch around the general form).
 template <bool TE>
-__device__ __forceinline__ void vs_sweep(float* Eq, const float* Eqm, const float* Eqp, const float* Rq, const float* Rqm, const float* Rqp, int e4, int oS,
-                                         int oYm, int oYp, bool stS, bool stYm, bool stYp, bool stZm, bool stZp, const VsArgs& a) {
-  const int tg = TE ? 0 : VS_AF, ot = TE ? VS_AF : 0;
+__device__ __forceinline__ void vs_sweep(float* sb, int eq, int eqm, int eqp, int rq, int rqm, int rqp, bool stS, float mS, bool anyYZ, bool stYm,
+                                         bool stYp, bool stZm, bool stZp, const VsArgs& a) {
+  constexpr int tg = TE ? 0 : VS_AF, ot = TE ? VS_AF : 0;
+  constexpr int oS = TE ? -1 : 4;  // last cell of the group to the left / first cell of the group to the right
+  constexpr int oY = VS_NGX * 4;
   const float iD = a.iD;
-  const float4 V = ld4(Eq + ot + e4);
-  float S = stS ? Rq[ot + e4 + oS] * iD : Eq[ot + e4 + oS];
+  const float4 V = ld4(sb + eq + ot);
+  const float S = sb[(stS ? rq : eq) + ot + oS] * mS;
   float4 ym, yp, zm, zp;
-  if (stYm) ym = mul4s(ld4(Rq + tg + e4 + oYm), iD);
-  else ym = ld4(Eq + tg + e4 + oYm);
-  if (stYp) yp = mul4s(ld4(Rq + tg + e4 + oYp), iD);
-  else yp = ld4(Eq + tg + e4 + oYp);
-  if (stZm) zm = mul4s(ld4(Rqm + tg + e4), iD);
-  else zm = ld4(Eqm + tg + e4);
-  if (stZp) zp = mul4s(ld4(Rqp + tg + e4), iD);
-  else zp = ld4(Eqp + tg + e4);
-  float4 s = ld4(Rq + tg + e4);
+  if (!anyYZ) {
+    ym = ld4(sb + eq + tg - oY);
+    yp = ld4(sb + eq + tg + oY);
+    zm = ld4(sb + eqm + tg);
+    zp = ld4(sb + eqp + tg);
+  } else {
+    ym = stYm ? mul4s(ld4(sb + rq + tg - oY), iD) : ld4(sb + eq + tg - oY);
+    yp = stYp ? mul4s(ld4(sb + rq + tg + oY), iD) : ld4(sb + eq + tg + oY);
+    zm = stZm ? mul4s(ld4(sb + rqm + tg), iD) : ld4(sb + eqm + tg);
+    zp = stZp ? mul4s(ld4(sb + rqp + tg), iD) : ld4(sb + eqp + tg);
+  }
+  float4 s = ld4(sb + rq + tg);
   const float L0 = a.L0, L1 = a.L1, L2 = a.L2;
   float4 lf, rt;
   if (TE) {
@@ -95,7 +121,7 @@ __device__ __forceinline__ void vs_sweep(float* Eq, const float* Eqm, const floa
   s.w -= lf.w * L0 + rt.w * L0;
   s.w -= ym.w * L1 + yp.w * L1;
   s.w -= zm.w * L2 + zp.w * L2;
-  st4(Eq + tg + e4, mul4s(s, iD));
+  st4(sb + eq + tg, mul4s(s, iD));
 }
 
 // A ϵ at the 4 cells of one parity array (mult_uni order: ϵ·D, + x pair, + y pair, + z pair)
@@ -125,8 +151,8 @@ __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, con
 template <bool WITH_L2>
 __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
   extern __shared__ float4 vs_smem4[];
-  float* const ER = reinterpret_cast<float*>(vs_smem4);  // [VS_DE][2][VS_TH][VS_NGX] float4
-  float* const RR = ER + VS_DE * VS_PF;                  // [VS_DR][2][VS_TH][VS_NGX] float4
+  // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
+  float* const ER = reinterpret_cast<float*>(vs_smem4) + VS_PAD;
   const Grid& g = a.g;
   const Grid& gc = a.gc;
   const int n0 = g.N[0] - 2, n1 = g.N[1] - 2, n2 = g.N[2] - 2;
@@ -150,9 +176,10 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
   // neighbours across the domain's periodic faces (see header): the group's left / right x neighbour, the rows below / above
   const bool stL = xu == 1 || xu == n0 + 1, stR = xu + 8 == 1 || xu + 8 == n0 + 1;
   const bool stYm = yu == 1 || yu == n1 + 1, stYp = yu == 0 || yu == n1;
-  const int e4 = (ry * VS_NGX + gx) * 4;
-  const int oYm = ry > 0 ? -VS_NGX * 4 : 0, oYp = ry < VS_TH - 1 ? VS_NGX * 4 : 0;
-  const int oSl = gx > 0 ? -1 : 3, oSr = gx < VS_NGX - 1 ? 4 : 0;  // last cell of the group to the left / first cell of the group to the right
+  float* const sb = ER + (ry * VS_NGX + gx) * 4;  // the thread's element inside a parity array, relative to slot offsets
+  const bool stY = stYm || stYp;
+  const float mL = stL ? a.iD : 1.f, mR = stR ? a.iD : 1.f;
+  constexpr int oY = VS_NGX * 4;
   const bool core = act && gx >= 1 && gx <= VS_NGX - 2 && ry >= VS_HALO && ry < VS_TH - VS_HALO && xu <= n0 && yu <= n1;
   // global offsets (in-plane)
   const int gin = g.xo + xs + g.px * yr;
@@ -165,30 +192,49 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
   const float iD = a.iD;
   double l2 = 0.0;
 
+  // global loads are issued one step ahead of their use (the block's warps run in lockstep between barriers, nothing else
+  // would hide the DRAM latency): plane t+1 of r and the coarse solution around it for P, plane t−7 of x for the increment
+  struct PIn {
+    float4 f0, f1, C, Cy, Cz;
+    float cl, cr;
+  };
+  auto loadP = [&](int t) -> PIn {
+    PIn p;
+    const int zr = wrap(t, n2);
+    const int cz = (zr + 1) >> 1, czo = (wrap((zr & 1) ? zr - 1 : zr + 1, n2) + 1) >> 1;
+    const float* rp = a.r + g.s[2] * zr + gin;
+    p.f0 = ld4(rp);
+    p.f1 = ld4(rp + 4);
+    const float* cp = a.xc + gc.s[2] * cz + cinx;
+    p.C = ld4(cp + gc.px * cy);
+    p.cl = cp[gc.px * cy + dcl];
+    p.cr = cp[gc.px * cy + dcr];
+    p.Cy = ld4(cp + gc.px * cyo);
+    p.Cz = ld4(a.xc + gc.s[2] * czo + cinx + gc.px * cy);
+    return p;
+  };
+  PIn pin;
+  if (act) pin = loadP(z0 - VS_HALO);
+  float4 xi0 = f4zero(), xi1 = f4zero(), xiC = f4zero();  // x and the coarse solution for the increment of the NEXT step
+  auto loadX = [&](int q) {
+    if (core && q >= z0 && q <= z1 - 1) {
+      const i64 o = g.s[2] * q + gin;
+      xi0 = ld4(a.x + o);
+      xi1 = ld4(a.x + o + 4);
+      xiC = ld4(a.xc + gc.s[2] * ((q + 1) >> 1) + cinx + gc.px * cy);
+    }
+  };
+
   int se = 0, sr = 0;  // ring slots of plane t
   for (int t = z0 - VS_HALO; t <= z1 + 6; t++) {
-    auto Es = [&](int k) -> float* {  // ϵ ring slot of plane t−k
-      int s = se - k;
-      if (s < 0) s += VS_DE;
-      return ER + s * VS_PF;
-    };
-    auto Rs = [&](int k) -> float* {
-      int s = sr - k;
-      if (s < 0) s += VS_DR;
-      return RR + s * VS_PF;
-    };
+    const int* const le = vs_lut.e[se];  // slot offsets of planes t, t−1, …
+    const int* const lr = vs_lut.r[sr];
+    const bool doI = core && t - 7 >= z0 && t - 7 <= z1 - 1;
     // =============== phase α ===============
     if (act && t <= z1 + 4) {
       // ---- P: r¹ = r − ω·A ϵc with ϵc = coarse.x[down(·)], ϵ⁰ = r¹·iD, all 8 cells of the group on plane t ----
-      const int zr = wrap(t, n2);
-      const int cz = (zr + 1) >> 1, czo = (wrap((zr & 1) ? zr - 1 : zr + 1, n2) + 1) >> 1;
-      const float* rp = a.r + g.s[2] * zr + gin;
-      const float4 f0 = ld4(rp), f1 = ld4(rp + 4);
-      const float* cp = a.xc + gc.s[2] * cz + cinx;
-      const float4 C = ld4(cp + gc.px * cy);
-      const float cl = cp[gc.px * cy + dcl], cr = cp[gc.px * cy + dcr];
-      const float4 Cy = ld4(cp + gc.px * cyo);
-      const float4 Cz = ld4(a.xc + gc.s[2] * czo + cinx + gc.px * cy);
+      const float4 f0 = pin.f0, f1 = pin.f1, C = pin.C, Cy = pin.Cy, Cz = pin.Cz;
+      const float cl = pin.cl, cr = pin.cr;
       const float L0 = a.L0, L1 = a.L1, L2 = a.L2, D = a.D;
       // fine cell j of the group sits in coarse cell j/2; its x neighbour outside that coarse cell is on the left for even j
       auto Aec = [&](float c0, float xo, float yo, float zo) -> float {
@@ -207,12 +253,14 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       ro.z = f1.y - w * Aec(C.z, C.w, Cy.z, Cz.z);
       re.w = f1.z - w * Aec(C.w, C.z, Cy.w, Cz.w);
       ro.w = f1.w - w * Aec(C.w, cr, Cy.w, Cz.w);
-      float* Rt = Rs(0);
-      float* Et = Es(0);
-      st4(Rt + e4, re);
-      st4(Rt + VS_AF + e4, ro);
-      st4(Et + e4, mul4s(re, iD));
-      st4(Et + VS_AF + e4, mul4s(ro, iD));
+      st4(sb + lr[0], re);
+      st4(sb + lr[0] + VS_AF, ro);
+      st4(sb + le[0], mul4s(re, iD));
+      st4(sb + le[0] + VS_AF, mul4s(ro, iD));
+      // next plane's loads only now: a scoreboard counts all loads in flight from one instruction, so the loads of plane t+1
+      // must not be issued before the values of plane t have been consumed (the fence keeps the compiler from hoisting them)
+      asm volatile("" ::: "memory");
+      if (t + 1 <= z1 + 4) pin = loadP(t + 1);
     }
     // ---- sweeps 2 and 4 move the even cells ((x+y+z) even; the array of even positions holds odd x) ----
 #pragma unroll
@@ -223,10 +271,11 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
         const int zr = wrap(q, n2);
         const bool zsm = zr == 1, zsp = zr == n2;
         const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
+        const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSl, oYm, oYp, stL, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
         else
-          vs_sweep<false>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSr, oYm, oYp, stR, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
       }
     }
     __syncthreads();
@@ -240,33 +289,34 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
         const int zr = wrap(q, n2);
         const bool zsm = zr == 1, zsp = zr == n2;
         const bool te = ((1 + ypar + q) & 1) == 1;
+        const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSl, oYm, oYp, stL, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
         else
-          vs_sweep<false>(Es(k), Es(k + 1), Es(k - 1), Rs(k), Rs(k + 1), Rs(k - 1), e4, oSr, oYm, oYp, stR, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
       }
     }
     // ---- increment!: r² = r¹ − ω·A ϵ⁴ ; x² = (x + ω·ϵc) + ω·ϵ⁴ on plane t−7, core cells only ----
     {
       const int q = t - 7;
-      if (q >= z0 && q <= z1 - 1 && core) {
-        const float* Eq = Es(7);
-        const float* Eqm = Es(8);
-        const float* Eqp = Es(6);
-        const float* Rq = Rs(7);
-        const float4 ce = ld4(Eq + e4), co = ld4(Eq + VS_AF + e4);
-        const float sl = Eq[VS_AF + e4 + oSl], sr_ = Eq[e4 + oSr];
-        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, ld4(Eq + e4 + oYm), ld4(Eq + e4 + oYp), ld4(Eqm + e4), ld4(Eqp + e4), a);
-        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ld4(Eq + VS_AF + e4 + oYm), ld4(Eq + VS_AF + e4 + oYp), ld4(Eqm + VS_AF + e4),
-                                  ld4(Eqp + VS_AF + e4), a);
-        const float4 re = ld4(Rq + e4), ro = ld4(Rq + VS_AF + e4);
+      if (doI) {
+        const float* Eq = sb + le[7];
+        const float* Eqm = sb + le[8];
+        const float* Eqp = sb + le[6];
+        const float* Rq = sb + lr[7];
+        const float4 ce = ld4(Eq), co = ld4(Eq + VS_AF);
+        const float sl = Eq[VS_AF - 1], sr_ = Eq[4];
+        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, ld4(Eq - oY), ld4(Eq + oY), ld4(Eqm), ld4(Eqp), a);
+        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ld4(Eq + VS_AF - oY), ld4(Eq + VS_AF + oY), ld4(Eqm + VS_AF),
+                                  ld4(Eqp + VS_AF), a);
+        const float4 re = ld4(Rq), ro = ld4(Rq + VS_AF);
         const float4 ne = make_float4(re.x - w * Ae.x, re.y - w * Ae.y, re.z - w * Ae.z, re.w - w * Ae.w);
         const float4 no = make_float4(ro.x - w * Ao.x, ro.y - w * Ao.y, ro.z - w * Ao.z, ro.w - w * Ao.w);
         const i64 o = g.s[2] * q + gin;  // core rows and planes are inside the domain: no wrap
         st4(a.r2 + o, make_float4(ne.x, no.x, ne.y, no.y));
         st4(a.r2 + o + 4, make_float4(ne.z, no.z, ne.w, no.w));
-        const float4 C = ld4(a.xc + gc.s[2] * ((q + 1) >> 1) + cinx + gc.px * cy);
-        float4 x0 = ld4(a.x + o), x1 = ld4(a.x + o + 4);
+        const float4 C = xiC;
+        float4 x0 = xi0, x1 = xi1;
         x0.x = (x0.x + w * C.x) + w * ce.x;
         x0.y = (x0.y + w * C.x) + w * co.x;
         x0.z = (x0.z + w * C.y) + w * ce.y;
@@ -283,6 +333,8 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
         }
       }
     }
+    asm volatile("" ::: "memory");
+    loadX(t + 1 - 7);
     __syncthreads();
     se = se + 1 == VS_DE ? 0 : se + 1;
     sr = sr + 1 == VS_DR ? 0 : sr + 1;
