@@ -39,6 +39,8 @@ WORKLOADS = {
 # (perfect halo reuse) — DESIGN.md §kernels.  (general variable-coefficient form, uniform-coefficient form)
 ALG_WORDS = {
     "fm_conv": (10.5, 7.5),        # general: read u/u⁰ 3(+3 corrector) V 3, write f 3; uniform: read u⁰ 3 (+u 3 corrector), write u 3
+    "fm_conv4": (7.5, 7.5),        # uniform mode only: read u⁰ 3 (+u 3 corrector), write u 3
+    "f_vsmooth": (4.125, 4.125),   # uniform mode only: read r x (+ coarse x 1/8), write r' x  — replaces f_increment<PROLONG>, f_gs_a, 3 f_gs_half, f_increment
     "k_conv_bdim1": (10.5, 10.5),
     "k_bdim2": (22.5, 22.5),       # read f3 V3 μ₀3 μ₁9 (+u3 corrector); write u3
     "k_f_lowghost": (0, 0),
@@ -61,7 +63,13 @@ ALG_WORDS = {
     "f_cfl": (4, 3),               # read u3 [write σ]
     "k_cfl": (4, 4),
 }
-MULTILEVEL = {"f_jacobi", "k_jacobi", "k_restrict", "f_gs_a", "f_gs_half", "k_gs_init", "k_gs_sweep", "f_increment", "k_increment", "k_prolong_inc"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), by (workload, kernel)
+NCU_TRAFFIC = {
+    ("tgv512", "fm_conv4"): 4.06e9,   # profiles/r1_v3_fm_conv4.txt: predictor 3.24e9 + corrector 4.89e9, averaged (algorithmic 4.07e9)
+    ("tgv512", "f_vsmooth"): 2.22e9,  # profiles/r1_v3_vsmooth.txt: level-0 launch (algorithmic 2.24e9)
+}
 
 
 def peaks():
@@ -274,17 +282,15 @@ def main():
     uni = C2.c_int(0)
     check(fl.L, fl.L.wl_is_const_coeff(fl.h, C2.byref(uni)))
     uni = bool(uni.value)
-    lv = sim.pois.nlevels
-    cells_lvl = [int(np.prod(sim.pois.level_dims(l))) for l in range(lv)]
     tot_ms = sum(v[1] for v in tim.values())
     ksum = {}
-    for k, (cnt, m) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
+    for k, (cnt, m, ncells) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
         ent = {"launches": cnt, "ms": round(m, 3), "share": round(m / tot_ms, 4)}
         words = ALG_WORDS.get(k)
         if words and words[1 if uni else 0] > 0:
             w = words[1 if uni else 0]
-            # a multigrid kernel is launched once per level per call: its launches cover Σ_l cells_l per `lv` launches
-            per_launch = w * 4 * (sum(cells_lvl) / lv if k in MULTILEVEL else padded)
+            # the library reports, per kernel, the ghost-padded cells of the level every launch ran on (summed over the launches)
+            per_launch = w * 4 * ncells / cnt
             ach = per_launch / (m / cnt * 1e-3) / 1e9
             ent.update(alg_bytes_per_launch=int(per_launch), achieved_gbs=round(ach, 1), frac=round(ach / peak, 4))
         ksum[k] = ent
@@ -294,9 +300,10 @@ def main():
             "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": top.get("alg_bytes_per_launch"),
             "avg_launch_us": round(top["ms"] / top["launches"] * 1e3, 2),
             "note": "achieved = algorithmic bytes per launch / CUDA-event time on the library stream, averaged over the launches of the timed steps "
-                    "(multigrid kernels: averaged over the levels they run on)"}
-    if name == "fm_conv":
-        roof["note"] += "; fm_conv is FP32-issue-bound (≈900 instructions per cell for 15 QUICK flux evaluations), not HBM-bound: see DESIGN.md"
+                    "(multigrid kernels: bytes and time summed over the levels they run on)"}
+    if name in ("fm_conv", "fm_conv4"):
+        roof["note"] += "; the flux kernel is FP32-issue-bound (9.4 QUICK face fluxes of ≈36 exact-IEEE operations per cell), not HBM-bound: see DESIGN.md"
+    roof["traffic"] = NCU_TRAFFIC.get((args.workload, name))
     # whole-step roofline with the SURVEY §8d formulas
     if uni:
         b_alg, formula = 200 + 56 * n_v, "uniform-coefficient (no body, periodic): 200 + 56·n_V B/cell/step (SURVEY.md §8d)"

@@ -126,6 +126,7 @@ struct Chunk {
 struct ProfRec {
   const char* name;
   cudaEvent_t a, b;
+  double cells = 0;
 };
 
 struct wl_handle {
@@ -174,6 +175,7 @@ struct wl_handle {
   // Uniform mode on one GPU never reads the periodic ghost cells of u (every reader wraps its indices), so the BC! launches of
   // mom_step! are deferred until something outside the step loop looks at u (flush_ghosts).
   bool ghosts_dirty = false;
+  double prof_cells = 0;  // ghost-padded cells of the level the next launches run on (profiling: algorithmic bytes per kernel)
   cudaStream_t st = nullptr;
   int64_t launches = 0;
   double tol;
@@ -186,6 +188,7 @@ static void prof_begin(wl_handle* h, const char* name) {
   if (!h->prof) return;
   ProfRec r;
   r.name = name;
+  r.cells = h->prof_cells;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, h->st);
@@ -195,6 +198,13 @@ static void prof_end(wl_handle* h) {
   if (!h->prof) return;
   cudaEventRecord(h->prof_recs.back().b, h->st);
 }
+
+struct ProfLevel {  // launches inside this scope are accounted to level `l`
+  wl_handle* h;
+  double saved;
+  ProfLevel(wl_handle* h_, const Level& l) : h(h_), saved(h_->prof_cells) { h->prof_cells = (double)l.g.N[0] * l.g.N[1] * l.g.N[2]; }
+  ~ProfLevel() { h->prof_cells = saved; }
+};
 
 static Grid make_grid(int D, const int* N, const int* per) {
   Grid g;
@@ -641,6 +651,7 @@ static int read_slot(wl_handle* h, int slot, double* out) {
 
 // GaussSeidelRB!(p;it=4,ω)  src/Poisson.jl:141-148
 static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int with_l2) {
+  ProfLevel pl(h, l);
   dim3 b = blk(h->D);
   Box in = l.inside();
   if (l.fast && h->fused_gs && (l.g.N[2] - 2) % 2 == 0) {
@@ -693,6 +704,7 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
 // With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; *fused tells whether it was.
 static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fused_out) {
+  ProfLevel pl(h, l);
   dim3 b = blk(h->D);
   Box in = l.inside();
   bool fused = false;
@@ -790,6 +802,7 @@ static bool vs_fusable(const wl_handle* h, size_t li) {
 static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   Level& f = h->levels[li];
   Level& c = h->levels[li + 1];
+  ProfLevel pl(h, f);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(f_vsmooth<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
@@ -969,6 +982,7 @@ static int vcycle(wl_handle* h, size_t li, const float* wp, bool defer_up = fals
       TRY(smooth(h, coarse, wp, last ? 1 : 0, 0));
   }
   if (defer_up) return 0;
+  ProfLevel pl(h, fine);
   Box fin = fine.inside();
   if (fine.fast && coarse.fullc) {
     ProlongSrc ps{coarse.x, coarse.g, 0, 0, 0};
@@ -1877,6 +1891,7 @@ int wl_selftest_div6(uint64_t* nbad) {
 
 int wl_set_profiling(wl_handle* h, int enabled) {
   if (!h) return fail("null handle");
+  h->prof_cells = (double)h->g.N[0] * h->g.N[1] * h->g.N[2];
   h->prof = enabled != 0;
   return 0;
 }
@@ -1887,7 +1902,7 @@ int wl_get_timings(wl_handle* h, char* buf, int* len) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->st));
   std::vector<std::string> names;
-  std::vector<double> ms;
+  std::vector<double> ms, cells;
   std::vector<long> cnt;
   for (auto& r : h->prof_recs) {
     float t = 0;
@@ -1904,16 +1919,18 @@ int wl_get_timings(wl_handle* h, char* buf, int* len) {
     if (k == names.size()) {
       names.push_back(nm);
       ms.push_back(0);
+      cells.push_back(0);
       cnt.push_back(0);
     }
     ms[k] += t;
+    cells[k] += r.cells;
     cnt[k]++;
   }
   h->prof_recs.clear();
   std::string& out = h->prof_text;
   char line[256];
   for (size_t k = 0; k < names.size(); k++) {
-    snprintf(line, sizeof line, "%s %ld %.6f\n", names[k].c_str(), cnt[k], ms[k]);
+    snprintf(line, sizeof line, "%s %ld %.6f %.0f\n", names[k].c_str(), cnt[k], ms[k], cells[k]);
     out += line;
   }
   const int need = (int)out.size() + 1;

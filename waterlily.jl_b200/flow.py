@@ -165,7 +165,8 @@ class Flow:
         _lib.check(self.L, self.L.wl_set_profiling(self.h, int(on)))
 
     def timings(self):
-        """{kernel: (launches, total_ms)} recorded with CUDA events on the library's stream since the last call."""
+        """{kernel: (launches, total_ms, total_cells)} recorded with CUDA events on the library's stream since the last call;
+        total_cells = ghost-padded cells of the levels those launches ran on, summed over the launches."""
         n = C.c_int(0)
         _lib.check(self.L, self.L.wl_get_timings(self.h, None, C.byref(n)))
         buf = C.create_string_buffer(n.value + 16)
@@ -173,9 +174,9 @@ class Flow:
         _lib.check(self.L, self.L.wl_get_timings(self.h, buf, C.byref(n)))
         out = {}
         for line in buf.value.decode().splitlines():
-            k, c, ms = line.split()
-            c0, m0 = out.get(k, (0, 0.0))
-            out[k] = (c0 + int(c), m0 + float(ms))
+            k, c, ms, cells = line.split()
+            c0, m0, n0 = out.get(k, (0, 0.0, 0.0))
+            out[k] = (c0 + int(c), m0 + float(ms), n0 + float(cells))
         return out
 
     @property
