@@ -53,6 +53,7 @@ enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4,
 struct Level {
   Grid g;
   float *L = nullptr, *Dg = nullptr, *iD = nullptr, *x = nullptr, *eps = nullptr, *r = nullptr, *r2 = nullptr, *z = nullptr;
+  float *rext = nullptr, *xext = nullptr;  // z slabs, f_vsmooth: 2×4 planes of r and 2×2 planes of x beyond the ghost planes
   int c[3] = {0, 0, 0};  // coarsening mask from the previous (finer) level
   bool ownL = false, ownz = false;
   bool fast = false;     // march kernels apply (3-D, interior x size a multiple of 4)
@@ -158,7 +159,7 @@ struct wl_handle {
   int halo_seq = 0;
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
-  int slab_min_planes = 16;
+  int slab_min_planes = 64;  // measured at 2 GPUs, 512³: 16 → 9.70, 32 → 9.49, 64 → 9.27, 128 → 9.11 ms/step (exchange latency > redundant work on small levels)
   // persistent coarse-level kernel: levels >= small_from run inside one cooperative launch per V-cycle (0 = disabled)
   int small_from = 0;
   int small_grid = 0;
@@ -484,7 +485,8 @@ static int launch_exitbc(wl_handle* h, float* u, const float* u0, float dt_scale
 }
 
 // ---- Poisson hierarchy ---------------------------------------------------------------------
-static inline bool lazy_bc(const wl_handle* h) { return h->uni && h->D == 3 && !h->dist.on() && !h->cfg.exitBC; }
+// (z slabs too: the z ghost planes come from the halo exchange, and BC! of the x and y ghosts — also those inside the z ghost planes — is local)
+static inline bool lazy_bc(const wl_handle* h) { return h->uni && h->D == 3 && !h->cfg.exitBC; }
 // BC!(u) of mom_step! (src/Flow.jl:194,209,230): deferred in uniform mode, see wl_handle::ghosts_dirty
 static void step_bc(wl_handle* h, const float* keep) {
   if (lazy_bc(h)) {
@@ -597,6 +599,10 @@ static int build_levels(wl_handle* h) {
     TRY(dalloc(h, &l.eps, n));
     TRY(dalloc(h, &l.r, n));
     TRY(dalloc(h, &l.r2, n));
+    if (l.slab) {
+      TRY(dalloc(h, &l.rext, (size_t)8 * l.g.s[2]));
+      TRY(dalloc(h, &l.xext, (size_t)4 * l.g.s[2]));
+    }
   }
   return 0;
 }
@@ -790,13 +796,17 @@ static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int wi
 // f_vsmooth applies to level li: uniform mode on one GPU, a fully coarsened level below it that is not part of the persistent
 // coarse-level kernel's range, sizes that fit the kernel's 8-cell groups and red/black planes, enough planes to fill the pipeline
 static bool vs_fusable(const wl_handle* h, size_t li) {
-  if (!h->vsmooth || !h->uni || h->dist.on() || h->D != 3 || h->cfg.smoother != WL_SMOOTH_GSRB) return false;
+  if (!h->vsmooth || !h->uni || h->D != 3 || h->cfg.smoother != WL_SMOOTH_GSRB) return false;
   if (li + 1 >= h->levels.size()) return false;
   if (h->small_from > 0 && (int)li >= h->small_from) return false;
   const Level& f = h->levels[li];
   const Level& c = h->levels[li + 1];
   const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
-  return f.fast && c.fullc && !f.slab && n0 % 8 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && n0 >= 64 && n1 >= 32 && n2 >= 64;
+  if (f.slab) {  // z slab: the kernel's 5-plane halo comes from the neighbours by peer-to-peer pushes
+    if (!h->p2p || n2 < 16 || n2 % 2 || (c.slab && c.g.N[2] - 2 < 4)) return false;
+    return f.fast && c.fullc && n0 % 8 == 0 && n1 % 2 == 0 && n0 >= 64 && n1 >= 32;
+  }
+  return f.fast && c.fullc && n0 % 8 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && n0 >= 64 && n1 >= 32 && n2 >= 64;
 }
 // prolongate! + increment! + GaussSeidelRB! + increment! (+ L₂) of level li in one launch (wl_vsmooth.cuh)
 static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
@@ -840,6 +850,34 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   a.D = k.Dc;
   a.iD = k.iDc;
   a.zchunk = zc;
+  a.slab = f.slab ? 1 : 0;
+  a.cslab = c.slab ? 1 : 0;
+  a.zoff = f.slab ? f.g.zoff : 0;
+  a.n2g = f.Ng2 - 2;
+  a.rext = f.rext;
+  a.cxext = c.xext;
+  if (f.slab) {
+    // planes −4 … −1 and n2+2 … n2+5 of r (the ghost planes 0 and n2+1 are current since Jacobi!'s exchange), and, when the coarse
+    // level is a slab too, its planes −2, −1 and nc+2, nc+3 of x: pushed straight into the neighbours' rext / xext
+    PlaneMove mv[8];
+    int m = 0;
+    const i64 s2 = f.g.s[2];
+    for (int k = 0; k < 4; k++) {
+      mv[m++] = {f.r + s2 * (n2 - 4 + k), 1, f.rext + s2 * k};
+      mv[m++] = {f.r + s2 * (2 + k), 0, f.rext + s2 * (4 + k)};
+    }
+    TRY(p2p_push(h, f.g, mv, m));
+    if (c.slab) {
+      const i64 c2 = c.g.s[2];
+      const int nc = c.g.N[2] - 2;
+      m = 0;
+      for (int k = 0; k < 2; k++) {
+        mv[m++] = {c.x + c2 * (nc - 2 + k), 1, c.xext + c2 * k};
+        mv[m++] = {c.x + c2 * (2 + k), 0, c.xext + c2 * (2 + k)};
+      }
+      TRY(p2p_push(h, c.g, mv, m));
+    }
+  }
   dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
   if (with_l2)
@@ -850,6 +888,8 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   h->launches++;
   std::swap(f.r, f.r2);
   CK(cudaGetLastError());
+  TRY(exch2(h, f, f.r, f.x));
+  if (with_l2) TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
   return 0;
 }
 // ---- flattening of the coarse end of the V-cycle for k_small_levels ----------------------------------------------------
@@ -1424,6 +1464,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
+  if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
   if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);

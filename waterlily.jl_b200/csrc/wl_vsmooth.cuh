@@ -52,6 +52,14 @@ struct VsArgs {
   const float* wp;   // ω
   float L0, L1, L2, D, iD;
   int zchunk;
+  // z slab (multi-GPU): the level holds planes 1 … n2 of a globally periodic extent of n2g planes starting after global plane
+  // zoff; planes 0 and n2+1 of r are the exchanged ghost planes, the four planes beyond them on each side are in rext
+  // ([side][4] planes, nearest-to-farthest from the slab on the lower side reversed: index t+4 for t = −4…−1, t−n2−2 above).
+  // The coarse solution is either a slab too (cslab: local planes 0 … n2/2+1 in xc, two more per side in cxext) or replicated
+  // (whole periodic extent in xc, global indices).
+  int slab, cslab, zoff, n2g;
+  const float* rext;
+  const float* cxext;
 };
 
 __device__ __forceinline__ float4 mul4s(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -198,19 +206,33 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
     float4 f0, f1, C, Cy, Cz;
     float cl, cr;
   };
+  // plane t of r (t may lie up to 5 planes outside the level) and the coarse plane under fine plane t
+  auto rplane = [&](int t) -> const float* {
+    if (!a.slab) return a.r + g.s[2] * wrap(t, n2);
+    if (t < 0) return a.rext + g.s[2] * (t + 4);
+    if (t > n2 + 1) return a.rext + g.s[2] * (4 + t - n2 - 2);
+    return a.r + g.s[2] * t;
+  };
+  auto cplane = [&](int t) -> const float* {
+    if (!a.slab) return a.xc + gc.s[2] * ((wrap(t, n2) + 1) >> 1);
+    if (!a.cslab) return a.xc + gc.s[2] * ((wrap(t + a.zoff, a.n2g) + 1) >> 1);
+    const int c = (t + 1) >> 1, nc = n2 >> 1;  // arithmetic shift = floor: planes below the slab map to coarse planes ≤ 0
+    if (c < 0) return a.cxext + gc.s[2] * (c + 2);
+    if (c > nc + 1) return a.cxext + gc.s[2] * (2 + c - nc - 2);
+    return a.xc + gc.s[2] * c;
+  };
   auto loadP = [&](int t) -> PIn {
     PIn p;
-    const int zr = wrap(t, n2);
-    const int cz = (zr + 1) >> 1, czo = (wrap((zr & 1) ? zr - 1 : zr + 1, n2) + 1) >> 1;
-    const float* rp = a.r + g.s[2] * zr + gin;
+    const int tz = ((t + a.zoff) & 1) ? t - 1 : t + 1;  // the fine z neighbour outside the own coarse cell (zoff and n2 are even)
+    const float* rp = rplane(t) + gin;
     p.f0 = ld4(rp);
     p.f1 = ld4(rp + 4);
-    const float* cp = a.xc + gc.s[2] * cz + cinx;
+    const float* cp = cplane(t) + cinx;
     p.C = ld4(cp + gc.px * cy);
     p.cl = cp[gc.px * cy + dcl];
     p.cr = cp[gc.px * cy + dcr];
     p.Cy = ld4(cp + gc.px * cyo);
-    p.Cz = ld4(a.xc + gc.s[2] * czo + cinx + gc.px * cy);
+    p.Cz = ld4(cplane(tz) + cinx + gc.px * cy);
     return p;
   };
   PIn pin;
@@ -221,7 +243,7 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       const i64 o = g.s[2] * q + gin;
       xi0 = ld4(a.x + o);
       xi1 = ld4(a.x + o + 4);
-      xiC = ld4(a.xc + gc.s[2] * ((q + 1) >> 1) + cinx + gc.px * cy);
+      xiC = ld4(cplane(q) + cinx + gc.px * cy);
     }
   };
 
@@ -268,8 +290,8 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       const int q = t - k;
       const int h = k == 3 ? 3 : 1;  // sweep 2 is valid on planes z0−3 … z1+2, sweep 4 on z0−1 … z1
       if (act && q >= z0 - h && q <= z1 - 1 + h) {
-        const int zr = wrap(q, n2);
-        const bool zsm = zr == 1, zsp = zr == n2;
+        const int zr = a.slab ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == (a.slab ? a.n2g : n2);
         const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
         const bool anyYZ = stY || zsm || zsp;
         if (te)
@@ -286,8 +308,8 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       const int q = t - k;
       const int h = k == 1 ? 4 : 2;  // sweep 1 is valid on planes z0−4 … z1+3, sweep 3 on z0−2 … z1+1
       if (act && q >= z0 - h && q <= z1 - 1 + h) {
-        const int zr = wrap(q, n2);
-        const bool zsm = zr == 1, zsp = zr == n2;
+        const int zr = a.slab ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == (a.slab ? a.n2g : n2);
         const bool te = ((1 + ypar + q) & 1) == 1;
         const bool anyYZ = stY || zsm || zsp;
         if (te)
