@@ -297,3 +297,29 @@ def test_fused_kernels_equal_unfused_kernels(monkeypatch):
     a, b = outs
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert a[2] == b[2] and np.array_equal(a[3], b[3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("periodic", [True, False])
+def test_tiny_velocities_take_the_exact_division(periodic):
+    """A quiescent far field holds velocities like 1e-34 (first steps of a wake; tails of a localised vortex): outside the
+    proven range of the flux kernels' division-free x/6.  Both flux kernels (fm_conv4 in uniform mode, fm_conv with walls) must
+    fall back to the IEEE division there and stay bit-identical to the oracle — not raise an error."""
+    dims = (64, 64, 64) if periodic else (64, 32, 32)
+    N = tuple(d + 2 for d in dims)
+    rng = np.random.default_rng(5)
+    u0 = tgv3d_u0(N, dims[0])
+    u0[0] *= F(0.5)
+    u0[1] = (1e-33 * rng.standard_normal(u0[1].shape)).astype(F)   # below 2^-100 ≈ 7.9e-31
+    u0[2] = (1e-40 * rng.standard_normal(u0[2].shape)).astype(F)   # denormal
+    if periodic:
+        o, s = make_pair(dims, (0.0, 0.0, 0.0), nu=0.01, perdir=(1, 2, 3), u0=u0)
+    else:
+        o, s = make_pair(dims, (0.5, 0.0, 0.0), nu=0.01, u0=u0)
+    from wl_b200 import lib as wlib
+    for _ in range(2):
+        o.mom_step()
+        wlib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    s.flow.sync()
+    assert np.array_equal(s.flow.u, o.field("u"))
+    assert np.array_equal(s.flow.p, o.field("p"))

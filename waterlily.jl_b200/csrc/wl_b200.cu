@@ -159,11 +159,14 @@ struct wl_handle {
   int halo_seq = 0;
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
-  int slab_min_planes = 64;  // measured at 2 GPUs, 512³: 16 → 9.70, 32 → 9.49, 64 → 9.27, 128 → 9.11 ms/step (exchange latency > redundant work on small levels)
+  int slab_min_planes = 8;
+  double slab_min_cells = 3.0e6;  // 512³ on 2/4/8 GPUs: levels 514³ and 258³ are z slabs, 130³ and below replicated
   // persistent coarse-level kernel: levels >= small_from run inside one cooperative launch per V-cycle (0 = disabled)
   int small_from = 0;
   int small_grid = 0;
-  int* d_flags = nullptr;  // [0]: a flux kernel met a value outside the proven range of its division-free x/6 (non-finite or < 8e-31)
+  int* d_flags = nullptr;  // [0]: the uniform-mode flux kernel met a non-finite velocity (or |u| > 1e37)
+  int* d_redo = nullptr;   // fm_conv4: blocks to recompute with the IEEE division (see div6_chk)
+  size_t redo_cap = 0;
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
@@ -569,7 +572,10 @@ static int build_levels(wl_handle* h) {
     if (P > 1) {
       const int nz = l.g.N[2] - 2;
       const bool prev = i == 0 || h->levels[i - 1].slab;
-      l.slab = prev && nz % P == 0 && nz / P >= (i == 0 ? 4 : h->slab_min_planes) && (nz / P) % 2 == 0 && (i == 0 || l.c[2]);
+      // a level is decomposed while its slabs keep enough planes AND it is big enough for 1/P of its kernels to outweigh the
+      // exchanges after them (≈25 µs each); smaller levels are replicated on every rank
+      const double gcells = (double)l.g.N[0] * l.g.N[1] * l.g.N[2];
+      l.slab = prev && nz % P == 0 && nz / P >= (i == 0 ? 4 : h->slab_min_planes) && (nz / P) % 2 == 0 && (i == 0 || (l.c[2] && gcells > h->slab_min_cells));
       if (i == 0 && !l.slab) return fail("z-slab decomposition needs dims[3]=%d divisible by %d ranks with an even number (>=4) of planes each", nz, P);
       if (l.slab) {
         l.g = slab_grid(h, gl[i].g);
@@ -815,8 +821,10 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   ProfLevel pl(h, f);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(f_vsmooth<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
     attr = true;
   }
   const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
@@ -880,10 +888,17 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   }
   dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
-  if (with_l2)
-    f_vsmooth<true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-  else
-    f_vsmooth<false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  if (f.slab) {
+    if (with_l2)
+      f_vsmooth<true, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+    else
+      f_vsmooth<false, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  } else {
+    if (with_l2)
+      f_vsmooth<true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+    else
+      f_vsmooth<false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  }
   prof_end(h);
   h->launches++;
   std::swap(f.r, f.r2);
@@ -1173,15 +1188,28 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   if (FUSE && nowall && h->conv4 && (g.N[0] - 2) % 4 == 0) {  // uniform mode: four cells per thread
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(fm_conv4<LAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
+      cudaFuncSetAttribute(fm_conv4<LAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
+      cudaFuncSetAttribute(fm_conv4<LAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
       attr = true;
     }
     const int zc = std::min(h->conv4_zchunk, g.N[2] - 2);
     dim3 g4(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, C4TY), cdiv(g.N[2] - 2, zc));
     prof_begin(h, "fm_conv4");
-    fm_conv4<LAM><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags);
+    if ((size_t)g4.x * g4.y * g4.z + 1 > h->redo_cap) {
+      fail("fm_conv4: grid larger than the redo list");
+      return;
+    }
+    // fast x/6 everywhere; then the blocks that met an input outside its proven range (none, normally: that launch exits at once)
+    // again with the IEEE division
+    cudaMemsetAsync(h->d_redo, 0, sizeof(int), h->st);
+    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags,
+                                                               h->d_redo, (int)g4.x, (int)g4.y);
     prof_end(h);
-    h->launches++;
+    prof_begin(h, "fm_conv4_exact");
+    fm_conv4<LAM, true><<<dim3(2 * 148), dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext,
+                                                                         h->d_flags, h->d_redo, (int)g4.x, (int)g4.y);
+    prof_end(h);
+    h->launches += 2;
     return;
   }
   prof_begin(h, "fm_conv");
@@ -1297,7 +1325,12 @@ static int check_flags(wl_handle* h) {
   int f = 0;
   CK(cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  if (f) return fail("the flux kernel met a non-finite or denormal-range (<8e-31) value: the velocity field has diverged");
+  if (getenv("WL_DEBUG")) {
+    int n = 0;
+    cudaMemcpy(&n, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[wl_b200] fm_conv4 repeated %d warp-planes with the IEEE division so far\n", n);
+  }
+  if (f) return fail("the flux kernel met a non-finite velocity (or |u| > 1e37): the velocity field has diverged");
   if (h->mbox) {
     int e = 0;
     CK(cudaMemcpyAsync(&e, h->mbox + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -1465,6 +1498,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
+  if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);
   if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
@@ -1515,6 +1549,9 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       float* q = nullptr;
       if ((rc = dalloc(h, &q, 8))) break;
       h->d_flags = (int*)q;
+      h->redo_cap = (size_t)1 << 18;
+      if ((rc = dalloc(h, &q, h->redo_cap))) break;
+      h->d_redo = (int*)q;
     }
     if ((rc = build_levels(h))) break;
     if (h->D == 3 && h->cfg.pois_kind == WL_POIS_MULTILEVEL && h->cfg.smoother == WL_SMOOTH_GSRB && !(cfg->flags & WL_FLAG_NO_PERSISTENT)) {

@@ -25,16 +25,20 @@
 #define C4FILL ((C4H * C4Q + 32 * C4TY - 1) / (32 * C4TY))
 #define C4SMEM ((C4RING * C4PS + 2 * 3 * (C4TY + 1) * 32 * 4) * 4)
 
-// x/6, exact as div6_flag (wl_kernels.cuh).  The proven range of the two-FMA form is 2^-100 ≤ |x| ≤ 3e38: the lower bound is tested
-// here (a non-zero input below it raises `bad`, tested once per thread), the upper bound follows from the kernel's per-cell test
-// |u| ≤ 1e37 (|5c+2d−u| ≤ 8e37).
-__device__ __forceinline__ float div6_chk(float x, bool& bad) {
+// x/6, exact for every input.  Fast form (SAFE=false): the two FMAs of wl_kernels.cuh, proven equal to the IEEE division for
+// 2^-100 ≤ |x| ≤ 3e38; ±0 → ±0; a non-zero input below that range (the 1e-34 far-field velocities of a flow starting from rest)
+// raises `tiny`: the block then marks itself in the `redo` list and the SAFE=true instance of the kernel, launched right behind,
+// recomputes exactly the marked blocks with the IEEE division.  The upper end of the range is covered by the kernel's |u| ≤ 1e37
+// test (|5c+2d−u| ≤ 8e37), which also reports a diverged (non-finite) field.
+template <bool SAFE>
+__device__ __forceinline__ float div6_chk(float x, bool& tiny) {
+  if (SAFE) return x / 6.f;
   const float C = 0.16666667163372039794921875f;
   const float q0 = x * C;
   const float r = __fmaf_rn(-6.f, q0, x);
   const float q = __fmaf_rn(r, C, q0);
   const bool inr = fabsf(x) >= 7.888609052210118e-31f;
-  bad = bad || (!inr && x != 0.f);
+  tiny = tiny || (!inr && x != 0.f);
   return inr ? q : q0;  // ±0 → ±0 (= q0)
 }
 // ϕu(j, CI(I,i), u, û, λ) − ν ∂(j, CI(I,i), u) for an inner / periodic face (src/Flow.jl:8-11,52)
@@ -45,7 +49,7 @@ __device__ __forceinline__ float div6_chk(float x, bool& bad) {
 // mirroring (multiplying the three inputs by s = −1) is exact in IEEE arithmetic, so one code path serves both:
 // λ = s·min(max(min(a',b'), s·c), s·d) with s = sign(d−c).  d−c is ±(u[I]−u[I−δ]) with the sign of û, so s = sign(t·û).
 // (û = 0 gives conv = 0·λ = 0 whatever s is.)  min/max run on the half-rate ALU pipe, the multiplications on the FMA pipe.
-template <int LAM>
+template <int LAM, bool SAFE>
 __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, bool& bad) {
   const float t = u0c - um1;
   const float diff = nu * t;
@@ -55,7 +59,7 @@ __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0
   if (LAM == 0) {
     const float s = __uint_as_float((__float_as_uint(t * uf) & 0x80000000u) | 0x3f800000u);
     const float cs = c * s, ds = d * s, us = u * s;
-    const float a = div6_chk(5.f * cs + 2.f * ds - us, bad);
+    const float a = div6_chk<SAFE>(5.f * cs + 2.f * ds - us, bad);
     const float b = 10.f * cs - 9.f * us;
     lam = s * fminf(fmaxf(fminf(a, b), cs), ds);
   } else if (LAM == 1) {
@@ -65,11 +69,11 @@ __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0
   }
   return uf * lam - diff;
 }
-template <int LAM>
+template <int LAM, bool SAFE>
 __device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, float nu,
                                           bool& bad) {
-  return make_float4(flux_p<LAM>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
-                     flux_p<LAM>(uf.z, um2.z, um1.z, u0c.z, up1.z, nu, bad), flux_p<LAM>(uf.w, um2.w, um1.w, u0c.w, up1.w, nu, bad));
+  return make_float4(flux_p<LAM, SAFE>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM, SAFE>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
+                     flux_p<LAM, SAFE>(uf.z, um2.z, um1.z, u0c.z, up1.z, nu, bad), flux_p<LAM, SAFE>(uf.w, um2.w, um1.w, u0c.w, up1.w, nu, bad));
 }
 __device__ __forceinline__ float4 avg4(const float4& a, const float4& b) {
   return make_float4((a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f, (a.w + b.w) / 2.f);
@@ -79,21 +83,27 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
 
-template <int LAM>
+template <int LAM, bool SAFE>
 __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__ Grid g, const float* __restrict__ ua, const float* __restrict__ u0,
                                                          float* __restrict__ out, const float* __restrict__ dtp, float nu, int zchunk, int corrector, RedBuf R,
-                                                         int slot, const float* __restrict__ uext, int* __restrict__ flag) {
+                                                         int slot, const float* __restrict__ uext, int* __restrict__ flag, int* __restrict__ redo, int vgx,
+                                                         int vgy) {
+  // redo[0] = number of marked blocks, redo[1…] = their linear indices.  The fast launch runs one block per tile; the SAFE launch
+  // is a small persistent grid that walks the list (normally empty: it exits at once).
+  for (int it = SAFE ? (int)blockIdx.x : 0; it < (SAFE ? redo[0] : 1); it += SAFE ? (int)gridDim.x : 1) {
+  const int blin = SAFE ? redo[1 + it] : (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  const int vbx = SAFE ? blin % vgx : (int)blockIdx.x, vby = SAFE ? (blin / vgx) % vgy : (int)blockIdx.y, vbz = SAFE ? blin / (vgx * vgy) : (int)blockIdx.z;
   extern __shared__ float4 smem4[];
   float* const T = reinterpret_cast<float*>(smem4);      // [C4RING][3][C4H][C4W]
   float* const Fy = T + C4RING * C4PS;                    // [2][3][C4TY+1][32] float4: lower y fluxes of planes z, z+1 (row C4TY: the block's upper edge)
   const int lane = threadIdx.x, ty = threadIdx.y;
   const int tid = lane + 32 * ty;
-  const int xb = 1 + 128 * blockIdx.x, yb = 1 + C4TY * blockIdx.y;
+  const int xb = 1 + 128 * vbx, yb = 1 + C4TY * vby;
   const int x0 = xb + 4 * lane, y = yb + ty;
-  const int z0 = 1 + zchunk * blockIdx.z, z1 = min(z0 + zchunk, g.N[2] - 1);
+  const int z0 = 1 + zchunk * vbz, z1 = min(z0 + zchunk, g.N[2] - 1);
   const bool on = x0 <= g.N[0] - 2 && y <= g.N[1] - 2;
   const float dt = *dtp;
-  bool bad = false;
+  bool bad = false, tiny = false;
 
   // ---- tile fill: every plane is fetched with the same per-thread float4 elements ----
   int gof[C4FILL], sof[C4FILL];  // in-plane global offset / offset inside a component plane of the tile (-1: none)
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
           other = src[g.xo + min(xx, g.N[0] - 2) + (i64)g.px * min(y, g.N[1] - 2)];
         }
         const float* ei = e + lane * C4CS;
-        fex = flux_p<LAM>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu, bad);
+        fex = flux_p<LAM, SAFE>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu, tiny);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
         if (c == 0) uf = make_float4((a0.x + l2.y) / 2.f, (a0.y + a0.x) / 2.f, (a0.z + a0.y) / 2.f, (a0.w + a0.z) / 2.f);
         else if (c == 1) uf = avg4(a0, b1);
         else uf = avg4(a0, m1[0]);
-        const float4 lo = flux_p4<LAM>(uf, make_float4(l2.x, l2.y, a.x, a.y), make_float4(l2.y, a.x, a.y, a.z), a, make_float4(a.y, a.z, a.w, rr), nu, bad);
+        const float4 lo = flux_p4<LAM, SAFE>(uf, make_float4(l2.x, l2.y, a.x, a.y), make_float4(l2.y, a.x, a.y, a.z), a, make_float4(a.y, a.z, a.w, rr), nu, tiny);
         float hi = __shfl_down_sync(FULLMASK, lo.x, 1);
         const float e = __shfl_sync(FULLMASK, fex, c);
         if (lane == 31) hi = e;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       for (int c = 0; c < 3; c++) own[c] = ld4(p0 + c * C4CS);
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++)  // the range test behind div6_chk; catches NaN and Inf too
+    for (int c = 0; c < 3; c++)  // keeps |5c+2d−u| below the upper end of div6_chk's proven range; catches NaN and Inf (a diverged run)
       bad = bad || !(fabsf(own[c].x) <= 1e37f) || !(fabsf(own[c].y) <= 1e37f) || !(fabsf(own[c].z) <= 1e37f) || !(fabsf(own[c].w) <= 1e37f);
     // ---- y fluxes: lower flux of the own row from the previous step, upper flux = next row's lower flux ----
     float4 Fy2lo = f4zero();
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
         if (c == 0) uf = make_float4((w1.x + wl) / 2.f, (w1.y + w1.x) / 2.f, (w1.z + w1.y) / 2.f, (w1.w + w1.z) / 2.f);
         else if (c == 1) uf = avg4(w1, wd);
         else uf = avg4(w1, own[2]);
-        const float4 hi = flux_p4<LAM>(uf, m1[c], own[c], a1, a2, nu, bad);
+        const float4 hi = flux_p4<LAM, SAFE>(uf, m1[c], own[c], a1, a2, nu, tiny);
         if (live) {
           r[c].x += Fz[c].x;
           r[c].y += Fz[c].y;
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
           if (c == 0) uf = make_float4((v1.x + vl) / 2.f, (v1.y + v1.x) / 2.f, (v1.z + v1.y) / 2.f, (v1.w + v1.z) / 2.f);
           else if (c == 1) uf = avg4(v1, vd);
           else uf = avg4(v1, vz);
-          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM>(uf, s2, s1, s0, sp, nu, bad);
+          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM, SAFE>(uf, s2, s1, s0, sp, nu, tiny);
         }
       }
     }
@@ -324,6 +334,21 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
     __syncthreads();
   }
   if (bad) *flag = 1;
-  double v[1] = {(double)gmax}, fin[1];
-  grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+  if (!SAFE) {
+    // a block that met an input outside the fast division's range leaves its results to the SAFE launch (and keeps its Φ maximum out
+    // of this launch's reduction)
+    const int any = __syncthreads_or(tiny ? 1 : 0);
+    if (any && tid == 0) redo[1 + atomicAdd(redo, 1)] = blin;
+    double v[1] = {any ? 0.0 : (double)gmax}, fin[1];
+    grid_reduce<RED_MAX, 1>(v, R, slot, fin);
+  } else {
+    // the maximum of non-negative doubles is the maximum of their bit patterns: merge into the fast launch's result
+    float m = gmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(FULLMASK, m, o));
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(R.out + slot), (unsigned long long)__double_as_longlong((double)m));
+    if (tid == 0) atomicAdd(flag + 1, 1);  // [1] counts the recomputed blocks (diagnostics)
+    __syncthreads();                       // the next listed block reuses the shared-memory ring
+  }
+  }
 }

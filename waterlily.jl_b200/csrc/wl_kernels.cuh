@@ -23,17 +23,19 @@ __device__ __forceinline__ float div6(float x) {
   if (!(ax >= 7.888609052210118e-31f && ax <= 3.0e38f)) q = (ax == 0.f) ? q0 : div6_slow(x);  // ±0 keeps its sign; the rest is never physical
   return q;
 }
-// Branch-free variant for the flux kernel: outside the proven range (never for physical values) it raises *flag instead of taking
-// the slow path; the host turns a raised flag into an error, so a result is either exact or reported.
+// Variant for the flux kernels: the same two-FMA form; the rare inputs outside its proven range (tiny non-zero values such as the
+// 1e-34 far-field velocities of the first steps of a wake, ±0, non-finite) take the IEEE division, so every input is exact.
+// (`flag` is kept in the signature of the callers; it is no longer raised here.)
 __device__ __forceinline__ float div6_flag(float x, int* flag) {
   const float C = 0.16666667163372039794921875f;
   const float q0 = x * C;
   const float r = __fmaf_rn(-6.f, q0, x);
-  const float q = __fmaf_rn(r, C, q0);
+  float q = __fmaf_rn(r, C, q0);
   const float ax = fabsf(x);
   const bool inr = ax >= 7.888609052210118e-31f && ax <= 3.0e38f;
-  if (!inr && ax != 0.f) *flag = 1;
-  return inr ? q : q0;  // ±0 → ±0 (= q0)
+  if (!inr) q = (ax == 0.f) ? q0 : div6_slow(x);
+  (void)flag;
+  return q;
 }
 template <int LAM>
 __device__ __forceinline__ float limiter_f(float u, float c, float d, int* flag) {

@@ -156,7 +156,7 @@ __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, con
   return s;
 }
 
-template <bool WITH_L2>
+template <bool WITH_L2, bool SLAB>
 __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
   extern __shared__ float4 vs_smem4[];
   // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
   };
   // plane t of r (t may lie up to 5 planes outside the level) and the coarse plane under fine plane t
   auto rplane = [&](int t) -> const float* {
-    if (!a.slab) return a.r + g.s[2] * wrap(t, n2);
+    if (!SLAB) return a.r + g.s[2] * wrap(t, n2);
     if (t < 0) return a.rext + g.s[2] * (t + 4);
     if (t > n2 + 1) return a.rext + g.s[2] * (4 + t - n2 - 2);
     return a.r + g.s[2] * t;
   };
   auto cplane = [&](int t) -> const float* {
-    if (!a.slab) return a.xc + gc.s[2] * ((wrap(t, n2) + 1) >> 1);
+    if (!SLAB) return a.xc + gc.s[2] * ((wrap(t, n2) + 1) >> 1);
     if (!a.cslab) return a.xc + gc.s[2] * ((wrap(t + a.zoff, a.n2g) + 1) >> 1);
     const int c = (t + 1) >> 1, nc = n2 >> 1;  // arithmetic shift = floor: planes below the slab map to coarse planes ≤ 0
     if (c < 0) return a.cxext + gc.s[2] * (c + 2);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
   };
   auto loadP = [&](int t) -> PIn {
     PIn p;
-    const int tz = ((t + a.zoff) & 1) ? t - 1 : t + 1;  // the fine z neighbour outside the own coarse cell (zoff and n2 are even)
+    const int tz = ((t + (SLAB ? a.zoff : 0)) & 1) ? t - 1 : t + 1;  // the fine z neighbour outside the own coarse cell (zoff and n2 are even)
     const float* rp = rplane(t) + gin;
     p.f0 = ld4(rp);
     p.f1 = ld4(rp + 4);
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       const int q = t - k;
       const int h = k == 3 ? 3 : 1;  // sweep 2 is valid on planes z0−3 … z1+2, sweep 4 on z0−1 … z1
       if (act && q >= z0 - h && q <= z1 - 1 + h) {
-        const int zr = a.slab ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
-        const bool zsm = zr == 1, zsp = zr == (a.slab ? a.n2g : n2);
+        const int zr = SLAB ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == (SLAB ? a.n2g : n2);
         const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
         const bool anyYZ = stY || zsm || zsp;
         if (te)
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       const int q = t - k;
       const int h = k == 1 ? 4 : 2;  // sweep 1 is valid on planes z0−4 … z1+3, sweep 3 on z0−2 … z1+1
       if (act && q >= z0 - h && q <= z1 - 1 + h) {
-        const int zr = a.slab ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
-        const bool zsm = zr == 1, zsp = zr == (a.slab ? a.n2g : n2);
+        const int zr = SLAB ? wrap(q + a.zoff, a.n2g) : wrap(q, n2);
+        const bool zsm = zr == 1, zsp = zr == (SLAB ? a.n2g : n2);
         const bool te = ((1 + ypar + q) & 1) == 1;
         const bool anyYZ = stY || zsm || zsp;
         if (te)

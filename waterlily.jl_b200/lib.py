@@ -28,6 +28,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def library_path(fmad=False):
+    if os.environ.get("WL_B200_LIB"):  # A/B experiments against another build of the same ABI
+        return os.environ["WL_B200_LIB"]
     return os.path.join(_CSRC, "libwl_b200_fmad.so" if fmad else "libwl_b200.so")
 
 
