@@ -1575,7 +1575,9 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         if (!coop || per_sm < 1) {
           h->small_from = 0;
         } else {
-          h->small_grid = nsm * std::min(per_sm, 2);
+          int want = 2;
+          if (const char* e = getenv("WL_SMALL_PER_SM")) want = std::max(1, atoi(e));
+          h->small_grid = nsm * std::min(per_sm, want);
           void* q = nullptr;
           if (cudaMalloc(&q, 256 * sizeof(SmallOp)) != cudaSuccess) { rc = fail("cudaMalloc ops"); break; }
           h->d_ops = (SmallOp*)q;

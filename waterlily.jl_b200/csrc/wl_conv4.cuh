@@ -182,6 +182,12 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
   for (int z = z0 - 1; z < z1; z++) {
     const bool live = z >= z0;
     if (z + 1 < z1) fill(z + 3);  // into the slot plane z-1 left; read as plane z+2 of the next step
+    float4 ub[3] = {f4zero(), f4zero(), f4zero()};  // corrector: u⁰ of the own cells, requested a whole plane of work ahead of its use
+    if (corrector && live && on) {
+      const i64 o = (i64)g.xo + x0 + g.s[1] * y + g.s[2] * z;
+#pragma unroll
+      for (int c = 0; c < 3; c++) ub[c] = ld4(u0 + o + c * g.sc);
+    }
     const float* p0 = P(z);
     const float* p1 = P(z + 1);
     const float* p2 = P(z + 2);
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       const i64 o = (i64)g.xo + x0 + g.s[1] * y + g.s[2] * z;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        const float4 b = ld4(u0 + o + c * g.sc);
+        const float4 b = corrector ? ub[c] : own[c];  // predictor: ua is u⁰ itself, already in the tile
         float4 f = make_float4(b.x + dt * r[c].x, b.y + dt * r[c].y, b.z + dt * r[c].z, b.w + dt * r[c].w);
         if (corrector) f = make_float4((own[c].x + f.x) * 0.5f, (own[c].y + f.y) * 0.5f, (own[c].z + f.z) * 0.5f, (own[c].w + f.w) * 0.5f);
         st4(out + o + c * g.sc, f);
