@@ -89,6 +89,10 @@ int wl_create_dist(const wl_config* cfg, int rank, int nranks, const void* nccl_
  * (src/Flow.jl:116-124; used by Metrics/JLD2/VTK extensions).  Buffers hold ncomp*ΠN floats in the reference layout. */
 int wl_upload(wl_handle* h, int field, const float* src, int src_is_device);
 int wl_download(wl_handle* h, int field, float* dst, int dst_is_device);
+/* One component of a vector field (ΠN floats): what apply!(f,c) does per component when it fills u from a function initial
+ * condition (src/util.jl `apply!`, called by Flow's constructor src/Flow.jl:140) — lets a host hand over components it holds
+ * separately without assembling them first. */
+int wl_upload_component(wl_handle* h, int field, int comp, const float* src, int src_is_device);
 
 /* After uploading u from a function initial condition: BC!(u,uBC,exitBC,perdir); exitBC!(u,u,0); u⁰=copy(u)
  * (src/Flow.jl:141-142). */

@@ -86,14 +86,15 @@ class Flow:
         else:
             _lib.check(self.L, self.L.wl_create(C.byref(cfg), C.byref(self.h)))
         if u0 is not None:
-            arr = np.empty((D,) + tuple(reversed(self.N)), F)
-            if callable(u0):
-                for i in range(D):
-                    arr[i] = np.asarray(u0(i, loc_grid(self.N, i, self.zoff)), F)
-            else:
-                for i in range(D):
-                    arr[i] = F(u0[i])
-            self.upload("u", arr)
+            # apply!(u0, a.u) (src/Flow.jl:140): component by component, so that an array the caller already holds goes to the
+            # device without being assembled into one more host copy
+            shp = tuple(reversed(self.N))
+            for i in range(D):
+                a = u0(i, loc_grid(self.N, i, self.zoff)) if callable(u0) else u0[i]
+                a = np.asarray(a, F)
+                if a.shape != shp:
+                    a = np.broadcast_to(a, shp)
+                self.upload_component("u", i, a)
             _lib.check(self.L, self.L.wl_apply_bc(self.h))
 
     def close(self):
@@ -117,6 +118,13 @@ class Flow:
         out = np.empty(self._shape(name), F)
         _lib.check(self.L, self.L.wl_download(self.h, _FIELDS[name], out.ctypes.data_as(C.c_void_p), 0))
         return out
+
+    def upload_component(self, name, comp, arr):
+        a = np.ascontiguousarray(arr, F)
+        sp = tuple(reversed(self.N))
+        if a.shape != sp:
+            raise ValueError(f"{name}[{comp}]: expected shape {sp}, got {a.shape}")
+        _lib.check(self.L, self.L.wl_upload_component(self.h, _FIELDS[name], int(comp), a.ctypes.data_as(C.c_void_p), 0))
 
     def upload(self, name, arr):
         a = np.ascontiguousarray(arr, F)

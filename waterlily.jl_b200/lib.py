@@ -24,7 +24,7 @@ class Config(C.Structure):
 # makes it bit-identical to the CPU oracle (compiled with -ffp-contract=off) over whole simulations — see
 # DESIGN.md §numerics.  The kernels are HBM-bound, so giving up FMA contraction costs no measurable time.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC,-pthread", "-shared"]
 
 
 def library_path(fmad=False):
@@ -69,6 +69,7 @@ def load_library(fmad=False):
         "wl_destroy": [H],
         "wl_upload": [H, C.c_int, C.c_void_p, C.c_int],
         "wl_download": [H, C.c_int, C.c_void_p, C.c_int],
+        "wl_upload_component": [H, C.c_int, C.c_int, C.c_void_p, C.c_int],
         "wl_apply_bc": [H],
         "wl_update": [H],
         "wl_measure_bc": [H],
