@@ -33,6 +33,9 @@ WORKLOADS = {
     "tgv64": dict(kind="tgv", n=64),
     "sphere": dict(kind="sphere", dims=(512, 256, 256)),  # configs[2]
     "sphere128": dict(kind="sphere", dims=(128, 64, 64)),
+    "donut": dict(kind="donut", dims=(1024, 512, 512)),   # configs[3]: torus, axis along x, 8 GPUs
+    "donut256": dict(kind="donut", dims=(256, 128, 128)),
+    "tgv1024": dict(kind="tgv", n=1024),                  # configs[4]: strong-scaling sweep
 }
 
 # Algorithmic 4-byte words per launch and ghost-padded cell of the level the launch runs on, every field read once / written once
@@ -104,6 +107,10 @@ def make_case(name):
         return dict(dims=(n, n, n), uBC=(0.0, 0.0, 0.0), L=float(n), nu=nu, perdir=(1, 2, 3), exitBC=False, body=None, u0=("tgv", n))
     d = w["dims"]
     m = d[1]
+    if w["kind"] == "donut":  # centre (m/2,m/2,m/2), major radius m/4, minor m/16, L=R, ν=R/1000
+        R = m / 4
+        c = m / 2
+        return dict(dims=d, uBC=(1.0, 0.0, 0.0), L=R, nu=R / 1000, perdir=(), exitBC=True, body=("torus", (c, c, c), R, m / 16), u0=None)
     R = m / 8
     c = m / 2 - 1
     return dict(dims=d, uBC=(1.0, 0.0, 0.0), L=2 * R, nu=2 * R / 3700, perdir=(), exitBC=True, body=((c, c, c), R), u0=None)
@@ -111,7 +118,9 @@ def make_case(name):
 
 def build_sim(case, u0_host=None, dist=None, device=0):
     import wl_b200 as wl
-    body = wl.Sphere(*case["body"]) if case["body"] else None
+    body = None
+    if case["body"]:
+        body = wl.Torus(*case["body"][1:]) if case["body"][0] == "torus" else wl.Sphere(*case["body"])
     u0 = None
     if u0_host is not None:
         def u0(i, x):
@@ -178,7 +187,7 @@ def oracle_run(case, steps, warmup):
 
 def cpu_sample_for(name):
     """Bounded CPU sample of the same workload family (per-cell metric): TGV → 128³, sphere → 128×64×64."""
-    return "tgv128" if WORKLOADS[name]["kind"] == "tgv" else "sphere128"
+    return "tgv128" if WORKLOADS[name]["kind"] == "tgv" else "sphere128"  # (the donut is timed on the sphere sample: same kernels)
 
 
 def run_reference(args):
