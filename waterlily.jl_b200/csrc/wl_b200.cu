@@ -719,7 +719,8 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
 }
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
 // With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; *fused tells whether it was.
-static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fused_out) {
+// `skip_r_exch`: the caller follows up with vsmooth on this level, which pushes r's ghost plane together with its deeper halo
+static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fused_out, bool skip_r_exch = false) {
   ProfLevel pl(h, l);
   dim3 b = blk(h->D);
   Box in = l.inside();
@@ -740,7 +741,7 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
   }
   std::swap(l.r, l.r2);
-  TRY(exch(h, l, l.r, 1));
+  if (!skip_r_exch) TRY(exch(h, l, l.r, 1));
   if (fused && h->dist.on()) {
     if (l.slab && !coarse->slab)
       TRY(allgather_planes(h, *coarse, coarse->r, (l.g.N[2] - 2) / 2));
@@ -871,15 +872,17 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   if (f.slab) {
     // planes −4 … −1 and n2+2 … n2+5 of r (the ghost planes 0 and n2+1 are current since Jacobi!'s exchange), and, when the coarse
     // level is a slab too, its planes −2, −1 and nc+2, nc+3 of x: pushed straight into the neighbours' rext / xext
-    PlaneMove mv[8];
+    PlaneMove mv[10];
     int m = 0;
     const i64 s2 = f.g.s[2];
+    mv[m++] = {f.r + s2 * n2, 1, f.r};                  // the ghost planes themselves (Jacobi! left them to this push)
+    mv[m++] = {f.r + s2 * 1, 0, f.r + s2 * (n2 + 1)};
     for (int k = 0; k < 4; k++) {
       mv[m++] = {f.r + s2 * (n2 - 4 + k), 1, f.rext + s2 * k};
       mv[m++] = {f.r + s2 * (2 + k), 0, f.rext + s2 * (4 + k)};
     }
     TRY(p2p_push(h, f.g, mv, m));
-    if (c.slab) {
+    if (c.slab && !vs_fusable(h, li + 1)) {  // (a coarse level that ran vsmooth itself has pushed its xext planes already)
       const i64 c2 = c.g.s[2];
       const int nc = c.g.N[2] - 2;
       m = 0;
@@ -907,7 +910,22 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   h->launches++;
   std::swap(f.r, f.r2);
   CK(cudaGetLastError());
-  TRY(exch2(h, f, f.r, f.x));
+  if (f.slab && li > 0) {
+    // ghost planes of r and x, and for the finer level's vsmooth the two planes of x beyond them, in one push
+    PlaneMove mv[8];
+    int m = 0;
+    const i64 s2 = f.g.s[2];
+    mv[m++] = {f.r + s2 * n2, 1, f.r};
+    mv[m++] = {f.r + s2 * 1, 0, f.r + s2 * (n2 + 1)};
+    mv[m++] = {f.x + s2 * n2, 1, f.x};
+    mv[m++] = {f.x + s2 * 1, 0, f.x + s2 * (n2 + 1)};
+    for (int k = 0; k < 2; k++) {
+      mv[m++] = {f.x + s2 * (n2 - 2 + k), 1, f.xext + s2 * k};
+      mv[m++] = {f.x + s2 * (2 + k), 0, f.xext + s2 * (2 + k)};
+    }
+    TRY(p2p_push(h, f.g, mv, m));
+  } else
+    TRY(exch2(h, f, f.r, f.x));
   if (with_l2) TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
   return 0;
 }
@@ -1024,7 +1042,7 @@ static int vcycle(wl_handle* h, size_t li, const float* wp, bool defer_up = fals
   dim3 b = blk(h->D);
   Box cin = coarse.inside();
   bool fused = false;
-  TRY(jacobi(h, fine, li > 0, &coarse, &fused));
+  TRY(jacobi(h, fine, li > 0, &coarse, &fused, defer_up && fine.slab));
   if (!fused) {
     if (fine.slab) return fail("z-slab levels need the fused restriction (even sizes, full coarsening)");
     LAUNCH_D(h, k_restrict, grd(cin, b), b, coarse.g, fine.g, cin, coarse.r, (const float*)fine.r, coarse.c[0], coarse.c[1], coarse.c[2]);
