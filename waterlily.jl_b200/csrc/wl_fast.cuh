@@ -20,6 +20,9 @@
 
 #define FTY 8
 #define MARCH_MINB 6  // ≤40 registers ⇒ 6 blocks (48 warps) per SM: measured +10% on every march kernel over the compiler's default
+#ifndef DIVRES_MINB
+#define DIVRES_MINB 4  // f_div_residual carries two double accumulators and three velocity stencils: 40 registers spill
+#endif
 #define FULLMASK 0xffffffffu
 
 struct Coef {
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef
 // σ (=z) is not stored in UNI mode (it is pure scratch there; CFL rewrites the interior every step).
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
+__global__ void __launch_bounds__(32 * FTY, DIVRES_MINB) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
                                                            float* __restrict__ r, float* __restrict__ zarr, const float* __restrict__ dtp, float wdt,
                                                            int zchunk, RedBuf R, int slot) {
   const Frame f = make_frame(g, zchunk);
