@@ -176,6 +176,13 @@ struct wl_handle {
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
+  // mom_project! on one GPU in uniform mode: the level-1 f_vsmooth also forms the corrected velocity (into f) and p with the x it
+  // has just computed, so the projection ends with the solver (spec_w = the projection's w while it runs; spec_done = the last
+  // smoother call of the solve did it)
+  // Measured at 512³: the level-1 f_vsmooth goes from 1.58 to 3.2 ms (it is latency-bound with 14 warps per SM; the velocity
+  // loads of the extra stage are exposed) against 0.79 ms for the f_correct launch it replaces — OFF by default, WL_SPEC_CORRECT=1 enables.
+  bool spec_on = false, spec_done = false, spec_allowed = false;
+  float spec_w = 0.f;
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
   int conv4_zchunk = 32;
@@ -826,10 +833,11 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   ProfLevel pl(h, f);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(f_vsmooth<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    cudaFuncSetAttribute(f_vsmooth<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
     attr = true;
   }
   const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
@@ -895,19 +903,33 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   }
   dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
+  const bool corr = h->spec_on && li == 0 && with_l2 && !f.slab;
+  a.xo = f.x;
+  a.u = h->u;
+  a.uo = h->f;
+  a.p = h->p;
+  a.dtp = dtp(h);
+  a.wdt = h->spec_w;
+  if (corr) a.xo = f.eps;  // ϵ is not used on a level that runs f_vsmooth: x goes there and the two swap roles
   if (f.slab) {
     if (with_l2)
-      f_vsmooth<true, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+      f_vsmooth<true, true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
     else
-      f_vsmooth<false, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+      f_vsmooth<false, true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  } else if (corr) {
+    f_vsmooth<true, false, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
   } else {
     if (with_l2)
-      f_vsmooth<true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+      f_vsmooth<true, false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
     else
-      f_vsmooth<false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+      f_vsmooth<false, false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
   }
   prof_end(h);
   h->launches++;
+  if (corr) {
+    std::swap(f.x, f.eps);
+    h->spec_done = true;
+  }
   std::swap(f.r, f.r2);
   CK(cudaGetLastError());
   if (f.slab && li > 0) {
@@ -1312,11 +1334,18 @@ static void cfl(wl_handle* h, float* dt_out) {
 static int project(wl_handle* h, float w) {
   float r2;
   TRY(residual(h, 1, w, &r2));
-  TRY(solve_after_residual(h, r2, nullptr));
+  h->spec_on = lazy_bc(h) && !h->dist.on() && h->spec_allowed;
+  h->spec_done = false;
+  h->spec_w = w;
+  const int rc = solve_after_residual(h, r2, nullptr);
+  h->spec_on = false;
+  if (rc) return rc;
   Level& l = h->levels[0];
   dim3 b = blk(h->D);
   Box in = l.inside();
-  if (l.fast) {
+  if (h->spec_done) {
+    std::swap(h->u, h->f);  // the last f_vsmooth of the solve wrote the corrected velocity there, and p
+  } else if (l.fast) {
     if (h->uni)
       LAUNCH(h, f_correct<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, h->u, h->p, dtp(h), w, l.zchunk());
     else
@@ -1568,6 +1597,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
+  if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
   if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);
   if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));

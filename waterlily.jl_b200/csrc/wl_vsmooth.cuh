@@ -60,6 +60,16 @@ struct VsArgs {
   int slab, cslab, zoff, n2g;
   const float* rext;
   const float* cxext;
+  // CORR (level 1 on one GPU, inside mom_project!): the increment also applies the velocity correction and the pressure unscale
+  // of mom_project! (src/Flow.jl:227-230) with the x it has just formed — u_d −= L_d·(x − x[I−δ_d]) → uo, p = x/dt — so that the
+  // projection needs no further pass when this V-cycle turns out to be the last one.  x is then written out of place (xo): the
+  // x² of the neighbouring cells is re-evaluated from their old x.
+  float* xo;
+  const float* u;
+  float* uo;
+  float* p;
+  const float* dtp;
+  float wdt;
 };
 
 __device__ __forceinline__ float4 mul4s(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -156,7 +166,7 @@ __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, con
   return s;
 }
 
-template <bool WITH_L2, bool SLAB>
+template <bool WITH_L2, bool SLAB, bool CORR>
 __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
   extern __shared__ float4 vs_smem4[];
   // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
@@ -198,6 +208,7 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
   const int dcl = ((wrap(xs - 1, n0) + 1) >> 1) - cx, dcr = ((wrap(xs + 8, n0) + 1) >> 1) - cx;
   const float w = *a.wp;
   const float iD = a.iD;
+  const float cdt = CORR ? a.wdt * (*a.dtp) : 1.f;
   double l2 = 0.0;
 
   // global loads are issued one step ahead of their use (the block's warps run in lockstep between barriers, nothing else
@@ -244,6 +255,11 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
       xi0 = ld4(a.x + o);
       xi1 = ld4(a.x + o + 4);
       xiC = ld4(cplane(q) + cinx + gc.px * cy);
+      if (CORR) {  // the velocity the increment of the next step corrects: bring its lines into L2 (no registers to hold them a step)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + g.sc + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + 2 * g.sc + o));
+      }
     }
   };
 
@@ -328,9 +344,9 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
         const float* Rq = sb + lr[7];
         const float4 ce = ld4(Eq), co = ld4(Eq + VS_AF);
         const float sl = Eq[VS_AF - 1], sr_ = Eq[4];
-        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, ld4(Eq - oY), ld4(Eq + oY), ld4(Eqm), ld4(Eqp), a);
-        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ld4(Eq + VS_AF - oY), ld4(Eq + VS_AF + oY), ld4(Eqm + VS_AF),
-                                  ld4(Eqp + VS_AF), a);
+        const float4 yme = ld4(Eq - oY), ymo = ld4(Eq + VS_AF - oY), zme = ld4(Eqm), zmo = ld4(Eqm + VS_AF);
+        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, yme, ld4(Eq + oY), zme, ld4(Eqp), a);
+        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ymo, ld4(Eq + VS_AF + oY), zmo, ld4(Eqp + VS_AF), a);
         const float4 re = ld4(Rq), ro = ld4(Rq + VS_AF);
         const float4 ne = make_float4(re.x - w * Ae.x, re.y - w * Ae.y, re.z - w * Ae.z, re.w - w * Ae.w);
         const float4 no = make_float4(ro.x - w * Ao.x, ro.y - w * Ao.y, ro.z - w * Ao.z, ro.w - w * Ao.w);
@@ -347,8 +363,64 @@ __global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ Vs
         x1.y = (x1.y + w * C.z) + w * co.z;
         x1.z = (x1.z + w * C.w) + w * ce.w;
         x1.w = (x1.w + w * C.w) + w * co.w;
-        st4(a.x + o, x0);
-        st4(a.x + o + 4, x1);
+        float* const xout = CORR ? a.xo : a.x;
+        st4(xout + o, x0);
+        st4(xout + o + 4, x1);
+        if (CORR) {
+          // x² at the row below, the plane below and the cell to the left: the expression their owners evaluate, on the old x
+          const int ymr = wrap(yr - 1, n1), qm = wrap(q - 1, n2);
+          const int ginm = g.xo + xs + g.px * ymr;
+          const float* xq = a.x + g.s[2] * q;
+          float4 m0 = ld4(xq + ginm), m1 = ld4(xq + ginm + 4);
+          float4 z0 = ld4(a.x + g.s[2] * qm + gin), z1_ = ld4(a.x + g.s[2] * qm + gin + 4);
+          float xl = xq[g.xo + wrap(xs - 1, n0) + g.px * yr];
+          const float* cq = cplane(q) + cinx;
+          const float4 Cm = ld4(cq + gc.px * ((ymr + 1) >> 1));
+          const float4 Cz = ld4(cplane(q - 1) + cinx + gc.px * cy);
+          const float cl = cq[gc.px * cy + dcl];
+          const float4 u00 = ld4(a.u + o), u01 = ld4(a.u + o + 4);
+          const float4 u10 = ld4(a.u + g.sc + o), u11 = ld4(a.u + g.sc + o + 4);
+          const float4 u20 = ld4(a.u + 2 * g.sc + o), u21 = ld4(a.u + 2 * g.sc + o + 4);
+          xl = (xl + w * cl) + w * sl;
+          m0.x = (m0.x + w * Cm.x) + w * yme.x;
+          m0.y = (m0.y + w * Cm.x) + w * ymo.x;
+          m0.z = (m0.z + w * Cm.y) + w * yme.y;
+          m0.w = (m0.w + w * Cm.y) + w * ymo.y;
+          m1.x = (m1.x + w * Cm.z) + w * yme.z;
+          m1.y = (m1.y + w * Cm.z) + w * ymo.z;
+          m1.z = (m1.z + w * Cm.w) + w * yme.w;
+          m1.w = (m1.w + w * Cm.w) + w * ymo.w;
+          z0.x = (z0.x + w * Cz.x) + w * zme.x;
+          z0.y = (z0.y + w * Cz.x) + w * zmo.x;
+          z0.z = (z0.z + w * Cz.y) + w * zme.y;
+          z0.w = (z0.w + w * Cz.y) + w * zmo.y;
+          z1_.x = (z1_.x + w * Cz.z) + w * zme.z;
+          z1_.y = (z1_.y + w * Cz.z) + w * zmo.z;
+          z1_.z = (z1_.z + w * Cz.w) + w * zme.w;
+          z1_.w = (z1_.w + w * Cz.w) + w * zmo.w;
+          const float L0 = a.L0, L1 = a.L1, L2 = a.L2;
+          float4 v0, v1;  // u_x −= L·(x − x[I−δ_x])
+          v0.x = u00.x - L0 * (x0.x - xl);
+          v0.y = u00.y - L0 * (x0.y - x0.x);
+          v0.z = u00.z - L0 * (x0.z - x0.y);
+          v0.w = u00.w - L0 * (x0.w - x0.z);
+          v1.x = u01.x - L0 * (x1.x - x0.w);
+          v1.y = u01.y - L0 * (x1.y - x1.x);
+          v1.z = u01.z - L0 * (x1.z - x1.y);
+          v1.w = u01.w - L0 * (x1.w - x1.z);
+          st4(a.uo + o, v0);
+          st4(a.uo + o + 4, v1);
+          v0 = make_float4(u10.x - L1 * (x0.x - m0.x), u10.y - L1 * (x0.y - m0.y), u10.z - L1 * (x0.z - m0.z), u10.w - L1 * (x0.w - m0.w));
+          v1 = make_float4(u11.x - L1 * (x1.x - m1.x), u11.y - L1 * (x1.y - m1.y), u11.z - L1 * (x1.z - m1.z), u11.w - L1 * (x1.w - m1.w));
+          st4(a.uo + g.sc + o, v0);
+          st4(a.uo + g.sc + o + 4, v1);
+          v0 = make_float4(u20.x - L2 * (x0.x - z0.x), u20.y - L2 * (x0.y - z0.y), u20.z - L2 * (x0.z - z0.z), u20.w - L2 * (x0.w - z0.w));
+          v1 = make_float4(u21.x - L2 * (x1.x - z1_.x), u21.y - L2 * (x1.y - z1_.y), u21.z - L2 * (x1.z - z1_.z), u21.w - L2 * (x1.w - z1_.w));
+          st4(a.uo + 2 * g.sc + o, v0);
+          st4(a.uo + 2 * g.sc + o + 4, v1);
+          st4(a.p + o, make_float4(x0.x / cdt, x0.y / cdt, x0.z / cdt, x0.w / cdt));
+          st4(a.p + o + 4, make_float4(x1.x / cdt, x1.y / cdt, x1.z / cdt, x1.w / cdt));
+        }
         if (WITH_L2) {
           l2 += (double)ne.x * ne.x + (double)no.x * no.x + (double)ne.y * ne.y + (double)no.y * no.y;
           l2 += (double)ne.z * ne.z + (double)no.z * no.z + (double)ne.w * ne.w + (double)no.w * no.w;
