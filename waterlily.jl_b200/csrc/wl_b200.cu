@@ -848,7 +848,7 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   int best = 1;
   long bestcost = -1;
   for (int nz = 1; nz <= std::max(1, n2 / 16); nz++) {
-    const long cost = (long)cdiv(tiles * nz, nsm) * (cdiv(n2, nz) + 12);
+    const long cost = (long)cdiv(tiles * nz, nsm * VS_BPS) * (cdiv(n2, nz) + 12);
     if (bestcost < 0 || cost < bestcost) {
       bestcost = cost;
       best = nz;

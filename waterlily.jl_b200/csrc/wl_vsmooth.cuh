@@ -31,7 +31,12 @@
 
 #define VS_NGX 8                       // groups of 8 cells per tile row: 6 core groups + one halo group on each side (8 float4 = one quarter-warp: row breaks cause no bank conflicts)
 #define VS_CX ((VS_NGX - 2) * 8)       // core width  (48)
+#ifndef VS_CY
 #define VS_CY 42                       // core height
+#endif
+#ifndef VS_BPS
+#define VS_BPS 1                       // blocks per SM the shared-memory footprint allows
+#endif
 #define VS_HALO 5
 #define VS_TH (VS_CY + 2 * VS_HALO)    // tile rows (52)
 #define VS_DE 9                        // ring depth of ϵ   (planes t … t−8)
@@ -167,7 +172,7 @@ __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, con
 }
 
 template <bool WITH_L2, bool SLAB, bool CORR>
-__global__ void __launch_bounds__(VS_NT, 1) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
+__global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
   extern __shared__ float4 vs_smem4[];
   // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
   float* const ER = reinterpret_cast<float*>(vs_smem4) + VS_PAD;
