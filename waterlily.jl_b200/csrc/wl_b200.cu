@@ -397,14 +397,20 @@ static int exch2(wl_handle* h, const Level& l, float* a0, float* a1) {
   return 0;
 }
 // Velocity halo: two planes per side (QUICK reads I-2δ … I+δ, src/Flow.jl:8); the second plane lands in h->uext.
-static int exch_u(wl_handle* h, float* u) {
+// `p`: the pressure's ghost planes ride along (after a projection)
+static int exch_u(wl_handle* h, float* u, float* p = nullptr) {
   if (!h->dist.on()) return 0;
   const Grid& g = h->g;
   const size_t cnt = (size_t)g.s[2];
   const Dist& d = h->dist;
+  if (p && !h->p2p) TRY(exch(h, h->levels[0], p, 1));
   if (h->p2p) {
-    PlaneMove mv[12];
+    PlaneMove mv[14];
     int n = 0;
+    if (p) {
+      mv[n++] = {p + g.s[2] * (g.N[2] - 2), 1, p};
+      mv[n++] = {p + g.s[2] * 1, 0, p + g.s[2] * (g.N[2] - 1)};
+    }
     for (int c = 0; c < 3; c++) {
       float* b = u + (size_t)c * g.sc;
       float* elo = h->uext + (size_t)c * g.s[2];
@@ -444,10 +450,10 @@ static int exch_u(wl_handle* h, float* u) {
   return 0;
 }
 // In-place all-reduce of one reduction slot (double) across the ranks, on the compute stream.
-static int allreduce_slot(wl_handle* h, int slot, int op) {
+static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `count` adjacent slots in one call
   if (!h->dist.on()) return 0;
   prof_begin(h, "allreduce");
-  NCK(g_nccl.AllReduce(h->red.out + slot, h->red.out + slot, 1, WL_NCCL_DOUBLE, op, h->dist.comm, h->st));
+  NCK(g_nccl.AllReduce(h->red.out + slot, h->red.out + slot, count, WL_NCCL_DOUBLE, op, h->dist.comm, h->st));
   prof_end(h);
   return 0;
 }
@@ -1126,8 +1132,7 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
     else
       LAUNCH(h, f_div_residual<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
              l.zchunk(), h->red, SLOT_RSUM);
-    TRY(allreduce_slot(h, SLOT_RSUM, WL_NCCL_SUM));
-    TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
+    TRY(allreduce_slot(h, SLOT_RSUM, WL_NCCL_SUM, 2));  // Σr and Σr² (adjacent slots)
     // residual! subtracts the mean only when |s| > 2eps (src/Poisson.jl:96); otherwise r is final and the Σr² of the same pass is L₂
     static_assert(SLOT_R2 == SLOT_RSUM + 1, "f_div_residual reduces Σr and Σr² into adjacent slots");
     CK(cudaMemcpyAsync(h->h_out + SLOT_RSUM, h->red.out + SLOT_RSUM, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -1319,8 +1324,13 @@ static void cfl(wl_handle* h, float* dt_out) {
       LAUNCH(h, f_cfl<false>, l.fgrid(), dim3(32, FTY), g, (const float*)h->u, h->sigma, h->cfg.nu, dt_out, l.zchunk(), h->red, SLOT_CFLINT, sg, fin);
     }
     if (h->dist.on()) {
-      allreduce_slot(h, SLOT_CFLINT, WL_NCCL_MAX);
-      allreduce_slot(h, sg, WL_NCCL_MAX);
+      static_assert(SLOT_CFLINT == SLOT_PHIMAX + 1, "the two CFL maxima of uniform mode are reduced together");
+      if (sg == SLOT_PHIMAX)
+        allreduce_slot(h, SLOT_PHIMAX, WL_NCCL_MAX, 2);
+      else {
+        allreduce_slot(h, SLOT_CFLINT, WL_NCCL_MAX);
+        allreduce_slot(h, sg, WL_NCCL_MAX);
+      }
       LAUNCH(h, k_cfl_final, 1, 1, h->red, SLOT_CFLINT, sg, h->cfg.nu, dt_out);
     }
     return;
@@ -1353,8 +1363,7 @@ static int project(wl_handle* h, float w) {
   } else
     LAUNCH_D(h, k_correct, grd(in, b), b, l.dev(), in, h->u, h->p, dtp(h), w);
   step_bc(h, h->u);
-  TRY(exch_u(h, h->u));
-  TRY(exch(h, l, h->p, 1));
+  TRY(exch_u(h, h->u, h->p));
   return 0;
 }
 
