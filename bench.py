@@ -62,6 +62,7 @@ ALG_WORDS = {
     "k_increment": (9, 9),
     "k_prolong_inc": (8.125, 8.125),
     "f_correct": (11, 8),          # read x u3 [L3]; write u3 p
+    "f_correct_cfl": (8, 8),       # uniform mode: the same out of place; the corrector launch also forms CFL's flux_out (no extra bytes)
     "k_correct": (11, 11),
     "f_cfl": (4, 3),               # read u3 [write σ]
     "k_cfl": (4, 4),

@@ -183,6 +183,7 @@ struct wl_handle {
   // loads of the extra stage are exposed) against 0.79 ms for the f_correct launch it replaces — OFF by default, WL_SPEC_CORRECT=1 enables.
   bool spec_on = false, spec_done = false, spec_allowed = false;
   float spec_w = 0.f;
+  bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
   int conv4_zchunk = 32;
@@ -1341,7 +1342,9 @@ static void cfl(wl_handle* h, float* dt_out) {
 }
 
 // mom_project!(a,b,w,t)  src/Flow.jl:223-232
-static int project(wl_handle* h, float w) {
+// `dt_cfl`: (corrector) the caller wants push!(Δt, CFL(a)) right after this projection: in uniform mode the correction kernel
+// computes it on the way (f_correct_cfl) and *cfl_done is set
+static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_done = nullptr) {
   float r2;
   TRY(residual(h, 1, w, &r2));
   h->spec_on = lazy_bc(h) && !h->dist.on() && h->spec_allowed;
@@ -1355,6 +1358,20 @@ static int project(wl_handle* h, float w) {
   Box in = l.inside();
   if (h->spec_done) {
     std::swap(h->u, h->f);  // the last f_vsmooth of the solve wrote the corrected velocity there, and p
+  } else if (l.fast && h->uni && dt_cfl && lazy_bc(h) && h->fuse_cfl) {
+    const int fin = h->dist.on() ? 0 : 1;
+    LAUNCH(h, f_correct_cfl<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
+           h->cfg.nu, dt_cfl, h->red, SLOT_CFLINT, SLOT_PHIMAX, fin);
+    std::swap(h->u, h->f);
+    if (h->dist.on()) {
+      allreduce_slot(h, SLOT_PHIMAX, WL_NCCL_MAX, 2);
+      LAUNCH(h, k_cfl_final, 1, 1, h->red, SLOT_CFLINT, SLOT_PHIMAX, h->cfg.nu, dt_cfl);
+    }
+    if (cfl_done) *cfl_done = true;
+  } else if (l.fast && h->uni && lazy_bc(h) && h->fuse_cfl) {  // out of place into f (free in uniform mode), then the two swap roles
+    LAUNCH(h, f_correct_cfl<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
+           h->cfg.nu, (float*)nullptr, h->red, SLOT_CFLINT, SLOT_PHIMAX, 0);
+    std::swap(h->u, h->f);
   } else if (l.fast) {
     if (h->uni)
       LAUNCH(h, f_correct<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, h->u, h->p, dtp(h), w, l.zchunk());
@@ -1427,9 +1444,10 @@ static int mom_step(wl_handle* h) {
   momentum(h, 1);
   step_bc(h, h->u);
   TRY(exch_u(h, h->u));
-  TRY(project(h, 0.5f));
+  bool cfl_done = false;
+  TRY(project(h, 0.5f, h->d_dthist + h->dt_dev_len, &cfl_done));
   // push!(a.Δt, CFL(a))
-  cfl(h, h->d_dthist + h->dt_dev_len);
+  if (!cfl_done) cfl(h, h->d_dthist + h->dt_dev_len);
   h->dt_dev_len++;
   CK(cudaGetLastError());
   return 0;
@@ -1606,6 +1624,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
+  if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
   if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
   if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);

@@ -508,6 +508,111 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_correct(Grid g, Coef c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// f_correct_cfl (uniform mode): the corrector's velocity correction + pressure unscale (f_correct) fused with CFL's flux_out on the
+// corrected field (f_cfl; src/Flow.jl:234-244): flux_out(I) needs the corrected u_d at I+δ_d, which this thread forms itself from the
+// raw neighbours (u is corrected OUT OF PLACE, u_in → u_out, so raw values stay readable while other blocks work).  Same
+// operations in the same order as the two kernels ⇒ same bits; one pass over u instead of two.
+// ------------------------------------------------------------------------------------------------
+template <bool CFLQ>
+__global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ x,
+                                                            const float* __restrict__ ui, float* __restrict__ uo, float* __restrict__ p,
+                                                            const float* __restrict__ dtp, float wdt, int zchunk, float nu, float* __restrict__ dt_out,
+                                                            RedBuf R, int slot, int slot_ghost, int finalize) {
+  const Frame f = make_frame(g, zchunk);
+  const float dt = wdt * (*dtp);
+  const float L0 = c.Lc[0], L1 = c.Lc[1], L2 = c.Lc[2];
+  double m = 0.0;
+  float4 zm = f4zero(), xc = f4zero(), uz = f4zero();
+  if (f.on) {
+    zm = ld4(x + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0);
+    xc = ld4(x + f.row + g.s[2] * f.z0 + f.x0);
+    uz = ld4(ui + 2 * g.sc + f.row + g.s[2] * f.z0 + f.x0);
+  }
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 pz = g.s[2] * z;
+    const i64 o = f.row + pz + f.x0;
+    const i64 ozp = f.row + g.s[2] * zwrap_hi(g, z) + f.x0;
+    float4 ym = f4zero(), yp = f4zero(), xzp = f4zero(), ux = f4zero(), uy = f4zero(), uyp = f4zero(), uzp = f4zero();
+    float el = 0.f, xr = 0.f, uxr = 0.f;
+    if (f.on) {
+      ym = ld4(x + f.rowm + pz + f.x0);
+      if (CFLQ) yp = ld4(x + f.rowp + pz + f.x0);
+      xzp = ld4(x + ozp);
+      ux = ld4(ui + o);
+      uy = ld4(ui + g.sc + o);
+      if (CFLQ) uyp = ld4(ui + g.sc + f.rowp + pz + f.x0);
+      uzp = ld4(ui + 2 * g.sc + ozp);
+      if (f.lane == 0) el = x[f.row + pz + f.xl];
+      if (CFLQ && (f.lane == 31 || f.lastgrp)) {
+        xr = x[f.row + pz + f.xr];
+        uxr = ui[f.row + pz + f.xr];
+      }
+    }
+    float left = __shfl_up_sync(FULLMASK, xc.w, 1);
+    if (f.lane == 0) left = el;
+    // corrected velocity on the own cells (f_correct)
+    float4 a = ux, b = uy, d = uz;
+    a.x -= L0 * (xc.x - left);
+    a.y -= L0 * (xc.y - xc.x);
+    a.z -= L0 * (xc.z - xc.y);
+    a.w -= L0 * (xc.w - xc.z);
+    b.x -= L1 * (xc.x - ym.x);
+    b.y -= L1 * (xc.y - ym.y);
+    b.z -= L1 * (xc.z - ym.z);
+    b.w -= L1 * (xc.w - ym.w);
+    d.x -= L2 * (xc.x - zm.x);
+    d.y -= L2 * (xc.y - zm.y);
+    d.z -= L2 * (xc.z - zm.z);
+    d.w -= L2 * (xc.w - zm.w);
+    // corrected velocity one cell up in x, y, z (what the owner of that cell computes)
+    float ar = __shfl_down_sync(FULLMASK, a.x, 1);
+    if (f.lane == 31 || f.lastgrp) ar = uxr - L0 * (xr - xc.w);
+    float4 bu = uyp, du = uzp;
+    bu.x -= L1 * (yp.x - xc.x);
+    bu.y -= L1 * (yp.y - xc.y);
+    bu.z -= L1 * (yp.z - xc.z);
+    bu.w -= L1 * (yp.w - xc.w);
+    du.x -= L2 * (xzp.x - xc.x);
+    du.y -= L2 * (xzp.y - xc.y);
+    du.z -= L2 * (xzp.z - xc.z);
+    du.w -= L2 * (xzp.w - xc.w);
+    if (f.on) {
+      st4(uo + o, a);
+      st4(uo + g.sc + o, b);
+      st4(uo + 2 * g.sc + o, d);
+      st4(p + o, make_float4(xc.x / dt, xc.y / dt, xc.z / dt, xc.w / dt));
+      float4 s = f4zero();  // flux_out (f_cfl)
+      if (CFLQ) {
+      s.x = 0.f + (fmaxf(0.f, a.y) + fmaxf(0.f, -a.x));
+      s.x += fmaxf(0.f, bu.x) + fmaxf(0.f, -b.x);
+      s.x += fmaxf(0.f, du.x) + fmaxf(0.f, -d.x);
+      s.y = 0.f + (fmaxf(0.f, a.z) + fmaxf(0.f, -a.y));
+      s.y += fmaxf(0.f, bu.y) + fmaxf(0.f, -b.y);
+      s.y += fmaxf(0.f, du.y) + fmaxf(0.f, -d.y);
+      s.z = 0.f + (fmaxf(0.f, a.w) + fmaxf(0.f, -a.z));
+      s.z += fmaxf(0.f, bu.z) + fmaxf(0.f, -b.z);
+      s.z += fmaxf(0.f, du.z) + fmaxf(0.f, -d.z);
+      s.w = 0.f + (fmaxf(0.f, ar) + fmaxf(0.f, -a.w));
+      s.w += fmaxf(0.f, bu.w) + fmaxf(0.f, -b.w);
+      s.w += fmaxf(0.f, du.w) + fmaxf(0.f, -d.w);
+      m = fmax(m, (double)fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w)));
+      }
+    }
+    zm = xc;
+    xc = xzp;
+    uz = uzp;
+  }
+  if (!CFLQ) return;  // plain out-of-place correction (predictor): measurably faster than correcting u in place
+  double v[1] = {m}, fin[1];
+  if (grid_reduce<RED_MAX, 1>(v, R, slot, fin) && finalize) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const float mm = (float)fmax(fin[0], R.out[slot_ghost]);
+      *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
+    }
+  }
+}
+
 // Device check that the uniform-coefficient specialisation is legal: μ₀ ≡ 1 on every cell the operator reads, μ₁ ≡ 0, V ≡ 0.
 // Writes the number of offending values (as a max-reduced 0/1 flag) to out[slot].
 __global__ void __launch_bounds__(256) k_check_uniform(const float* __restrict__ mu0, const float* __restrict__ mu1, const float* __restrict__ V, Grid g,
