@@ -20,6 +20,9 @@
 
 #define FTY 8
 #define MARCH_MINB 6  // ≤40 registers ⇒ 6 blocks (48 warps) per SM: measured +10% on every march kernel over the compiler's default
+#ifndef JACOBI_MINB
+#define JACOBI_MINB MARCH_MINB
+#endif
 #ifndef DIVRES_MINB
 #define DIVRES_MINB 4  // f_div_residual carries two double accumulators and three velocity stencils: 40 registers spill
 #endif
@@ -269,7 +272,7 @@ __device__ __forceinline__ void b_f_jacobi(const Grid& g, const Coef& c, const f
   });
 }
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
+__global__ void __launch_bounds__(32 * FTY, JACOBI_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
                                                      int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
   b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
 }
