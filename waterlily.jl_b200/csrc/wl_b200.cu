@@ -183,6 +183,7 @@ struct wl_handle {
   // loads of the extra stage are exposed) against 0.79 ms for the f_correct launch it replaces — OFF by default, WL_SPEC_CORRECT=1 enables.
   bool spec_on = false, spec_done = false, spec_allowed = false;
   float spec_w = 0.f;
+  bool attr_vs = false, attr_c4[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
@@ -838,7 +839,7 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   Level& f = h->levels[li];
   Level& c = h->levels[li + 1];
   ProfLevel pl(h, f);
-  static bool attr = false;
+  bool& attr = h->attr_vs;  // per handle: the attribute belongs to the device the handle lives on
   if (!attr) {
     cudaFuncSetAttribute(f_vsmooth<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
     cudaFuncSetAttribute(f_vsmooth<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
@@ -1236,7 +1237,7 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
   dim3 gr(cdiv(XM, 32), cdiv(YM, CTY), cdiv(ZM, zchunk));
   const bool nowall = g.per[0] && g.per[1] && (g.per[2] || (g.zopen[0] && g.zopen[1]));
   if (FUSE && nowall && h->conv4 && (g.N[0] - 2) % 4 == 0) {  // uniform mode: four cells per thread
-    static bool attr = false;
+    bool& attr = h->attr_c4[LAM];
     if (!attr) {
       cudaFuncSetAttribute(fm_conv4<LAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
       cudaFuncSetAttribute(fm_conv4<LAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
