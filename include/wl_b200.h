@@ -80,8 +80,10 @@ int wl_destroy(wl_handle* h);
  * GPU.  Rank 0 obtains a 128-byte NCCL id with wl_dist_unique_id and the host broadcasts it (torch.distributed, MPI, …); every
  * rank then calls wl_create_dist with the GLOBAL configuration.  Each rank owns dims[3]/nranks planes (an even number >= 4);
  * wl_upload / wl_download move the rank's own slab, ghost planes included: shape (N1, N2, dims[3]/nranks + 2[, ncomp]).
- * Ghost planes are exchanged by ncclSend/ncclRecv over NVLink, the scalar reductions by ncclAllReduce, and multigrid levels
- * with fewer than 4 planes per rank are replicated on every rank (ncclAllGather of the restricted residual). */
+ * Ghost planes move by peer-to-peer stores over NVLink (CUDA IPC mappings of the neighbours' field memory and a flag handshake;
+ * grouped ncclSend/ncclRecv when IPC is unavailable), the scalar reductions by ncclAllReduce, and multigrid levels of at most
+ * 3 M cells (or fewer than 8 planes per rank) are replicated on every rank (ncclAllGather of the restricted residual).
+ * A P-rank run is bit-identical to the single-GPU run. */
 int wl_dist_unique_id(void* id128);
 int wl_create_dist(const wl_config* cfg, int rank, int nranks, const void* nccl_id128, wl_handle** out);
 

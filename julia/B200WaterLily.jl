@@ -55,6 +55,9 @@ end
 
 upload!(a::B200Flow, f::Symbol, A::Array{Float32}) =
     check(ccall((:wl_upload, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Cint), a.h, FIELD[f], A, 0))
+# one component (0-based `i`) of a vector field held separately on the host: no assembled copy
+upload_component!(a::B200Flow, f::Symbol, i::Integer, A::Array{Float32}) =
+    check(ccall((:wl_upload_component, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float32}, Cint), a.h, FIELD[f], i, A, 0))
 function download(a::B200Flow{D}, f::Symbol) where D
     nc = f in (:p, :σ) ? () : f === :μ₁ ? (D, D) : (D,)
     A = Array{Float32}(undef, a.N..., nc...)

@@ -323,3 +323,21 @@ def test_tiny_velocities_take_the_exact_division(periodic):
     s.flow.sync()
     assert np.array_equal(s.flow.u, o.field("u"))
     assert np.array_equal(s.flow.p, o.field("p"))
+
+
+@pytest.mark.gpu
+def test_upload_component_equals_upload():
+    """wl_upload_component (apply! per component) and the staged host transfers: component-wise upload = whole-field upload,
+    and a download returns exactly what was uploaded (reference layout, ghost cells included)."""
+    o, s = make_pair((24, 16, 8), (1.0, 0.0, 0.0), nu=0.02)
+    u = smooth_field(o.N, 3, seed=3)
+    s.flow.upload("u", u)
+    a = s.flow.download("u")
+    for i in range(3):
+        s.flow.upload_component("u", i, u[i] * F(2))
+    b = s.flow.download("u")
+    assert np.array_equal(a, u) and np.array_equal(b, u * F(2))
+    with pytest.raises(Exception):
+        s.flow.upload_component("u", 3, u[0])
+    with pytest.raises(Exception):
+        s.flow.upload_component("p", 1, u[0])
