@@ -55,6 +55,7 @@ enum { SLOT_EXIT0 = 0, SLOT_EXIT1 = 1, SLOT_RSUM = 2, SLOT_R2 = 3, SLOT_CFL = 4,
 struct Level {
   Grid g;
   float *L = nullptr, *Dg = nullptr, *iD = nullptr, *x = nullptr, *eps = nullptr, *r = nullptr, *r2 = nullptr, *z = nullptr;
+  unsigned char* semi = nullptr;  // general mode: semi-uniform flag per march block (Coef::semi), nullptr = not used
   float *rext = nullptr, *xext = nullptr;  // z slabs, f_vsmooth: 2×4 planes of r and 2×2 planes of x beyond the ghost planes
   int c[3] = {0, 0, 0};  // coarsening mask from the previous (finer) level
   bool ownL = false, ownz = false;
@@ -77,7 +78,7 @@ struct Level {
     }
     k.Dc = s;
     k.iDc = (s == 0.f) ? s : 1.f / s;
-    (void)uni;
+    k.semi = uni ? nullptr : semi;
     return k;
   }
   // planes a block marches over: 16 when that still gives every SM several blocks, fewer (even, ≥2) on small grids and thin slabs
@@ -184,6 +185,7 @@ struct wl_handle {
   bool spec_on = false, spec_done = false, spec_allowed = false;
   float spec_w = 0.f;
   bool attr_vs = false, attr_c4[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
+  bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
@@ -624,6 +626,12 @@ static int build_levels(wl_handle* h) {
     TRY(dalloc(h, &l.eps, n));
     TRY(dalloc(h, &l.r, n));
     TRY(dalloc(h, &l.r2, n));
+    if (l.fast && h->semi_on) {
+      const dim3 fg = l.fgrid();
+      float* q = nullptr;
+      TRY(dalloc(h, &q, ((size_t)fg.x * fg.y * fg.z + 3) / 4 + 1));
+      l.semi = (unsigned char*)q;
+    }
     if (l.slab) {
       TRY(dalloc(h, &l.rext, (size_t)8 * l.g.s[2]));
       TRY(dalloc(h, &l.xext, (size_t)4 * l.g.s[2]));
@@ -655,6 +663,7 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
     TRY(exch(h, l, l.L, h->D));
     LAUNCH_D(h, k_set_diag, grd(l.inside(), b), b, l.g, l.inside(), (const float*)l.L, l.Dg, l.iD);
     TRY(exch(h, l, l.iD, 1));
+    if (l.semi) LAUNCH(h, k_semi_flags, l.fgrid(), 256, l.g, (const float*)l.L, l.Lc[0], l.Lc[1], l.Lc[2], l.zchunk(), l.semi);
   }
   // uniform-coefficient specialisation: legal iff no body (μ₀≡1, μ₁≡0, V≡0) and every direction periodic
   h->uni = false;
@@ -1625,6 +1634,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
+  if (const char* e = getenv("WL_SEMI")) h->semi_on = atoi(e) != 0;
   if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
   if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));

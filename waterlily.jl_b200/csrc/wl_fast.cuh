@@ -32,6 +32,10 @@ struct Coef {
   const float* L;
   const float* Dg;
   const float* iD;
+  // general mode: per march block, 1 if every face coefficient the block reads is the level's fluid value Lc (0 on wall faces, the
+  // pattern BC!(L,0) leaves) — no body nearby.  Such blocks take L from registers and read only D and iD ("semi-uniform"): 12 B
+  // per cell less in every pressure kernel, same bits.  nullptr: disabled.
+  const unsigned char* semi;
   float Lc[3];  // UNI: face coefficient per direction
   float Dc, iDc;
 };
@@ -59,6 +63,8 @@ struct Frame {
   int ym, yp;               // neighbouring rows (periodic wrap applied)
   i64 row;                  // offset of (i=0, y, k=0) incl. xo
   i64 rowm, rowp;           // same for rows ym, yp
+  bool semi;                // this block is semi-uniform (Coef::semi)
+  bool wx0, wx1, wy0, wy1;  // the group's first / last cell, the row: next to a wall in -x, +x, -y, +y (face coefficient 0)
 };
 
 __device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk, const int3 vb) {
@@ -78,8 +84,23 @@ __device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk, const int
   f.row = (i64)g.xo + g.s[1] * yy;
   f.rowm = (i64)g.xo + g.s[1] * f.ym;
   f.rowp = (i64)g.xo + g.s[1] * f.yp;
+  f.semi = false;
+  f.wx0 = !g.per[0] && f.x0 == 1;
+  f.wx1 = !g.per[0] && f.x0 + 3 == g.N[0] - 2;
+  f.wy0 = !g.per[1] && yy == 1;
+  f.wy1 = !g.per[1] && yy == g.N[1] - 2;
   return f;
 }
+// the same for a kernel that reads coefficients: picks up the block's semi-uniform flag
+__device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk, const int3 vb, const Coef& c) {
+  Frame f = make_frame(g, zchunk, vb);
+  if (c.semi) f.semi = c.semi[vb.x + cdiv(g.N[0] - 2, 128) * (vb.y + cdiv(g.N[1] - 2, FTY) * vb.z)] != 0;
+  return f;
+}
+// face coefficients of a semi-uniform block: lower / upper z faces of plane z, and the splats used by the operators
+__device__ __forceinline__ bool wall_zlo(const Grid& g, int z) { return !g.per[2] && !g.zopen[0] && z == 1; }
+__device__ __forceinline__ bool wall_zhi(const Grid& g, int z) { return !g.per[2] && !g.zopen[1] && z == g.N[2] - 2; }
+__device__ __forceinline__ float4 splat4(float v) { return make_float4(v, v, v, v); }
 __device__ __forceinline__ Frame make_frame(const Grid& g, int zchunk) { return make_frame(g, zchunk, real_block()); }
 __device__ __forceinline__ int zwrap_lo(const Grid& g, int z) { return (g.per[2] && z == 1) ? g.N[2] - 2 : z - 1; }
 __device__ __forceinline__ int zwrap_hi(const Grid& g, int z) { return (g.per[2] && z == g.N[2] - 2) ? 1 : z + 1; }
@@ -148,6 +169,13 @@ __device__ __forceinline__ float4 apply_A(const Grid& g, const Coef& c, const Fr
                                           const float4& yp, const float4& zm, const float4& zp) {
   if (UNI) return mult_uni(c, xc, left, right, ym, yp, zm, zp);
   const i64 o = f.row + pz + f.x0;
+  if (f.semi) {
+    const bool wz0 = !g.per[2] && !g.zopen[0] && pz == g.s[2], wz1 = !g.per[2] && !g.zopen[1] && pz == g.s[2] * (g.N[2] - 2);
+    float4 Llo0 = splat4(c.Lc[0]);
+    if (f.wx0) Llo0.x = 0.f;
+    return mult_gen(xc, left, right, ym, yp, zm, zp, ld4(c.Dg + o), Llo0, f.wx1 ? 0.f : c.Lc[0], splat4(f.wy0 ? 0.f : c.Lc[1]), splat4(f.wy1 ? 0.f : c.Lc[1]),
+                    splat4(wz0 ? 0.f : c.Lc[2]), splat4(wz1 ? 0.f : c.Lc[2]));
+  }
   const float4 Dg = ld4(c.Dg + o);
   const float4 Llo0 = ld4(c.L + o);
   const float Lhi0r = c.L[o + 4];
@@ -218,7 +246,7 @@ template <bool UNI>
 __device__ __forceinline__ void b_f_jacobi(const Grid& g, const Coef& c, const float* r, float* r2, float* x,
                                                      int x_is_zero, int zchunk, Grid gc, float* rc, int do_restrict, int zoffc, const int3 vb) {
   __shared__ float4 ex[FTY][32];
-  const Frame f = make_frame(g, zchunk, vb);
+  const Frame f = make_frame(g, zchunk, vb, c);
   SField F;
   F.q = r;
   F.w = c.iD;
@@ -294,7 +322,7 @@ template <bool UNI, bool PROLONG>
 __device__ __forceinline__ void b_f_increment(const Grid& g, const Coef& c, const float* eps, ProlongSrc ps, float* r,
                                                         float* x, const float* wp, int x_is_zero, int zchunk, int with_l2,
                                                         RedBuf R, int slot, const int3 vb) {
-  const Frame f = make_frame(g, zchunk, vb);
+  const Frame f = make_frame(g, zchunk, vb, c);
   const float w = *wp;
   double l2 = 0.0;
   if (!PROLONG) {
@@ -375,7 +403,7 @@ template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, DIVRES_MINB) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
                                                            float* __restrict__ r, float* __restrict__ zarr, const float* __restrict__ dtp, float wdt,
                                                            int zchunk, RedBuf R, int slot) {
-  const Frame f = make_frame(g, zchunk);
+  const Frame f = make_frame(g, zchunk, real_block(), c);
   const float dt = wdt * (*dtp);
   SField F;
   F.q = p;
@@ -460,7 +488,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_resid_fix(Grid g, floa
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
                                                       const float* __restrict__ dtp, float wdt, int zchunk) {
-  const Frame f = make_frame(g, zchunk);
+  const Frame f = make_frame(g, zchunk, real_block(), c);
   const float dt = wdt * (*dtp);
   float4 zm = f4zero();
   if (f.on) zm = ld4(x + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0);
@@ -482,6 +510,11 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_correct(Grid g, Coef c
         L0 = make_float4(c.Lc[0], c.Lc[0], c.Lc[0], c.Lc[0]);
         L1 = make_float4(c.Lc[1], c.Lc[1], c.Lc[1], c.Lc[1]);
         L2 = make_float4(c.Lc[2], c.Lc[2], c.Lc[2], c.Lc[2]);
+      } else if (f.semi) {
+        L0 = splat4(c.Lc[0]);
+        if (f.wx0) L0.x = 0.f;
+        L1 = splat4(f.wy0 ? 0.f : c.Lc[1]);
+        L2 = splat4(wall_zlo(g, z) ? 0.f : c.Lc[2]);
       } else {
         L0 = ld4(c.L + o);
         L1 = ld4(c.L + g.sc + o);
@@ -614,6 +647,39 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_consta
       *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
     }
   }
+}
+
+// Semi-uniform flags (Coef::semi): one CUDA block per march block (grid = the level's march grid).  The march kernels of that
+// block read L[I,d] on the block's cells and L[I+δ_d,d] one cell further in direction d; the flag is 1 iff all of them equal the
+// fluid value Lc[d], or 0 on a wall face — exactly what a body-free region holds after BC!(L,0) (src/Flow.jl:145).
+__global__ void __launch_bounds__(256) k_semi_flags(const __grid_constant__ Grid g, const float* __restrict__ L, float L0, float L1, float L2, int zchunk,
+                                                    unsigned char* __restrict__ flags) {
+  const int xlo = 1 + 128 * blockIdx.x, ylo = 1 + FTY * blockIdx.y, zlo = 1 + zchunk * blockIdx.z;
+  const int xhi = min(xlo + 128, g.N[0] - 1), yhi = min(ylo + FTY, g.N[1] - 1), zhi = min(zlo + zchunk, g.N[2] - 1);  // exclusive, core
+  const float Lc[3] = {L0, L1, L2};
+  auto expect = [&](int d, int idx) -> float {
+    const bool wall = !g.per[d] && (idx <= 1 ? !(d == 2 && g.zopen[0]) : (idx >= g.N[d] - 1 ? !(d == 2 && g.zopen[1]) : false));
+    return wall ? 0.f : Lc[d];
+  };
+  const int nx = xhi - xlo + 1, ny = yhi - ylo + 1, nz = zhi - zlo + 1;  // one extra layer in each direction
+  int ok = 1;
+  for (int q = threadIdx.x; q < nx * ny * nz; q += blockDim.x) {
+    const int i = q % nx, j = (q / nx) % ny, k = q / (nx * ny);
+    const int x = xlo + i, y = ylo + j, z = zlo + k;
+    const bool ex = x == xhi, ey = y == yhi, ez = z == zhi;
+    if ((int)ex + (int)ey + (int)ez > 1) continue;  // edges / corners of the extra layers are never read
+    const i64 o = (i64)g.xo + x + g.s[1] * y + g.s[2] * z;
+    const int I[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const bool ext = ex || ey || ez;
+      const bool mine = (d == 0 && ex) || (d == 1 && ey) || (d == 2 && ez);
+      if (ext && !mine) continue;  // an extra layer is read for its own direction only
+      if (L[o + g.sc * d] != expect(d, I[d])) ok = 0;
+    }
+  }
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0) flags[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)] = (unsigned char)ok;
 }
 
 // Device check that the uniform-coefficient specialisation is legal: μ₀ ≡ 1 on every cell the operator reads, μ₁ ≡ 0, V ≡ 0.
@@ -1018,10 +1084,11 @@ struct Gs {
   const float* r;
   int lane, x0, xl, xr;
   bool on, lastgrp, wrapl, wrapr;  // wrapl/wrapr: the row ends of this lane are periodic faces
+  bool semi, wx0, wx1, wy0, wy1;   // semi-uniform block and its wall faces (Frame)
 
   __device__ __forceinline__ Gs(const Grid& g_, const Coef& c_, const float* eps_, const float* r_, const Frame& f)
       : g(g_), c(c_), eps(eps_), r(r_), lane(f.lane), x0(f.x0), xl(f.xl), xr(f.xr), on(f.on), lastgrp(f.lastgrp),
-        wrapl(g_.per[0] && f.x0 == 1), wrapr(g_.per[0] && f.x0 + 3 == g_.N[0] - 2) {}
+        wrapl(g_.per[0] && f.x0 == 1), wrapr(g_.per[0] && f.x0 + 3 == g_.N[0] - 2), semi(f.semi), wx0(f.wx0), wx1(f.wx1), wy0(f.wy0), wy1(f.wy1) {}
 
   __device__ __forceinline__ i64 off(int y, int z) const { return (i64)g.xo + g.s[1] * y + g.s[2] * z; }
   __device__ __forceinline__ float iD1(i64 o) const { return UNI ? c.iDc : c.iD[o]; }
@@ -1030,7 +1097,7 @@ struct Gs {
   __device__ __forceinline__ float4 stale4(i64 o) const { return mul4(ld4(r + o), iD4(o)); }
 
   // gauss(I,r,L,iD,x) (src/Poisson.jl:116-122) for the 4 cells of the lane: (r − Σ_d (lo·L[I,d] + hi·L[I+δ_d,d]))·iD
-  __device__ __forceinline__ float4 gauss4(i64 o, const float4& rr, const float4& ec, float left, float right, const float4& ym, const float4& yp,
+  __device__ __forceinline__ float4 gauss4(i64 o, int z, const float4& rr, const float4& ec, float left, float right, const float4& ym, const float4& yp,
                                            const float4& zm, const float4& zp) const {
     float4 s = rr;
     if (UNI) {
@@ -1048,10 +1115,24 @@ struct Gs {
       s.w -= ym.w * L1 + yp.w * L1;
       s.w -= zm.w * L2 + zp.w * L2;
     } else {
-      const float4 A0 = ld4(c.L + o);
-      const float A0r = c.L[o + 4];
-      const float4 A1 = ld4(c.L + g.sc + o), B1 = ld4(c.L + g.sc + o + g.s[1]);
-      const float4 A2 = ld4(c.L + 2 * g.sc + o), B2 = ld4(c.L + 2 * g.sc + o + g.s[2]);
+      float4 A0, A1, B1, A2, B2;
+      float A0r;
+      if (semi) {  // no body near this block: the fluid value on every face, 0 on wall faces
+        A0 = splat4(c.Lc[0]);
+        if (wx0) A0.x = 0.f;
+        A0r = wx1 ? 0.f : c.Lc[0];
+        A1 = splat4(wy0 ? 0.f : c.Lc[1]);
+        B1 = splat4(wy1 ? 0.f : c.Lc[1]);
+        A2 = splat4(wall_zlo(g, z) ? 0.f : c.Lc[2]);
+        B2 = splat4(wall_zhi(g, z) ? 0.f : c.Lc[2]);
+      } else {
+        A0 = ld4(c.L + o);
+        A0r = c.L[o + 4];
+        A1 = ld4(c.L + g.sc + o);
+        B1 = ld4(c.L + g.sc + o + g.s[1]);
+        A2 = ld4(c.L + 2 * g.sc + o);
+        B2 = ld4(c.L + 2 * g.sc + o + g.s[2]);
+      }
       s.x -= left * A0.x + ec.y * A0.y;
       s.x -= ym.x * A1.x + yp.x * B1.x;
       s.x -= zm.x * A2.x + zp.x * B2.x;
@@ -1067,21 +1148,6 @@ struct Gs {
     }
     return mul4(s, iD4(o));
   }
-  // the same for one cell at x (scalar), neighbours given
-  __device__ __forceinline__ float gauss1(i64 o, float rr, float xm, float xp, float ym, float yp, float zm, float zp) const {
-    float s = rr;
-    if (UNI) {
-      s -= xm * c.Lc[0] + xp * c.Lc[0];
-      s -= ym * c.Lc[1] + yp * c.Lc[1];
-      s -= zm * c.Lc[2] + zp * c.Lc[2];
-    } else {
-      s -= xm * c.L[o] + xp * c.L[o + 1];
-      s -= ym * c.L[g.sc + o] + yp * c.L[g.sc + o + g.s[1]];
-      s -= zm * c.L[2 * g.sc + o] + zp * c.L[2 * g.sc + o + g.s[2]];
-    }
-    return s * iD1(o);
-  }
-
   // One half-sweep update of ALL four cells of the lane's group on the absolute interior row (y,z), reading the STORED field
   // `eps` (the caller keeps only the lanes of the colour that moves).  Periodic faces read the stale r·iD.  All lanes must call.
   __device__ __forceinline__ float4 row_update(int y, int z, float4& stored) const {
@@ -1109,28 +1175,7 @@ struct Gs {
     if (lane == 0) left = el;
     if (lane == 31 || lastgrp) right = er;
     if (!on) return f4zero();
-    return gauss4(o, rr, ec, left, right, vym, vyp, vzm, vzp);
-  }
-  // The same update for the single interior cell (x,y,z) (used at the two ends of a warp's row segment).
-  __device__ __forceinline__ float cell_update(int x, int y, int z) const {
-    const i64 o = off(y, z) + x;
-    auto nb = [&](int d, int dir) -> float {  // stored value of the neighbour, stale across a periodic face
-      const int I[3] = {x, y, z};
-      const int v = I[d] + dir;
-      const bool edge = (v == 0 || v == g.N[d] - 1);
-      const bool w = edge && (g.per[d] || (d == 2 && g.zstale[v == 0 ? 0 : 1]));  // stale across a global periodic face
-      const int vv = (edge && g.per[d]) ? (v == 0 ? g.N[d] - 2 : 1) : v;
-      const i64 on_ = o + (i64)(vv - I[d]) * g.s[d];
-      return w ? stale1(on_) : eps[on_];
-    };
-    return gauss1(o, r[o], nb(0, -1), nb(0, 1), nb(1, -1), nb(1, 1), nb(2, -1), nb(2, 1));
-  }
-  // The field after the kernel's first half-sweep (the B colour moves in f_gs_b and f_gs_c) on the interior row (y,z):
-  // stored value on A lanes, recomputed update on B lanes.
-  __device__ __forceinline__ float4 after_first(int y, int z) const {
-    float4 st;
-    const float4 up = row_update(y, z, st);
-    return select_A(first_is_A(x0, y, z), st, up);
+    return gauss4(o, z, rr, ec, left, right, vym, vyp, vzm, vzp);
   }
 };
 
@@ -1138,7 +1183,7 @@ struct Gs {
 template <bool UNI>
 __device__ __forceinline__ void b_f_gs_a(const Grid& g, const Coef& c, const float* r,
                                                    float* eps, int zchunk, const int3 vb) {
-  const Frame f = make_frame(g, zchunk, vb);
+  const Frame f = make_frame(g, zchunk, vb, c);
   const Gs<UNI> G(g, c, eps, r, f);
   SField F;
   F.q = r;
@@ -1148,7 +1193,7 @@ __device__ __forceinline__ void b_f_gs_a(const Grid& g, const Coef& c, const flo
   march7(g, f, F, [&](int z, i64 pz, i64 o, const float4& e, float left, float right, const float4& ym, const float4& yp, const float4& zm,
                       const float4& zp) {
     if (f.on) {
-      const float4 up = G.gauss4(o, ld4(r + o), e, left, right, ym, yp, zm, zp);
+      const float4 up = G.gauss4(o, z, ld4(r + o), e, left, right, ym, yp, zm, zp);
       st4(eps + o, select_A(first_is_A(f.x0, f.y, z), up, e));
     }
   });
@@ -1165,7 +1210,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_cons
 template <bool UNI>
 __device__ __forceinline__ void b_f_gs_half(const Grid& g, const Coef& c, const float* r,
                                                       float* eps, int k0, int zchunk, const int3 vb) {
-  const Frame f = make_frame(g, zchunk, vb);
+  const Frame f = make_frame(g, zchunk, vb, c);
   const Gs<UNI> G(g, c, eps, r, f);
   const int y = min(f.y, g.N[1] - 2);
   const bool moveA = (k0 & 1) != 0;
