@@ -20,6 +20,9 @@
 
 #define FTY 8
 #define MARCH_MINB 6  // ≤40 registers ⇒ 6 blocks (48 warps) per SM: measured +10% on every march kernel over the compiler's default
+#ifndef MARCH_MINB_GEN
+#define MARCH_MINB_GEN 4  // general-coefficient variants: 64 registers, no spills (sphere 512×256×256: 6 → 13.0, 5 → 12.0, 4 → 11.6 ms/step)
+#endif
 #ifndef JACOBI_MINB
 #define JACOBI_MINB MARCH_MINB
 #endif
@@ -300,7 +303,7 @@ __device__ __forceinline__ void b_f_jacobi(const Grid& g, const Coef& c, const f
   });
 }
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, JACOBI_MINB) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
+__global__ void __launch_bounds__(32 * FTY, (UNI ? JACOBI_MINB : MARCH_MINB_GEN)) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
                                                      int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
   b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
 }
@@ -388,7 +391,7 @@ __device__ __forceinline__ void b_f_increment(const Grid& g, const Coef& c, cons
   }
 }
 template <bool UNI, bool PROLONG>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
                                                         float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
                                                         RedBuf R, int slot) {
   b_f_increment<UNI, PROLONG>(g, c, eps, ps, r, x, wp, x_is_zero, zchunk, with_l2, R, slot, real_block());
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_resid_fix(Grid g, floa
 //   u_d[I] −= L[I,d]·(x[I] − x[I−δ_d]);  p = x/dt
 // ------------------------------------------------------------------------------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
+__global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
                                                       const float* __restrict__ dtp, float wdt, int zchunk) {
   const Frame f = make_frame(g, zchunk, real_block(), c);
   const float dt = wdt * (*dtp);
@@ -1199,7 +1202,7 @@ __device__ __forceinline__ void b_f_gs_a(const Grid& g, const Coef& c, const flo
   });
 }
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                    float* __restrict__ eps, int zchunk) {
   b_f_gs_a<UNI>(g, c, r, eps, zchunk, real_block());
 }
@@ -1225,7 +1228,7 @@ __device__ __forceinline__ void b_f_gs_half(const Grid& g, const Coef& c, const 
   }
 }
 template <bool UNI>
-__global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+__global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                       float* eps, int k0, int zchunk) {
   b_f_gs_half<UNI>(g, c, r, eps, k0, zchunk, real_block());
 }
