@@ -185,6 +185,8 @@ struct wl_handle {
   bool spec_on = false, spec_done = false, spec_allowed = false;
   float spec_w = 0.f;
   bool attr_vs = false, attr_c4[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
+  unsigned char* nobody = nullptr;  // general mode: per k_bdim2 block, no body inside (k_nobody_flags); valid after wl_update until μ₀/μ₁/V change
+  bool nobody_valid = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
@@ -664,6 +666,18 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
     LAUNCH_D(h, k_set_diag, grd(l.inside(), b), b, l.g, l.inside(), (const float*)l.L, l.Dg, l.iD);
     TRY(exch(h, l, l.iD, 1));
     if (l.semi) LAUNCH(h, k_semi_flags, l.fgrid(), 256, l.g, (const float*)l.L, l.Lc[0], l.Lc[1], l.Lc[2], l.zchunk(), l.semi);
+  }
+  if (h->semi_on) {  // body-free blocks of BDIM-2
+    dim3 b = blk(h->D);
+    Box in = h->levels[0].inside();
+    const dim3 gr = grd(in, b);
+    if (!h->nobody) {
+      float* q = nullptr;
+      TRY(dalloc(h, &q, ((size_t)gr.x * gr.y * gr.z + 3) / 4 + 1));
+      h->nobody = (unsigned char*)q;
+    }
+    LAUNCH_D(h, k_nobody_flags, gr, b, h->g, in, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, h->nobody);
+    h->nobody_valid = true;
   }
   // uniform-coefficient specialisation: legal iff no body (μ₀≡1, μ₁≡0, V≡0) and every direction periodic
   h->uni = false;
@@ -1317,7 +1331,8 @@ static void momentum(wl_handle* h, int corrector) {
     exch(h, l, h->f, 3);  // BDIM-2 reads f one plane beyond the slab
   } else
     conv_bdim1(h, corrector ? h->u : h->u0, 1);
-  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, corrector);
+  LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, corrector,
+           (const unsigned char*)(h->nobody_valid ? h->nobody : nullptr));
 }
 
 // CFL(a) → *dt_out on the device
@@ -1804,6 +1819,7 @@ int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
   float* p;
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
+  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false;  // until the next wl_update
   return copy_in(h, h->g, p, src, nc, src_is_device);  // z slabs: the caller's slab carries its own ghost planes
 }
 
@@ -1815,6 +1831,7 @@ int wl_upload_component(wl_handle* h, int field, int comp, const float* src, int
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
   if (comp < 0 || comp >= nc) return fail("component %d out of range (field has %d)", comp, nc);
+  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false;
   return copy_in(h, h->g, p + (size_t)comp * h->g.sc, src, 1, src_is_device);
 }
 
