@@ -76,6 +76,10 @@ NCU_TRAFFIC = {
 }
 
 
+# general mode, semi-uniform blocks: the face coefficients come from registers, D and iD are still read; BDIM-2 reads f only
+SEMI_WORDS = {"f_jacobi": 6.125, "f_gs_a": 3, "f_gs_half": 4, "f_increment": 6, "f_div_residual": 9, "f_correct": 8, "k_bdim2": 7.5}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -297,6 +301,8 @@ def main():
     for k, (cnt, m, ncells) in sorted(tim.items(), key=lambda kv: -kv[1][1]):
         ent = {"launches": cnt, "ms": round(m, 3), "share": round(m / tot_ms, 4)}
         words = ALG_WORDS.get(k)
+        if words and not uni and k in SEMI_WORDS:
+            words = (SEMI_WORDS[k], words[1])  # general mode: all but a few per cent of the blocks are semi-uniform (no body nearby)
         if words and words[1 if uni else 0] > 0:
             w = words[1 if uni else 0]
             # the library reports, per kernel, the ghost-padded cells of the level every launch ran on (summed over the launches)
@@ -329,7 +335,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "dims": list(case["dims"]), "periodic": list(case["perdir"]), "body": bool(case["body"]),
                        "poisson_iters_per_step": round(n_v, 3), "l2_flush": "state (%.1f GB) exceeds L2" % (padded * 32 * 4 / 1e9),
-                       "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient",
+                       "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient (semi-uniform blocks away from the body)",
                        "parallelism": "single GPU" if world == 1 else "z-slab x%d (NCCL halo planes + all-reduce; coarse levels replicated)" % world},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "kernel_times": ksum}
 
