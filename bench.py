@@ -42,6 +42,7 @@ WORKLOADS = {
 # (perfect halo reuse) — DESIGN.md §kernels.  (general variable-coefficient form, uniform-coefficient form)
 ALG_WORDS = {
     "fm_conv": (10.5, 7.5),        # general: read u/u⁰ 3(+3 corrector) V 3, write f 3; uniform: read u⁰ 3 (+u 3 corrector), write u 3
+    "fm_conv4g": (10.5, 10.5),     # general mode: read u/u⁰ 3(+3 corrector) V 3, write f 3
     "fm_conv4": (7.5, 7.5),        # uniform mode only: read u⁰ 3 (+u 3 corrector), write u 3
     "f_vsmooth": (4.125, 4.125),   # uniform mode only: read r x (+ coarse x 1/8), write r' x  — replaces f_increment<PROLONG>, f_gs_a, 3 f_gs_half, f_increment
     "k_conv_bdim1": (10.5, 10.5),

@@ -19,6 +19,7 @@
 #include "wl_dist.h"
 #include "wl_fast.cuh"
 #include "wl_conv4.cuh"
+#include "wl_conv4g.cuh"
 #include "wl_vsmooth.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -184,9 +185,13 @@ struct wl_handle {
   // loads of the extra stage are exposed) against 0.79 ms for the f_correct launch it replaces — OFF by default, WL_SPEC_CORRECT=1 enables.
   bool spec_on = false, spec_done = false, spec_allowed = false;
   float spec_w = 0.f;
-  bool attr_vs = false, attr_c4[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
+  bool attr_vs = false, attr_c4[3] = {false, false, false}, attr_c4g[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
   unsigned char* nobody = nullptr;  // general mode: per k_bdim2 block, no body inside (k_nobody_flags); valid after wl_update until μ₀/μ₁/V change
   bool nobody_valid = false;
+  // general mode: fm_conv4g (four cells per thread, bit-identical) — OFF by default: on the sphere wake it runs at 1.26 ms per launch
+  // against 1.12 ms for fm_conv (its grid wastes a fifth of the blocks on the ghost column / row / plane, and the wake's denormal far
+  // field sends a quarter of the warps through the IEEE division).  WL_CONV4G=1 enables.
+  bool conv4g = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
@@ -1286,6 +1291,20 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
     h->launches += 2;
     return;
   }
+  if (!FUSE && h->conv4g && (g.N[0] - 2) % 4 == 0 && g.N[0] - 2 >= 8) {  // general mode, four cells per thread
+    bool& attr = h->attr_c4g[LAM];
+    if (!attr) {
+      cudaFuncSetAttribute(fm_conv4g<LAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
+      attr = true;
+    }
+    const int zc = std::min(h->conv4_zchunk, g.N[2] - 1);
+    dim3 g4(cdiv(g.N[0] - 1, 128), cdiv(g.N[1] - 1, C4TY), cdiv(g.N[2] - 1, zc));
+    prof_begin(h, "fm_conv4g");
+    fm_conv4g<LAM><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zc, h->uext, h->d_flags);
+    prof_end(h);
+    h->launches++;
+    return;
+  }
   prof_begin(h, "fm_conv");
   if (nowall)
     fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
@@ -1650,6 +1669,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
   if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
   if (const char* e = getenv("WL_SEMI")) h->semi_on = atoi(e) != 0;
+  if (const char* e = getenv("WL_CONV4G")) h->conv4g = atoi(e) != 0;
   if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
   if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));

@@ -30,14 +30,20 @@
 // raises `tiny`: the block then marks itself in the `redo` list and the SAFE=true instance of the kernel, launched right behind,
 // recomputes exactly the marked blocks with the IEEE division.  The upper end of the range is covered by the kernel's |u| ≤ 1e37
 // test (|5c+2d−u| ≤ 8e37), which also reports a diverged (non-finite) field.
-template <bool SAFE>
+// SAFE: 0 = fast form, `tiny` raised outside its range; 1 = IEEE division; 2 = fast form with the IEEE division taken in place
+// outside its range (general mode: a wake's far field keeps denormal velocities for many steps, a second pass would run every step)
+template <int SAFE>
 __device__ __forceinline__ float div6_chk(float x, bool& tiny) {
-  if (SAFE) return x / 6.f;
+  if (SAFE == 1) return x / 6.f;
   const float C = 0.16666667163372039794921875f;
   const float q0 = x * C;
   const float r = __fmaf_rn(-6.f, q0, x);
   const float q = __fmaf_rn(r, C, q0);
   const bool inr = fabsf(x) >= 7.888609052210118e-31f;
+  if (SAFE == 2) {
+    if (!inr && x != 0.f) return div6_slow(x);
+    return inr ? q : q0;
+  }
   tiny = tiny || (!inr && x != 0.f);
   return inr ? q : q0;  // ±0 → ±0 (= q0)
 }
@@ -49,7 +55,7 @@ __device__ __forceinline__ float div6_chk(float x, bool& tiny) {
 // mirroring (multiplying the three inputs by s = −1) is exact in IEEE arithmetic, so one code path serves both:
 // λ = s·min(max(min(a',b'), s·c), s·d) with s = sign(d−c).  d−c is ±(u[I]−u[I−δ]) with the sign of û, so s = sign(t·û).
 // (û = 0 gives conv = 0·λ = 0 whatever s is.)  min/max run on the half-rate ALU pipe, the multiplications on the FMA pipe.
-template <int LAM, bool SAFE>
+template <int LAM, int SAFE>
 __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, bool& bad) {
   const float t = u0c - um1;
   const float diff = nu * t;
@@ -69,7 +75,7 @@ __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0
   }
   return uf * lam - diff;
 }
-template <int LAM, bool SAFE>
+template <int LAM, int SAFE>
 __device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, float nu,
                                           bool& bad) {
   return make_float4(flux_p<LAM, SAFE>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM, SAFE>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
