@@ -13,7 +13,11 @@ __device__ __forceinline__ float median3(float a, float b, float c) { return fma
 // x/6 correctly rounded without the division sequence: q0 = x·RN(1/6); the exact remainder r = x − 6·q0 (one FMA) corrects it,
 // q = q0 + r·RN(1/6) (one FMA).  Bit-identical to IEEE x/6.f for every finite x with |x| ≥ 2^-100 — verified exhaustively over
 // all 2^32 inputs on the device by wl_selftest_div6 (tests/test_gpu_parity.py); tiny and non-finite inputs take the real division.
-__device__ __noinline__ float div6_slow(float x) { return x / 6.f; }
+// The rare path (tiny, zero, non-finite inputs).  Through double: x/6.0 is correctly rounded in 53 bits, and rounding that to Float32
+// equals the Float32 division (double rounding is innocuous for a quotient when the wider format has ≥ 2·24+2 bits; ties at .5 of a
+// subnormal ulp are exact in double) — without the Float32 division's denormal subroutine, which a wake's far field would hit on every
+// step.  Covered by the same exhaustive test as the fast form.
+__device__ __noinline__ float div6_slow(float x) { return (float)((double)x / 6.0); }
 __device__ __forceinline__ float div6(float x) {
   const float C = 0.16666667163372039794921875f;  // RN(1/6)
   const float q0 = x * C;
