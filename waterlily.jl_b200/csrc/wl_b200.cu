@@ -193,6 +193,7 @@ struct wl_handle {
   // field sends a quarter of the warps through the IEEE division).  WL_CONV4G=1 enables.
   bool conv4g = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
+  bool divres_uni = true;  // uniform mode: f_divres_uni (WL_DIVRES_UNI=0: f_div_residual<true>)
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
   bool conv4 = true;       // uniform mode: fm_conv4 (WL_CONV4=0 falls back to fm_conv)
@@ -773,7 +774,9 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     const Grid& gc = fused ? coarse->g : l.g;
     float* rc = fused ? coarse->r : nullptr;
     const int zoffc = (fused && l.slab && !coarse->slab) ? coarse->zoffc : 0;
-    if (h->uni)
+    if (h->uni && h->divres_uni && fused && !x_is_zero)
+      LAUNCH(h, f_jacobi_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc);
+    else if (h->uni)
       LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
              zoffc);
     else
@@ -1156,7 +1159,10 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
   for (int d = 0; d < h->D; d++) count *= (float)((d == 2 && l.slab ? l.Ng2 : l.g.N[d]) - 2);
   if (h->dist.on() && !(l.fast && with_div)) return fail("standalone residual! is not available with z-slab decomposition");
   if (l.fast && with_div) {
-    if (h->uni)
+    if (h->uni && h->divres_uni)
+      LAUNCH(h, f_divres_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, dtp(h), w, l.zchunk(), h->red,
+             SLOT_RSUM);
+    else if (h->uni)
       LAUNCH(h, f_div_residual<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
              l.zchunk(), h->red, SLOT_RSUM);
     else
@@ -1671,6 +1677,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_SEMI")) h->semi_on = atoi(e) != 0;
   if (const char* e = getenv("WL_CONV4G")) h->conv4g = atoi(e) != 0;
   if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
+  if (const char* e = getenv("WL_DIVRES_UNI")) h->divres_uni = atoi(e) != 0;
   if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
   if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);

@@ -308,6 +308,77 @@ __global__ void __launch_bounds__(32 * FTY, (UNI ? JACOBI_MINB : MARCH_MINB_GEN)
   b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
 }
 
+// f_jacobi<true> (uniform mode, x not zero, restriction fused) with every load of a plane issued before the first use and the planes
+// of r carried in registers — the structure of f_divres_uni / f_correct_cfl: same operations in the same order as b_f_jacobi.
+__global__ void __launch_bounds__(32 * FTY, 4) f_jacobi_uni(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
+                                                           float* __restrict__ r2, float* __restrict__ x, int zchunk, const __grid_constant__ Grid gc,
+                                                           float* __restrict__ rc, int zoffc) {
+  __shared__ float4 ex[FTY][32];
+  const Frame f = make_frame(g, zchunk);
+  const float iD = c.iDc;
+  float4 zm = f4zero(), rc0 = f4zero();  // r·iD on plane z−1, raw r on plane z
+  if (f.on) {
+    zm = scale4(ld4(r + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0), iD);
+    rc0 = ld4(r + f.row + g.s[2] * f.z0 + f.x0);
+  }
+  float2 acc = make_float2(0.f, 0.f);
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 pz = g.s[2] * z;
+    const i64 o = f.row + pz + f.x0;
+    float4 rzp = f4zero(), ym = f4zero(), yp = f4zero(), xo = f4zero();
+    float el = 0.f, er = 0.f;
+    if (f.on) {
+      rzp = ld4(r + f.row + g.s[2] * zwrap_hi(g, z) + f.x0);
+      ym = ld4(r + f.rowm + pz + f.x0);
+      yp = ld4(r + f.rowp + pz + f.x0);
+      xo = ld4(x + o);
+      if (f.lane == 0) el = r[f.row + pz + f.xl];
+      if (f.lane == 31 || f.lastgrp) er = r[f.row + pz + f.xr];
+    }
+    const float4 e = scale4(rc0, iD), zp = scale4(rzp, iD);
+    ym = scale4(ym, iD);
+    yp = scale4(yp, iD);
+    el = el * iD;
+    er = er * iD;
+    float left, right;
+    x_nbrs(f, e, el, er, left, right);
+    float4 rn = f4zero();
+    if (f.on) {
+      const float4 Ae = mult_uni(c, e, left, right, ym, yp, zm, zp);
+      rn = make_float4(rc0.x - 1.f * Ae.x, rc0.y - 1.f * Ae.y, rc0.z - 1.f * Ae.z, rc0.w - 1.f * Ae.w);
+      st4(r2 + o, rn);
+      st4(x + o, make_float4(xo.x + 1.f * e.x, xo.y + 1.f * e.y, xo.z + 1.f * e.z, xo.w + 1.f * e.w));
+    }
+    // restrict!(coarse.r, fine.r): x fastest, then y, then z  (src/MultiLevelPoisson.jl:13-19)
+    ex[threadIdx.y][f.lane] = rn;
+    __syncthreads();
+    if ((threadIdx.y & 1) == 0) {
+      const float4 up = ex[threadIdx.y + 1][f.lane];
+      const bool zlow = ((z - 1) & 1) == 0;
+      if (zlow) {
+        acc.x = 0.f;
+        acc.y = 0.f;
+      }
+      acc.x += rn.x;
+      acc.x += rn.y;
+      acc.x += up.x;
+      acc.x += up.y;
+      acc.y += rn.z;
+      acc.y += rn.w;
+      acc.y += up.z;
+      acc.y += up.w;
+      if (!zlow && f.on) {
+        const i64 oc = (i64)gc.xo + (f.x0 + 1) / 2 + gc.s[1] * ((f.y + 1) / 2) + gc.s[2] * ((z + 1) / 2 + zoffc);
+        rc[oc] = acc.x;
+        rc[oc + 1] = acc.y;
+      }
+    }
+    __syncthreads();
+    zm = e;
+    rc0 = rzp;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // increment!(p;ω) (src/Poisson.jl:100-104) with the ϵ source either the level's own ϵ array (after GaussSeidelRB!) or
 // the prolongation of the coarse solution, ϵ[I] = coarse.x[down(I)] (src/MultiLevelPoisson.jl:50,99-100), never stored:
@@ -458,6 +529,78 @@ __global__ void __launch_bounds__(32 * FTY, DIVRES_MINB) f_div_residual(Grid g, 
       l2 += (double)rr.x * rr.x + (double)rr.y * rr.y + (double)rr.z * rr.z + (double)rr.w * rr.w;
     }
   });
+  double v[2] = {sum, l2}, fin[2];
+  grid_reduce<RED_SUM, 2>(v, R, slot, fin);
+}
+
+// f_div_residual<true> with every load of a plane issued before the first use and the planes of p and u_z carried in registers
+// (the structure that took f_correct_cfl to the copy peak): same operations in the same order.
+__global__ void __launch_bounds__(32 * FTY, 4) f_divres_uni(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ u,
+                                                           const float* __restrict__ p, float* __restrict__ x, float* __restrict__ r,
+                                                           const float* __restrict__ dtp, float wdt, int zchunk, RedBuf R, int slot) {
+  const Frame f = make_frame(g, zchunk);
+  const float dt = wdt * (*dtp);
+  double sum = 0.0, l2 = 0.0;
+  float4 zm = f4zero(), xc = f4zero(), uz = f4zero();
+  if (f.on) {
+    zm = scale4(ld4(p + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0), dt);
+    xc = scale4(ld4(p + f.row + g.s[2] * f.z0 + f.x0), dt);
+    uz = ld4(u + 2 * g.sc + f.row + g.s[2] * f.z0 + f.x0);
+  }
+  for (int z = f.z0; z < f.z1; z++) {
+    const i64 pz = g.s[2] * z;
+    const i64 o = f.row + pz + f.x0;
+    const i64 ozp = f.row + g.s[2] * zwrap_hi(g, z) + f.x0;
+    float4 zp = f4zero(), ym = f4zero(), yp = f4zero(), ux = f4zero(), uy = f4zero(), uyp = f4zero(), uzp = f4zero();
+    float el = 0.f, er = 0.f, uxr = 0.f;
+    if (f.on) {
+      zp = ld4(p + ozp);
+      ym = ld4(p + f.rowm + pz + f.x0);
+      yp = ld4(p + f.rowp + pz + f.x0);
+      ux = ld4(u + o);
+      uy = ld4(u + g.sc + o);
+      uyp = ld4(u + g.sc + f.rowp + pz + f.x0);
+      uzp = ld4(u + 2 * g.sc + ozp);
+      if (f.lane == 0) el = p[f.row + pz + f.xl];
+      if (f.lane == 31 || f.lastgrp) {
+        er = p[f.row + pz + f.xr];
+        uxr = u[f.row + pz + f.xr];
+      }
+    }
+    zp = scale4(zp, dt);
+    ym = scale4(ym, dt);
+    yp = scale4(yp, dt);
+    el = el * dt;
+    er = er * dt;
+    float left, right;
+    x_nbrs(f, xc, el, er, left, right);
+    float unext = __shfl_down_sync(FULLMASK, ux.x, 1);
+    if (f.lane == 31 || f.lastgrp) unext = uxr;
+    if (f.on) {
+      float4 dv;
+      dv.x = 0.f + (ux.y - ux.x);
+      dv.x += uyp.x - uy.x;
+      dv.x += uzp.x - uz.x;
+      dv.y = 0.f + (ux.z - ux.y);
+      dv.y += uyp.y - uy.y;
+      dv.y += uzp.y - uz.y;
+      dv.z = 0.f + (ux.w - ux.z);
+      dv.z += uyp.z - uy.z;
+      dv.z += uzp.z - uz.z;
+      dv.w = 0.f + (unext - ux.w);
+      dv.w += uyp.w - uy.w;
+      dv.w += uzp.w - uz.w;
+      const float4 Ax = mult_uni(c, xc, left, right, ym, yp, zm, zp);
+      const float4 rr = make_float4(dv.x - Ax.x, dv.y - Ax.y, dv.z - Ax.z, dv.w - Ax.w);
+      st4(x + o, xc);
+      st4(r + o, rr);
+      sum += (double)rr.x + (double)rr.y + (double)rr.z + (double)rr.w;
+      l2 += (double)rr.x * rr.x + (double)rr.y * rr.y + (double)rr.z * rr.z + (double)rr.w * rr.w;
+    }
+    zm = xc;
+    xc = zp;
+    uz = uzp;
+  }
   double v[2] = {sum, l2}, fin[2];
   grid_reduce<RED_SUM, 2>(v, R, slot, fin);
 }
