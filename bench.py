@@ -51,7 +51,7 @@ ALG_WORDS = {
     "f_div_residual": (12, 6),     # read u3 p [L3 D iD]; write x r [z]
     "k_div_residual": (12, 12),
     "f_divres_uni": (6, 6),        # uniform mode: read u3 p; write x r
-    "f_jacobi_uni": (4.125, 4.125),  # uniform mode, level 1: read r x; write r' x (+ coarse r 1/8)
+    "f_jacobi_uni2": (4.125, 4.125),  # uniform mode, level 1: read r x; write r' x (+ coarse r 1/8)
     "f_resid_fix": (1, 1),
     "k_resid_fix": (1, 1),
     "f_jacobi": (9.125, 4.125),    # read r x [iD L3 D]; write r' x (+ coarse r 1/8)

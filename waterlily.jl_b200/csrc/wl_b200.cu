@@ -193,6 +193,7 @@ struct wl_handle {
   // field sends a quarter of the warps through the IEEE division).  WL_CONV4G=1 enables.
   bool conv4g = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
+  bool jacobi2 = true;     // uniform mode, level 1: f_jacobi_uni2 (WL_JACOBI2=0: f_jacobi<true>)
   bool divres_uni = true;  // uniform mode: f_divres_uni (WL_DIVRES_UNI=0: f_div_residual<true>)
   bool fuse_cfl = true;    // uniform mode: f_correct_cfl (WL_FUSE_CFL=0: f_correct + f_cfl)
   bool vsmooth = true;     // uniform mode: f_vsmooth fuses prolongation, GaussSeidelRB! and both increments (WL_VSMOOTH=0: separate launches)
@@ -774,8 +775,8 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     const Grid& gc = fused ? coarse->g : l.g;
     float* rc = fused ? coarse->r : nullptr;
     const int zoffc = (fused && l.slab && !coarse->slab) ? coarse->zoffc : 0;
-    if (h->uni && h->divres_uni && fused && !x_is_zero)
-      LAUNCH(h, f_jacobi_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc);
+    if (h->uni && h->divres_uni && fused && !x_is_zero && h->jacobi2)
+      LAUNCH(h, f_jacobi_uni2, l.fgrid(), dim3(32, FTY / 2), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc);
     else if (h->uni)
       LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
              zoffc);
@@ -1678,6 +1679,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   if (const char* e = getenv("WL_CONV4G")) h->conv4g = atoi(e) != 0;
   if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
   if (const char* e = getenv("WL_DIVRES_UNI")) h->divres_uni = atoi(e) != 0;
+  if (const char* e = getenv("WL_JACOBI2")) h->jacobi2 = atoi(e) != 0;
   if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
   if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
   if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);
