@@ -775,8 +775,8 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     const Grid& gc = fused ? coarse->g : l.g;
     float* rc = fused ? coarse->r : nullptr;
     const int zoffc = (fused && l.slab && !coarse->slab) ? coarse->zoffc : 0;
-    if (h->uni && h->divres_uni && fused && !x_is_zero && h->jacobi2)
-      LAUNCH(h, f_jacobi_uni2, l.fgrid(), dim3(32, FTY / 2), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc);
+    if (h->uni && h->divres_uni && fused && h->jacobi2)
+      LAUNCH(h, f_jacobi_uni2, l.fgrid(), dim3(32, FTY / 2), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc, x_is_zero);
     else if (h->uni)
       LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
              zoffc);

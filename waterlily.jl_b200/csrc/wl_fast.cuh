@@ -308,13 +308,13 @@ __global__ void __launch_bounds__(32 * FTY, (UNI ? JACOBI_MINB : MARCH_MINB_GEN)
   b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
 }
 
-// f_jacobi<true> (uniform mode, x not zero, restriction fused) with every load of a plane issued before the first use and the planes
+// f_jacobi<true> (uniform mode, restriction fused) with every load of a plane issued before the first use and the planes
 // of r carried in registers — the structure of f_divres_uni / f_correct_cfl — and TWO rows per thread (blockDim = (32, FTY/2)): the y pair
 // of a coarse cell sits in one thread, so the restriction needs neither shared memory nor block barriers, and the rows serve as each
 // other's y neighbours.  Same operations in the same order as b_f_jacobi.  0.37 ms at 512³ (94 % of the copy peak) against 0.47 ms.
 __global__ void __launch_bounds__(32 * FTY / 2, 6) f_jacobi_uni2(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                                 float* __restrict__ r2, float* __restrict__ x, int zchunk, const __grid_constant__ Grid gc,
-                                                                float* __restrict__ rc, int zoffc) {
+                                                                float* __restrict__ rc, int zoffc, int x_is_zero) {
   const int lane = threadIdx.x;
   const int x0 = 1 + 4 * (32 * blockIdx.x + lane);
   const int ya = 1 + FTY * blockIdx.y + 2 * threadIdx.y;  // rows ya, ya+1 (the interior height is even)
@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(32 * FTY / 2, 6) f_jacobi_uni2(const __grid_co
       rpb = ld4(r + rowb + pp + x0);
       ym = ld4(r + rowm + pz + x0);
       yp = ld4(r + rowp + pz + x0);
-      xa = ld4(x + rowa + pz + x0);
-      xb = ld4(x + rowb + pz + x0);
+      if (!x_is_zero) {
+        xa = ld4(x + rowa + pz + x0);
+        xb = ld4(x + rowb + pz + x0);
+      }
       if (lane == 0) {
         ela = r[rowa + pz + xl];
         elb = r[rowb + pz + xl];
@@ -377,8 +379,13 @@ __global__ void __launch_bounds__(32 * FTY / 2, 6) f_jacobi_uni2(const __grid_co
       const float4 nb = make_float4(rb.x - 1.f * Ab.x, rb.y - 1.f * Ab.y, rb.z - 1.f * Ab.z, rb.w - 1.f * Ab.w);
       st4(r2 + rowa + pz + x0, na);
       st4(r2 + rowb + pz + x0, nb);
-      st4(x + rowa + pz + x0, make_float4(xa.x + 1.f * ea.x, xa.y + 1.f * ea.y, xa.z + 1.f * ea.z, xa.w + 1.f * ea.w));
-      st4(x + rowb + pz + x0, make_float4(xb.x + 1.f * eb.x, xb.y + 1.f * eb.y, xb.z + 1.f * eb.z, xb.w + 1.f * eb.w));
+      if (x_is_zero) {  // fill!(x,0) before it: x = ϵ
+        st4(x + rowa + pz + x0, ea);
+        st4(x + rowb + pz + x0, eb);
+      } else {
+        st4(x + rowa + pz + x0, make_float4(xa.x + 1.f * ea.x, xa.y + 1.f * ea.y, xa.z + 1.f * ea.z, xa.w + 1.f * ea.w));
+        st4(x + rowb + pz + x0, make_float4(xb.x + 1.f * eb.x, xb.y + 1.f * eb.y, xb.z + 1.f * eb.z, xb.w + 1.f * eb.w));
+      }
       // restrict!(coarse.r, fine.r): x fastest, then y, then z  (src/MultiLevelPoisson.jl:13-19)
       const bool zlow = ((z - 1) & 1) == 0;
       if (zlow) {
