@@ -60,3 +60,18 @@ def test_median3_is_the_middle_value():
     x = rng.standard_normal((3, 100000)).astype(F)
     x[1, :1000] = x[0, :1000]
     assert np.array_equal(median3(x[0], x[1], x[2]), np.sort(x, axis=0)[1])
+
+
+def test_division_by_six_through_double_is_the_float_division():
+    """div6_slow (wl_kernels.cuh): (float)((double)x / 6.0) == x / 6.f for every Float32, subnormal results and ties included.
+    (The GPU test checks all 2^32 inputs on the device; here a 10 M sample of bit patterns plus every subnormal with 3 | m or not.)"""
+    rng = np.random.default_rng(13)
+    bits = rng.integers(0, 2 ** 32, 10_000_000, dtype=np.uint64).astype(np.uint32)
+    sub = np.arange(0, 1 << 23, 7, dtype=np.uint32)            # subnormals and their negatives
+    small = (np.arange(0, 1 << 22, 5, dtype=np.uint32) + np.uint32(1 << 23))  # the smallest normals: quotients are subnormal
+    x = np.concatenate([bits, sub, sub | np.uint32(1 << 31), small]).view(F)
+    with np.errstate(all="ignore"):
+        a = x / F(6)
+        b = (x.astype(np.float64) / 6.0).astype(F)
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    assert bool(same.all())
