@@ -72,11 +72,19 @@ ALG_WORDS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), by (workload, kernel)
-NCU_TRAFFIC = {
-    ("tgv512", "fm_conv4"): 4.06e9,   # profiles/r1_v3_fm_conv4.txt: predictor 3.24e9 + corrector 4.89e9, averaged (algorithmic 4.07e9)
-    ("tgv512", "f_vsmooth"): 2.22e9,  # profiles/r1_v3_vsmooth.txt: level-0 launch (algorithmic 2.24e9)
-}
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures: profiles/ncu_traffic.json
+    maps workload → kernel → {bytes, file, src, src_sha16}.  The entry is stamped with the hash of the kernel's source file at capture
+    time; if the source has changed since, the number is reported with "traffic_stale": true instead of silently going stale."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f)[workload][kernel]
+        with open(os.path.join(ROOT, ent["src"]), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+        return ent["bytes"], {"traffic_source": ent["file"], "traffic_stale": sha != ent["src_sha16"]}
+    except Exception:
+        return None, {}
 
 
 # general mode, semi-uniform blocks (DESIGN.md §4): the face coefficients come from registers, D and iD are still read; BDIM-2 reads f only
@@ -179,6 +187,8 @@ def oracle_run(case, steps, warmup):
     """The CPU port (oracle/) on all host threads: returns seconds per step and the thread count."""
     import oracle
     from oracle import OracleSim
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on explicitly
+    oracle.lib().wlo_set_num_threads(len(os.sched_getaffinity(0)))
     u0 = tgv_u0(case["u0"][1]) if case["u0"] else None
     o = OracleSim(case["dims"], case["uBC"], nu=case["nu"], perdir=case["perdir"], exitBC=case["exitBC"], u0=u0)
     if case["body"]:
@@ -322,7 +332,8 @@ def main():
                     "(multigrid kernels: bytes and time summed over the levels they run on)"}
     if name in ("fm_conv", "fm_conv4"):
         roof["note"] += "; the flux kernel is FP32-issue-bound (9.4 QUICK face fluxes of ≈36 exact-IEEE operations per cell), not HBM-bound: see DESIGN.md"
-    roof["traffic"] = NCU_TRAFFIC.get((args.workload, name))
+    roof["traffic"], extra = ncu_traffic(args.workload, name)
+    roof.update(extra)
     # whole-step roofline with the SURVEY §8d formulas
     if uni:
         b_alg, formula = 200 + 56 * n_v, "uniform-coefficient (no body, periodic): 200 + 56·n_V B/cell/step (SURVEY.md §8d)"
@@ -330,8 +341,8 @@ def main():
         b_alg = (468 if case["body"] else 264) + 120 * n_v
         formula = "general coefficients: %d + 120·n_V B/cell/step (SURVEY.md §8d)" % (468 if case["body"] else 264)
     step_ach = b_alg * padded / (ms * 1e-3 / args.steps) / 1e9
-    roof["step"] = {"alg_bytes_per_cell": round(b_alg, 1), "n_V": round(n_v, 3), "achieved": round(step_ach, 1), "frac": round(step_ach / peak, 4),
-                    "formula": formula}
+    roof["step"] = {"alg_bytes_per_cell": round(b_alg, 1), "n_V": round(n_v, 3), "achieved": round(step_ach, 1),
+                    "frac": round(step_ach / (peak * world), 4), "peak_all_gpus": round(peak * world, 1), "formula": formula}
 
     line = {"metric": METRIC, "value": round(ns_cell, 5), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -346,43 +357,51 @@ def main():
     if not args.no_e2e:
         sim.close()
         del sim
-        pinned = None
-        if u0_host is not None:
-            pinned = torch.from_numpy(u0_host).pin_memory().numpy()
-        torch.cuda.synchronize()
-        distarg2 = new_dist()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        sim2 = build_sim(case, pinned, distarg2, local)
-        h2d = (pinned.nbytes if pinned is not None else 0)
-        if case["body"]:
-            h2d += 4 * padded * (3 + 9 + 3 + 1)
-        t_setup = time.perf_counter() - t0
-        for _ in range(args.warmup):
-            wl.sim_step(sim2)
-        sim2.flow.sync()
-        t1 = time.perf_counter()
-        last_dt = 0.0
-        for _ in range(args.steps):
-            wl.sim_step(sim2)
-            last_dt = float(sim2.flow.Δt[-1])  # device→host read of the step's result
-        u = sim2.flow.u
-        p = sim2.flow.p
-        t2 = time.perf_counter()
-        e2e_s = (t2 - t1) + t_setup
-        d2h = (u.nbytes + p.nbytes) * world
-        h2d *= world
-        if world > 1:
-            tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
+
+        def e2e_leg(u0_arr):
+            torch.cuda.synchronize()
+            distarg2 = new_dist()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            sim2 = build_sim(case, u0_arr, distarg2, local)
+            h2d = (u0_arr.nbytes if u0_arr is not None else 0)
+            if case["body"]:
+                h2d += 4 * padded * (3 + 9 + 3 + 1)
+            t_setup = time.perf_counter() - t0
+            for _ in range(args.warmup):
+                wl.sim_step(sim2)
+            sim2.flow.sync()
+            t1 = time.perf_counter()
+            last_dt = 0.0
+            for _ in range(args.steps):
+                wl.sim_step(sim2)
+                last_dt = float(sim2.flow.Δt[-1])  # device→host read of the step's result
+            u = sim2.flow.u
+            p = sim2.flow.p
+            t2 = time.perf_counter()
+            e2e_s = (t2 - t1) + t_setup
+            d2h = (u.nbytes + p.nbytes) * world + 4 * len(sim2.flow.Δt) * args.steps
+            h2d *= world
+            if world > 1:
+                tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                e2e_s = float(tt.item())
+            sim2.close()
+            return e2e_s, t_setup, h2d, d2h, last_dt
+
+        pinned = torch.from_numpy(u0_host).pin_memory().numpy() if u0_host is not None else None
+        e2e_s, t_setup, h2d, d2h, last_dt = e2e_leg(pinned)
         line["e2e"] = {"value": round(e2e_s * 1e9 / args.steps / cells, 5), "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
-                       "d2h_bytes_per_step": int(d2h / args.steps + 4 * len(sim2.flow.Δt)),
-                       "what": "Simulation(host u0) set-up + K×sim_step with Δt read back each step + u,p downloaded to host, all timed "
-                               "(max over ranks; every rank moves its own z slab)",
+                       "d2h_bytes_per_step": int(d2h / args.steps),
+                       "what": "Simulation(host u0, pinned) set-up + K×sim_step with Δt read back each step + u,p downloaded to host, all timed "
+                               "(max over ranks; every rank moves its own z slab; the process-wide NCCL communicator made for the first "
+                               "handle is reused)",
                        "setup_s": round(t_setup, 3), "last_dt": last_dt}
-        sim2.close()
+        if u0_host is not None:  # the same from ordinary pageable memory (what a Julia Array is)
+            e2e_p, t_setup_p, _, _, _ = e2e_leg(np.array(u0_host, copy=True))
+            line["e2e"]["pageable_host_value"] = round(e2e_p * 1e9 / args.steps / cells, 5)
+            line["e2e"]["pageable_setup_s"] = round(t_setup_p, 3)
 
     # ---- CPU baseline beside it (rank 0, bounded sample) ------------------------------------------------
     if not args.no_cpu and rank == 0:

@@ -65,6 +65,11 @@ enum {
   WL_FLAG_NO_PERSISTENT = 4, /* launch every coarse-level operation separately instead of the one cooperative coarse-level kernel */
   WL_FLAG_NCCL_HALO = 8,     /* multi-GPU: exchange halo planes with ncclSend/ncclRecv instead of the peer-to-peer NVLink kernel */
   WL_FLAG_UNFUSED_GS = 2,    /* run GaussSeidelRB! as six separate launches like the reference (debugging aid) */
+  /* A/B switches between kernel variants that produce the same bits (used by the parity tests to compare them): */
+  WL_FLAG_NO_VSMOOTH = 16,   /* constant-coefficient mode: separate prolongation / GaussSeidelRB! / increment launches instead of f_vsmooth */
+  WL_FLAG_NO_CONV4 = 32,     /* constant-coefficient mode: the one-cell-per-thread flux kernel fm_conv instead of fm_conv4 */
+  WL_FLAG_NO_FUSED_UNI = 64, /* constant-coefficient mode: f_div_residual / f_jacobi / f_correct + f_cfl instead of their fused forms */
+  WL_FLAG_NO_SEMI = 128,     /* general mode: always read the face coefficients L (no semi-uniform march blocks, no body-free BDIM blocks) */
 };
 
 const char* wl_last_error(void);
@@ -162,6 +167,9 @@ int wl_selftest_div6(uint64_t* nbad);
 int wl_sync(wl_handle* h);
 /* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
 int wl_launch_count(wl_handle* h, int64_t* count);
+/* Launch-geometry overrides for tests and tuning (results do not depend on them): "vs_nz" = number of z chunks of f_vsmooth
+ * (0 = automatic), "conv4_zchunk" = planes per block of fm_conv4. */
+int wl_set_tuning(wl_handle* h, const char* key, int value);
 /* 1 if the constant-coefficient (NoBody) kernel variants are active. */
 int wl_is_const_coeff(wl_handle* h, int* flag);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller). */

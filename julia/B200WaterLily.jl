@@ -71,7 +71,14 @@ struct B200Poisson <: AbstractPoisson{Float32,Array{Float32},Array{Float32}}
     flow::B200Flow
     n::Vector{Int16}
 end
-pois_ctor(flow::B200Flow) = B200Poisson(flow, Int16[])
+# Simulation's constructor calls measure!(flow,body) and only then pois_ctor(flow) (src/WaterLily.jl:104-105): the reference
+# builds D, iD and the coarse levels from the measured μ₀, so this constructor rebuilds the handle's hierarchy (the one wl_create
+# made belongs to the body-free μ₀≡1).  The library would also do it by itself before the next step (any upload of μ₀/μ₁/V marks
+# the hierarchy stale), but the reference order is kept explicit here.
+function pois_ctor(flow::B200Flow)
+    check(ccall((:wl_update, lib), Cint, (Ptr{Cvoid},), flow.h))
+    B200Poisson(flow, Int16[])
+end
 update!(b::B200Poisson) = check(ccall((:wl_update, lib), Cint, (Ptr{Cvoid},), b.flow.h))
 
 function sync_histories!(a::B200Flow, b::B200Poisson)
@@ -92,8 +99,10 @@ end
 function measure!(a::B200Flow{D}, body::WaterLily.AbstractBody; t=0f0, ϵ=1) where D
     body isa WaterLily.NoBody && return
     host = WaterLily.Flow(a.N .- 2, a.uBC; perdir=a.perdir, exitBC=a.exitBC, T=Float32)   # scratch CPU flow
-    WaterLily.measure!(host, body; t, ϵ)
+    WaterLily.measure!(host, body; t, ϵ)          # includes the trailing BC!(μ₀,0), BC!(V,0,exitBC) (src/Body.jl:49-50)
     upload!(a, :μ₀, host.μ₀); upload!(a, :μ₁, host.μ₁); upload!(a, :V, host.V); upload!(a, :σ, host.σ)
+    # every one of these uploads marks the Poisson hierarchy stale inside the library: it is rebuilt by pois_ctor / update!,
+    # or at the latest by the next wl_mom_step — sim_step!(sim; remeasure=true) therefore works with host-measured bodies
 end
 time(a::B200Flow) = sum(@view(a.Δt[1:end-1]))
 CFL(a::B200Flow) = (v = Ref{Float32}(); check(ccall((:wl_cfl, lib), Cint, (Ptr{Cvoid}, Ref{Float32}), a.h, v)); v[])

@@ -86,6 +86,8 @@ def lib():
         L.wlo_exitBC.argtypes = [C.c_int, ip, fp, fp, C.c_float]
         L.wlo_perBC.argtypes = [C.c_int, ip, fp, ip]
         L.wlo_num_threads.restype = C.c_int
+        L.wlo_set_num_threads.argtypes = [C.c_int]
+        L.wlo_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -215,11 +217,9 @@ class OracleSim:
         return out
 
     def time(self):
-        """time(a) = sum(Δt[1:end-1]) (src/Flow.jl:174), Float32 running sum."""
-        s = np.float32(0)
-        for v in self.dt[:-1]:
-            s = np.float32(s + v)
-        return float(s)
+        """time(a) = sum(Δt[1:end-1]) (src/Flow.jl:174).  Julia's pairwise/@simd Float32 sum has no pinned order; the oracle
+        returns the Float32 nearest to the exact sum (accumulated in double), which every summation order agrees with to a few ulp."""
+        return float(np.float32(np.sum(self.dt[:-1].astype(np.float64))))
 
     def sim_step_until(self, t_end, U=1.0, Lscale=1.0, max_steps=10**9):
         """sim_step!(sim,t_end;remeasure=false) (src/WaterLily.jl:128-135)"""

@@ -1017,6 +1017,14 @@ void wlo_perBC(int D, const int* N, float* a, const int* per) {
   Grid g{D, {N[0], N[1], D > 2 ? N[2] : 1}};
   perBC(g, a, per);
 }
+// bench.py: under torchrun the environment carries OMP_NUM_THREADS=1; the CPU baseline must use all host cores it may run on
+void wlo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int wlo_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

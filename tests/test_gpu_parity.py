@@ -50,9 +50,11 @@ def test_bc_and_conv_diff_bit_exact(name, lam):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-def test_mom_step_two_steps(name):
+@pytest.mark.parametrize("lam", ["quick", "cds", "vanLeer"])
+def test_mom_step_two_steps(name, lam):
+    """Whole steps through the production kernels (3-D: fm_conv<λ> + k_bdim2, 2-D: k_conv_bdim1<λ>) for every limiter."""
     sphere = None
-    cfg = CASES[name]
+    cfg = dict(CASES[name], lam=lam)
     if name in ("3d_box", "3d_mixed_exit"):
         sphere = (tuple(d / 2 for d in cfg["dims"]), 3.0)
     if name == "2d_box":
@@ -234,13 +236,33 @@ def test_circle_2d_100_steps_parity():
     assert dn.max() <= 1
 
 
-def test_pcg_smoother_and_single_level_step():
-    o, s = make_pair((32, 32), (1.0, 0.0), nu=0.05, sphere=((12.0, 16.0), 4.0), pois="single")
+PCG_CASES = {
+    # solver!(::Poisson) = pcg! until Σr² < tol (src/Poisson.jl:204-214), with a body / fully periodic (perdot, src/Poisson.jl:156-157)
+    "single_2d_body": dict(dims=(32, 32), uBC=(1.0, 0.0), nu=0.05, sphere=((12.0, 16.0), 4.0), pois="single"),
+    "single_2d_periodic": dict(dims=(32, 32), uBC=(0.0, 0.0), nu=0.01, perdir=(1, 2), pois="single"),
+    "single_3d_periodic": dict(dims=(16, 16, 16), uBC=(0.0, 0.0, 0.0), nu=0.01, perdir=(1, 2, 3), pois="single"),
+    # smooth!(p) = pcg!(p) inside the V-cycle (src/MultiLevelPoisson.jl:106 rebound; test/test_poisson.jl:62-67 runs both smoothers)
+    "ml_pcg_2d_body": dict(dims=(64, 32), uBC=(1.0, 0.0), nu=0.05, sphere=((20.0, 16.0), 5.0), smoother="pcg"),
+    "ml_pcg_3d_box": dict(dims=(32, 16, 16), uBC=(1.0, 0.0, 0.0), nu=0.05, sphere=((10.0, 8.0, 8.0), 3.0), smoother="pcg"),
+    "ml_pcg_3d_periodic": dict(dims=(32, 32, 32), uBC=(0.0, 0.0, 0.0), nu=0.01, perdir=(1, 2, 3), smoother="pcg"),
+}
+
+
+@pytest.mark.parametrize("name", list(PCG_CASES))
+def test_pcg_solver_and_smoother(name):
+    """pcg! as the single-level solver and as the V-cycle smoother, walls / body / periodic (perdot), held to the north-star
+    tolerance (1e-5; the dots are double-accumulated on both sides, so the iterates agree to rounding)."""
+    cfg = PCG_CASES[name]
+    o, s = make_pair(**cfg)
+    if cfg.get("perdir"):
+        upload_same_u(o, s, seed=4)
+    from wl_b200 import lib as wlib
     for _ in range(3):
         o.mom_step()
-        s.flow.L.wl_mom_step(s.flow.h)
-    assert np.abs(np.asarray(o.iters, int) - np.asarray(s.pois.n, int)).max() <= 1
-    assert rel_l2(s.flow.u, o.field("u")) < 1e-4
+        wlib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    assert np.abs(np.asarray(o.iters, int) - np.asarray(s.pois.n, int)).max() <= 1, (list(o.iters), list(s.pois.n))
+    eu, ep = rel_l2(s.flow.u, o.field("u")), rel_l2(s.flow.p, o.field("p"))
+    assert eu <= 1e-5 and ep <= 1e-5, (eu, ep)
 
 
 def test_div6_is_ieee_division_for_all_floats():
@@ -264,12 +286,13 @@ def _tgv_pair(dims, oracle_too=True):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims,nz", [((64, 64, 64), 0), ((128, 96, 64), 2)])
-def test_fused_upstroke_matches_oracle(dims, nz, monkeypatch):
+def test_fused_upstroke_matches_oracle(dims, nz):
     """f_vsmooth (prolongation + GaussSeidelRB! + increments in one pass, wl_vsmooth.cuh) and fm_conv4 on grids large enough to
     take those paths, with several tiles per direction and (nz=2) several z chunks: bit-identical to the oracle."""
-    if nz:
-        monkeypatch.setenv("WL_VS_NZ", str(nz))
     o, s = _tgv_pair(dims)
+    if nz:
+        from wl_b200 import lib as wlib
+        wlib.check(s.flow.L, s.flow.L.wl_set_tuning(s.flow.h, b"vs_nz", nz))
     for _ in range(4):
         o.mom_step()
         s.flow.L.wl_mom_step(s.flow.h)
@@ -280,18 +303,16 @@ def test_fused_upstroke_matches_oracle(dims, nz, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_fused_kernels_equal_unfused_kernels(monkeypatch):
+def test_fused_kernels_equal_unfused_kernels():
     """128³ (two levels take f_vsmooth): the fused uniform-mode kernels against the separate march kernels, bit for bit."""
     import wl_b200 as wl
     outs = []
-    for flags in ({"WL_VSMOOTH": "1", "WL_CONV4": "1"}, {"WL_VSMOOTH": "0", "WL_CONV4": "0"}):
-        for k, v in flags.items():
-            monkeypatch.setenv(k, v)
+    for flags in (0, wl.lib.FLAGS["no_vsmooth"] | wl.lib.FLAGS["no_conv4"] | wl.lib.FLAGS["no_fused_uni"]):
         n = 128
         u0 = tgv3d_u0((n + 2,) * 3, n)
         u0[2] = (0.1 * np.roll(u0[0], 3, axis=0)).astype(F)
         nu = float(F(1 / (2 * np.pi / n * 1600)))
-        s = wl.Simulation((n,) * 3, (0.0, 0.0, 0.0), float(n), ν=nu, perdir=(1, 2, 3), u0=lambda i, x: u0[i])
+        s = wl.Simulation((n,) * 3, (0.0, 0.0, 0.0), float(n), ν=nu, perdir=(1, 2, 3), u0=lambda i, x: u0[i], flags=flags)
         wl.lib.check(s.flow.L, s.flow.L.wl_sim_step_n(s.flow.h, 3))
         outs.append((s.flow.u.copy(), s.flow.p.copy(), list(s.pois.n), np.asarray(s.flow.Δt).copy()))
     a, b = outs
@@ -341,3 +362,179 @@ def test_upload_component_equals_upload():
         s.flow.upload_component("u", 3, u[0])
     with pytest.raises(Exception):
         s.flow.upload_component("p", 1, u[0])
+
+
+# ---- round 2: the north-star gate on every BASELINE.json config family, at sizes that take the production kernels ----------
+def _gate(o, s, nsteps=100, exact=True):
+    eu, ep, dn = _hundred_steps(o, s, nsteps)
+    assert eu <= 1e-5 and ep <= 1e-5, (eu, ep)
+    assert dn.max() <= 1
+    if exact:  # in practice the two paths execute the same IEEE operations
+        assert np.array_equal(s.flow.u, o.field("u")) and np.array_equal(s.flow.p, o.field("p"))
+        assert list(np.asarray(o.iters)) == list(np.asarray(s.pois.n))
+        assert np.array_equal(np.asarray(o.dt, F), np.asarray(s.flow.Δt, F))
+
+
+def test_tgv128_100_steps_gate():
+    """BASELINE.json configs[1]: 3-D TGV 128³, periodic, 100 steps — fm_conv4 with several z chunks, f_vsmooth on two levels,
+    f_jacobi_uni2, f_divres_uni, f_correct_cfl, the persistent coarse-level kernel, over a developing flow (ω back-off,
+    mean-removal and n_V ≠ 2 branches as they occur)."""
+    n = 128
+    u0 = tgv3d_u0((n + 2,) * 3, n)
+    nu = float(F(1 / (2 * np.pi / n * 1600)))
+    o, s = make_pair((n,) * 3, (0.0, 0.0, 0.0), nu=nu, perdir=(1, 2, 3), u0=u0)
+    _gate(o, s)
+    import wl_b200 as wl
+    flag = wl.lib.C.c_int()
+    s.flow.L.wl_is_const_coeff(s.flow.h, wl.lib.C.byref(flag))
+    assert flag.value == 1
+
+
+def test_sphere_128_100_steps_gate():
+    """configs[2] family (sphere wake, exit BC) at 128×64×64: general-mode march kernels with semi-uniform blocks."""
+    o, s = make_pair((128, 64, 64), (1.0, 0.0, 0.0), nu=8 / 100, sphere=((31.0, 31.0, 31.0), 8.0), exitBC=True)
+    _gate(o, s)
+
+
+def test_torus_100_steps_gate():
+    """configs[3] family (donut: torus SDF, axis along x, R/r = 4) at 128×64×64 with the exit BC."""
+    o, s = make_pair((128, 64, 64), (1.0, 0.0, 0.0), nu=16 / 1000, torus=((32.0, 32.0, 32.0), 16.0, 4.0), exitBC=True)
+    for name in ("mu0", "mu1", "V"):
+        a, b = o.field(name), getattr(s.flow, {"mu0": "μ0", "mu1": "μ1", "V": "V"}[name])
+        assert max_ulp(b, a) <= 2.0, name
+    _gate(o, s, exact=False)
+
+
+@pytest.mark.parametrize("lam", ["quick", "cds", "vanLeer"])
+@pytest.mark.parametrize("case", ["per64", "wall64", "sphere64"])
+def test_limiters_on_the_hot_flux_kernels(case, lam):
+    """cds / vanLeer / quick through fm_conv4<λ> (periodic 64³, uniform mode) and fm_conv<λ> (walls, exit plane, body) on grids
+    with several blocks per direction: bit-identical to the oracle after 3 steps."""
+    if case == "per64":
+        u0 = tgv3d_u0((66,) * 3, 64)
+        u0[2] = (0.1 * np.roll(u0[0], 3, axis=0)).astype(F)
+        o, s = make_pair((64, 64, 64), (0.0, 0.0, 0.0), nu=0.01, perdir=(1, 2, 3), u0=u0, lam=lam)
+    elif case == "wall64":
+        o, s = make_pair((64, 32, 32), (1.0, 0.0, 0.0), nu=0.02, perdir=(3,), exitBC=True, lam=lam)
+        upload_same_u(o, s, seed=6)
+    else:
+        o, s = make_pair((64, 32, 32), (1.0, 0.0, 0.0), nu=0.05, sphere=((15.0, 15.0, 15.0), 4.0), lam=lam)
+        upload_same_u(o, s, seed=7)
+    from wl_b200 import lib as wlib
+    for _ in range(3):
+        o.mom_step()
+        wlib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    assert np.array_equal(s.flow.u, o.field("u"))
+    assert np.array_equal(s.flow.p, o.field("p"))
+    assert list(np.asarray(o.iters)) == list(np.asarray(s.pois.n))
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_body_upload_without_update_rebuilds_the_hierarchy(periodic):
+    """A host binding that uploads μ₀/μ₁/V after construction and never calls wl_update (the reference measures the body BEFORE it
+    builds the Poisson, src/WaterLily.jl:104-105, and calls no update!): the library must rebuild D/iD/coarse L — and, on a fully
+    periodic domain, leave constant-coefficient mode — before it steps."""
+    import wl_b200 as wl
+    from wl_b200 import lib as wlib
+    kw = dict(perdir=(1, 2, 3), uBC=(0.0, 0.0, 0.0)) if periodic else dict(uBC=(1.0, 0.0, 0.0))
+    sphere = ((15.0, 15.0, 15.0), 4.0)
+    dims = (32, 32, 32)
+    o, s = make_pair(dims, nu=0.05, sphere=sphere, measure=False, **kw)
+    upload_same_u(o, s, seed=8)
+    mu0, mu1, V, sigma = wl.measure_body(s.flow.N, wl.Sphere(*sphere), 1.0)
+    s.flow.upload("mu0", mu0)
+    s.flow.upload("mu1", mu1)
+    s.flow.upload("V", V)
+    wlib.check(s.flow.L, s.flow.L.wl_measure_bc(s.flow.h))  # BC!(μ₀), BC!(V): the tail of measure! — but NO wl_update
+    for _ in range(2):
+        o.mom_step()
+        wlib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    flag = wlib.C.c_int(7)
+    s.flow.L.wl_is_const_coeff(s.flow.h, wlib.C.byref(flag))
+    assert flag.value == 0
+    assert list(np.asarray(o.iters)) == list(np.asarray(s.pois.n))
+    assert rel_l2(s.flow.u, o.field("u")) <= 1e-6 and rel_l2(s.flow.p, o.field("p")) <= 1e-5
+
+
+def test_linf_and_solver_log_on_gpu():
+    """L∞(p) and the solver log (src/Poisson.jl:190, src/MultiLevelPoisson.jl:111,116): rows (iter, r∞, r₂, ω) against the oracle's
+    (iter, r₂, ω) rows, and the last r∞ against the oracle's L∞ of its final residual."""
+    import wl_b200 as wl
+    o, s = make_pair((32, 16, 16), (1.0, 0.0, 0.0), nu=0.04, sphere=((8.0, 7.0, 7.0), 3.0))
+    wl.lib.check(s.flow.L, s.flow.L.wl_set_logging(s.flow.h, 1))
+    o.mom_step()
+    wl.lib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    lg, lo = s.pois.log, o.log
+    assert lg.shape[0] == lo.shape[0] >= 4
+    assert np.array_equal(lg[:, 0], lo[:, 0])
+    assert np.allclose(lg[:, 2], lo[:, 1], rtol=1e-5) and np.allclose(lg[:, 3], lo[:, 2], rtol=1e-6)
+    assert np.isclose(lg[-1, 1], o.L.wlo_pois_Linf(o.h), rtol=1e-6)
+    wl.lib.check(s.flow.L, s.flow.L.wl_set_logging(s.flow.h, 0))
+    wl.lib.check(s.flow.L, s.flow.L.wl_mom_step(s.flow.h))
+    assert s.pois.log.shape[0] == lg.shape[0]  # nothing is appended while logging is off
+
+
+def _two_rank_worker(rank, world, port, case, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import wl_b200 as wl
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(wl.dist_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    idb = bytes(idt.cpu().numpy().tobytes())
+    n, steps = 64, 5
+    if case == "tgv":
+        dims = (n, n, n)
+        u0g = tgv3d_u0((n + 2,) * 3, n)
+        kw = dict(ν=float(F(1 / (2 * np.pi / n * 1600))), perdir=(1, 2, 3))
+        uBC, body = (0.0, 0.0, 0.0), None
+    else:
+        dims = (2 * n, n, n)
+        u0g = None
+        kw = dict(ν=n / 8 / 100.0, exitBC=True)
+        uBC, body = (1.0, 0.0, 0.0), wl.Sphere((n / 2 - 1,) * 3, n / 8)
+    nzl = dims[2] // world
+    u0f = None
+    if u0g is not None:
+        sl = u0g[:, rank * nzl: rank * nzl + nzl + 2]
+        u0f = lambda i, x: sl[i]  # noqa: E731
+    sim = wl.Simulation(dims, uBC, float(n), u0=u0f, body=body, device=rank, dist=(rank, world, idb), **kw)
+    wl.lib.check(sim.flow.L, sim.flow.L.wl_sim_step_n(sim.flow.h, steps))
+    u, p, dt, its = sim.flow.u, sim.flow.p, sim.flow.Δt, sim.pois.n
+    ok = None
+    if rank == 0:
+        u0f1 = (lambda i, x: u0g[i]) if u0g is not None else None
+        ref = wl.Simulation(dims, uBC, float(n), u0=u0f1, body=body, device=rank, **kw)
+        wl.lib.check(ref.flow.L, ref.flow.L.wl_sim_step_n(ref.flow.h, steps))
+        ur, pr = ref.flow.u[:, 0: nzl + 2], ref.flow.p[0: nzl + 2]
+        ok = (bool(np.array_equal(u[:, 1:-1], ur[:, 1:-1])), bool(np.array_equal(p[1:-1], pr[1:-1])),
+              bool(np.array_equal(dt, ref.flow.Δt)), list(its) == list(ref.pois.n))
+    dist.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["tgv", "sphere"])
+def test_two_rank_slab_run_is_bit_identical_to_one_gpu(case):
+    """§8e parity: a 2-rank z-slab run (P2P halos, all-reduces, replicated coarse levels) equals the single-GPU run bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 150
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for pr in procs:
+        pr.join(60)
+    assert res[0] == (True, True, True, True), res

@@ -56,19 +56,27 @@ def tgv3d_u0(N, L):
     return u
 
 
-def make_pair(dims, uBC, nu=0.0, dt0=0.25, perdir=(), exitBC=False, lam="quick", u0=None, sphere=None, pois="ml",
-              smoother="gs"):
-    """Returns (oracle OracleSim, B200 Simulation) for the same configuration.  `sphere`=(center, radius)."""
+def make_pair(dims, uBC, nu=0.0, dt0=0.25, perdir=(), exitBC=False, lam="quick", u0=None, sphere=None, torus=None, pois="ml",
+              smoother="gs", flags=0, measure=True, **kw):
+    """Returns (oracle OracleSim, B200 Simulation) for the same configuration.  `sphere`=(center, radius),
+    `torus`=(center, R, r) (axis along x).  `flags`: WL_FLAG_* bits or a list of names from wl_b200.lib.FLAGS.
+    `measure=False` builds the B200 side without its body (the caller uploads μ₀/μ₁/V itself)."""
     import oracle
     import wl_b200 as wl
 
+    if not isinstance(flags, int):
+        flags = sum(wl.lib.FLAGS[f] for f in flags)
     o = oracle.OracleSim(dims, uBC, nu=nu, dt0=dt0, perdir=perdir, exitBC=exitBC, lam=lam, u0=u0, pois=pois)
     if sphere is not None:
         o.measure_sphere(*sphere)
+    if torus is not None:
+        o.measure_torus(*torus)
     o.init_pois()
     if smoother != "gs":
         o.set_solver(smoother=smoother)
-    body = wl.Sphere(*sphere) if sphere is not None else None
+    body = None
+    if measure:
+        body = wl.Sphere(*sphere) if sphere is not None else wl.Torus(*torus) if torus is not None else None
     u0f = None
     if u0 is not None:
         u0arr = np.asarray(u0, F)
@@ -76,5 +84,5 @@ def make_pair(dims, uBC, nu=0.0, dt0=0.25, perdir=(), exitBC=False, lam="quick",
         def u0f(i, x):
             return u0arr[i]
     s = wl.Simulation(dims, uBC, 1.0, ν=nu, Δt=dt0, perdir=perdir, exitBC=exitBC, λ=lam, u0=u0f, body=body,
-                      pois="multilevel" if pois == "ml" else "single", smoother=smoother)
+                      pois="multilevel" if pois == "ml" else "single", smoother=smoother, flags=flags, **kw)
     return o, s

@@ -10,7 +10,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <sys/mman.h>
@@ -19,7 +21,6 @@
 #include "wl_dist.h"
 #include "wl_fast.cuh"
 #include "wl_conv4.cuh"
-#include "wl_conv4g.cuh"
 #include "wl_vsmooth.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -45,6 +46,7 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 static NcclApi g_nccl;
+static std::map<std::tuple<int, int, int>, ncclComm_t> g_comm_cache;  // (device, rank, nranks) → communicator, see create_impl
 #define NCK(call)                                                                               \
   do {                                                                                          \
     int r_ = (call);                                                                            \
@@ -150,6 +152,8 @@ struct wl_handle {
   float* d_scal = nullptr;  // [0]=omega, [1]=one, [2]=alpha, [3]=beta, [4]=scratch dt
   float* h_scal = nullptr;  // pinned
   std::vector<float> dt;    // host mirror of flow.Δt
+  double tsum = 0.0;        // Σ dt[0 .. tsum_n) in double (wl_time)
+  size_t tsum_n = 0;
   size_t dt_dev_len = 0;    // entries valid on the device
   std::vector<int16_t> iters;
   std::vector<float> log;  // rows of (iter, rinf, r2, omega)
@@ -178,20 +182,12 @@ struct wl_handle {
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
   bool uni = false;  // uniform-coefficient kernels active (no body, fully periodic)
   bool fused_gs = true;
-  // mom_project! on one GPU in uniform mode: the level-1 f_vsmooth also forms the corrected velocity (into f) and p with the x it
-  // has just computed, so the projection ends with the solver (spec_w = the projection's w while it runs; spec_done = the last
-  // smoother call of the solve did it)
-  // Measured at 512³: the level-1 f_vsmooth goes from 1.58 to 3.2 ms (it is latency-bound with 14 warps per SM; the velocity
-  // loads of the extra stage are exposed) against 0.79 ms for the f_correct launch it replaces — OFF by default, WL_SPEC_CORRECT=1 enables.
-  bool spec_on = false, spec_done = false, spec_allowed = false;
-  float spec_w = 0.f;
-  bool attr_vs = false, attr_c4[3] = {false, false, false}, attr_c4g[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
+  bool attr_vs = false, attr_c4[3] = {false, false, false};  // dynamic shared-memory opt-in done on this handle's device
   unsigned char* nobody = nullptr;  // general mode: per k_bdim2 block, no body inside (k_nobody_flags); valid after wl_update until μ₀/μ₁/V change
   bool nobody_valid = false;
-  // general mode: fm_conv4g (four cells per thread, bit-identical) — OFF by default: on the sphere wake it runs at 1.26 ms per launch
-  // against 1.12 ms for fm_conv (its grid wastes a fifth of the blocks on the ghost column / row / plane, and the wake's denormal far
-  // field sends a quarter of the warps through the IEEE division).  WL_CONV4G=1 enables.
-  bool conv4g = false;
+  // V, μ₀ or μ₁ were written through the ABI since the hierarchy was built: every entry point that solves or steps rebuilds it
+  // first (update!(pois), src/MultiLevelPoisson.jl:79-86), so a host that forgets wl_update cannot step with stale D/iD/coarse L
+  bool pois_dirty = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
   bool jacobi2 = true;     // uniform mode, level 1: f_jacobi_uni2 (WL_JACOBI2=0: f_jacobi<true>)
   bool divres_uni = true;  // uniform mode: f_divres_uni (WL_DIVRES_UNI=0: f_div_residual<true>)
@@ -341,7 +337,7 @@ static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n) {
   const long long total4 = (long long)m * cnt4;
   const int nb = (int)std::max<long long>(1, std::min<long long>(128, (total4 + 2047) / 2048));
   prof_begin(h, "halo_exchange_p2p");
-  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 4000000000LL);
+  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 60000000000LL);
   prof_end(h);
   h->launches++;
   return 0;
@@ -650,6 +646,7 @@ static int build_levels(wl_handle* h) {
 }
 
 static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.jl:79-86
+  h->pois_dirty = false;
   const float zero[3] = {0, 0, 0};
   for (size_t i = 0; i < h->levels.size(); i++) {
     Level& l = h->levels[i];
@@ -699,6 +696,8 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
   CK(cudaGetLastError());
   return 0;
 }
+
+static inline int ensure_hierarchy(wl_handle* h) { return h->pois_dirty ? update_levels(h) : 0; }
 
 static void set_scalar(wl_handle* h, int idx, float v) {
   LAUNCH(h, k_set_scalar, 1, 1, h->d_scal + idx, v);
@@ -871,14 +870,19 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   Level& f = h->levels[li];
   Level& c = h->levels[li + 1];
   ProfLevel pl(h, f);
-  bool& attr = h->attr_vs;  // per handle: the attribute belongs to the device the handle lives on
-  if (!attr) {
-    cudaFuncSetAttribute(f_vsmooth<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    cudaFuncSetAttribute(f_vsmooth<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
-    attr = true;
+  // coefficient form of the level (vs_pair): 1 = unit faces (finest level), 2 = powers of two ≥ 1, 0 = as written
+  const Coef kk = f.coef(true);
+  auto pow2ge1 = [](float v) { int e; return v >= 1.f && std::frexp(v, &e) == 0.5f; };
+  const int lm = (kk.Lc[0] == 1.f && kk.Lc[1] == 1.f && kk.Lc[2] == 1.f) ? 1 : (pow2ge1(kk.Lc[0]) && pow2ge1(kk.Lc[1]) && pow2ge1(kk.Lc[2])) ? 2 : 0;
+  typedef void (*VsKern)(const VsArgs, RedBuf, int);
+  static const VsKern vs_tab[2][2][3] = {
+      {{f_vsmooth<false, false, 0>, f_vsmooth<false, false, 1>, f_vsmooth<false, false, 2>},
+       {f_vsmooth<false, true, 0>, f_vsmooth<false, true, 1>, f_vsmooth<false, true, 2>}},
+      {{f_vsmooth<true, false, 0>, f_vsmooth<true, false, 1>, f_vsmooth<true, false, 2>},
+       {f_vsmooth<true, true, 0>, f_vsmooth<true, true, 1>, f_vsmooth<true, true, 2>}}};
+  if (!h->attr_vs) {  // per handle: the attribute belongs to the device the handle lives on
+    for (int i = 0; i < 12; i++) cudaFuncSetAttribute((&vs_tab[0][0][0])[i], cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM);
+    h->attr_vs = true;
   }
   const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
   const int tiles = cdiv(n0, VS_CX) * cdiv(n1, VS_CY);
@@ -943,33 +947,9 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   }
   dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
-  const bool corr = h->spec_on && li == 0 && with_l2 && !f.slab;
-  a.xo = f.x;
-  a.u = h->u;
-  a.uo = h->f;
-  a.p = h->p;
-  a.dtp = dtp(h);
-  a.wdt = h->spec_w;
-  if (corr) a.xo = f.eps;  // ϵ is not used on a level that runs f_vsmooth: x goes there and the two swap roles
-  if (f.slab) {
-    if (with_l2)
-      f_vsmooth<true, true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-    else
-      f_vsmooth<false, true, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-  } else if (corr) {
-    f_vsmooth<true, false, true><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-  } else {
-    if (with_l2)
-      f_vsmooth<true, false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-    else
-      f_vsmooth<false, false, false><<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
-  }
+  vs_tab[with_l2 ? 1 : 0][f.slab ? 1 : 0][lm]<<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
   prof_end(h);
   h->launches++;
-  if (corr) {
-    std::swap(f.x, f.eps);
-    h->spec_done = true;
-  }
   std::swap(f.r, f.r2);
   CK(cudaGetLastError());
   if (f.slab && li > 0) {
@@ -1145,6 +1125,7 @@ static int vcycle(wl_handle* h, size_t li, const float* wp, bool defer_up = fals
 }
 
 static void log_row(wl_handle* h, int it, float rinf, float r2, float w) {
+  if (!h->logging) return;
   h->log.push_back((float)it);
   h->log.push_back(rinf);
   h->log.push_back(r2);
@@ -1265,7 +1246,7 @@ static void conv_bdim1(wl_handle* h, const float* ua, int mode) {
 }
 
 template <int LAM, bool FUSE>
-static void fconv_launch(wl_handle* h, const float* ua, float* out, int corrector) {
+static int fconv_launch(wl_handle* h, const float* ua, float* out, int corrector) {
   const Grid& g = h->g;
   const int XM = FUSE ? g.N[0] - 2 : g.N[0] - 1, YM = FUSE ? g.N[1] - 2 : g.N[1] - 1, ZM = FUSE ? g.N[2] - 2 : g.N[2] - 1;
   const int zchunk = std::min(32, ZM);
@@ -1280,11 +1261,8 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
     }
     const int zc = std::min(h->conv4_zchunk, g.N[2] - 2);
     dim3 g4(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, C4TY), cdiv(g.N[2] - 2, zc));
+    if ((size_t)g4.x * g4.y * g4.z + 1 > h->redo_cap) return fail("fm_conv4: grid of %u×%u×%u blocks is larger than the redo list", g4.x, g4.y, g4.z);
     prof_begin(h, "fm_conv4");
-    if ((size_t)g4.x * g4.y * g4.z + 1 > h->redo_cap) {
-      fail("fm_conv4: grid larger than the redo list");
-      return;
-    }
     // fast x/6 everywhere; then the blocks that met an input outside its proven range (none, normally: that launch exits at once)
     // again with the IEEE division
     cudaMemsetAsync(h->d_redo, 0, sizeof(int), h->st);
@@ -1296,21 +1274,7 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
                                                                          h->d_flags, h->d_redo, (int)g4.x, (int)g4.y);
     prof_end(h);
     h->launches += 2;
-    return;
-  }
-  if (!FUSE && h->conv4g && (g.N[0] - 2) % 4 == 0 && g.N[0] - 2 >= 8) {  // general mode, four cells per thread
-    bool& attr = h->attr_c4g[LAM];
-    if (!attr) {
-      cudaFuncSetAttribute(fm_conv4g<LAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
-      attr = true;
-    }
-    const int zc = std::min(h->conv4_zchunk, g.N[2] - 1);
-    dim3 g4(cdiv(g.N[0] - 1, 128), cdiv(g.N[1] - 1, C4TY), cdiv(g.N[2] - 1, zc));
-    prof_begin(h, "fm_conv4g");
-    fm_conv4g<LAM><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zc, h->uext, h->d_flags);
-    prof_end(h);
-    h->launches++;
-    return;
+    return 0;
   }
   prof_begin(h, "fm_conv");
   if (nowall)
@@ -1321,19 +1285,17 @@ static void fconv_launch(wl_handle* h, const float* ua, float* out, int correcto
                                                                              h->red, SLOT_PHIMAX, h->uext, h->d_flags);
   prof_end(h);
   h->launches++;
+  return 0;
 }
 template <bool FUSE>
-static void fconv(wl_handle* h, const float* ua, float* out, int corrector) {
-  if (h->cfg.lambda == WL_QUICK)
-    fconv_launch<0, FUSE>(h, ua, out, corrector);
-  else if (h->cfg.lambda == WL_CDS)
-    fconv_launch<1, FUSE>(h, ua, out, corrector);
-  else
-    fconv_launch<2, FUSE>(h, ua, out, corrector);
+static int fconv(wl_handle* h, const float* ua, float* out, int corrector) {
+  if (h->cfg.lambda == WL_QUICK) return fconv_launch<0, FUSE>(h, ua, out, corrector);
+  if (h->cfg.lambda == WL_CDS) return fconv_launch<1, FUSE>(h, ua, out, corrector);
+  return fconv_launch<2, FUSE>(h, ua, out, corrector);
 }
 
 // Momentum update of mom_predict!/mom_correct! up to (not including) BC!: conv_diff! → BDIM! → scale_u!
-static void momentum(wl_handle* h, int corrector) {
+static int momentum(wl_handle* h, int corrector) {
   const Grid& g = h->g;
   dim3 b = blk(h->D);
   Level& l = h->levels[0];
@@ -1342,23 +1304,24 @@ static void momentum(wl_handle* h, int corrector) {
     // uniform mode: u_new straight from the flux kernel; the corrector must not update u in place (stencil reads), so it
     // writes into the f buffer (unused in this mode) and the two are swapped
     if (!corrector)
-      fconv<true>(h, h->u0, h->u, 0);
+      TRY(fconv<true>(h, h->u0, h->u, 0));
     else {
-      fconv<true>(h, h->u, h->f, 1);
+      TRY(fconv<true>(h, h->u, h->f, 1));
       std::swap(h->u, h->f);
     }
-    return;
+    return 0;
   }
   if (h->D == 3) {
-    fconv<false>(h, corrector ? h->u : h->u0, h->f, corrector);
+    TRY(fconv<false>(h, corrector ? h->u : h->u0, h->f, corrector));
     dim3 pb(32, 8, 1);
     int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
     LAUNCH(h, k_f_lowghost, dim3(cdiv(m0, 32), cdiv(m1, 8), 3), pb, g, (const float*)h->u0, (const float*)h->V, h->f, dtp(h));
-    exch(h, l, h->f, 3);  // BDIM-2 reads f one plane beyond the slab
+    TRY(exch(h, l, h->f, 3));  // BDIM-2 reads f one plane beyond the slab
   } else
     conv_bdim1(h, corrector ? h->u : h->u0, 1);
   LAUNCH_D(h, k_bdim2, grd(in, b), b, g, in, h->u, (const float*)h->f, (const float*)h->V, (const float*)h->mu0, (const float*)h->mu1, corrector,
            (const unsigned char*)(h->nobody_valid ? h->nobody : nullptr));
+  return 0;
 }
 
 // CFL(a) → *dt_out on the device
@@ -1398,18 +1361,11 @@ static void cfl(wl_handle* h, float* dt_out) {
 static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_done = nullptr) {
   float r2;
   TRY(residual(h, 1, w, &r2));
-  h->spec_on = lazy_bc(h) && !h->dist.on() && h->spec_allowed;
-  h->spec_done = false;
-  h->spec_w = w;
-  const int rc = solve_after_residual(h, r2, nullptr);
-  h->spec_on = false;
-  if (rc) return rc;
+  TRY(solve_after_residual(h, r2, nullptr));
   Level& l = h->levels[0];
   dim3 b = blk(h->D);
   Box in = l.inside();
-  if (h->spec_done) {
-    std::swap(h->u, h->f);  // the last f_vsmooth of the solve wrote the corrected velocity there, and p
-  } else if (l.fast && h->uni && dt_cfl && lazy_bc(h) && h->fuse_cfl) {
+  if (l.fast && h->uni && dt_cfl && lazy_bc(h) && h->fuse_cfl) {
     const int fin = h->dist.on() ? 0 : 1;
     LAUNCH(h, f_correct_cfl<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
            h->cfg.nu, dt_cfl, h->red, SLOT_CFLINT, SLOT_PHIMAX, fin);
@@ -1450,21 +1406,12 @@ static int ensure_dt_capacity(wl_handle* h, size_t need) {
   return 0;
 }
 static int check_flags(wl_handle* h) {
-  int f = 0;
+  int f = 0, e = 0;
   CK(cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (h->mbox) CK(cudaMemcpyAsync(&e, h->mbox + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  if (getenv("WL_DEBUG")) {
-    int n = 0;
-    cudaMemcpy(&n, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[wl_b200] fm_conv4 repeated %d warp-planes with the IEEE division so far\n", n);
-  }
   if (f) return fail("the flux kernel met a non-finite velocity (or |u| > 1e37): the velocity field has diverged");
-  if (h->mbox) {
-    int e = 0;
-    CK(cudaMemcpyAsync(&e, h->mbox + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    if (e) return fail("peer-to-peer halo exchange timed out waiting for a neighbouring rank");
-  }
+  if (e) return fail("peer-to-peer halo exchange timed out waiting for a neighbouring rank (the ring is marked failed; results after the timeout are invalid)");
   return 0;
 }
 static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vector
@@ -1479,6 +1426,7 @@ static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vec
 
 // mom_step!(a,b)  src/Flow.jl:156-167
 static int mom_step(wl_handle* h) {
+  TRY(ensure_hierarchy(h));
   TRY(ensure_dt_capacity(h, h->dt_dev_len + 1));
   const Grid& g = h->g;
   dim3 b = blk(h->D);
@@ -1486,13 +1434,13 @@ static int mom_step(wl_handle* h) {
   Box in = l.inside(), all = l.all();
   std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
   // predictor  src/Flow.jl:190-196
-  momentum(h, 0);
+  TRY(momentum(h, 0));
   step_bc(h, h->u0);
   if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
   TRY(exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
-  momentum(h, 1);
+  TRY(momentum(h, 1));
   step_bc(h, h->u);
   TRY(exch_u(h, h->u));
   bool cfl_done = false;
@@ -1672,18 +1620,11 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->D = cfg->D;
   h->tol = cfg->tol > 0 ? (double)cfg->tol : 1e-4;
   h->fused_gs = !(cfg->flags & WL_FLAG_UNFUSED_GS);
-  if (const char* e = getenv("WL_VSMOOTH")) h->vsmooth = atoi(e) != 0;
-  if (const char* e = getenv("WL_CONV4")) h->conv4 = atoi(e) != 0;  // tuning / A-B knobs, not part of the ABI
-  if (const char* e = getenv("WL_VS_NZ")) h->vs_nz = atoi(e);
-  if (const char* e = getenv("WL_SEMI")) h->semi_on = atoi(e) != 0;
-  if (const char* e = getenv("WL_CONV4G")) h->conv4g = atoi(e) != 0;
-  if (const char* e = getenv("WL_FUSE_CFL")) h->fuse_cfl = atoi(e) != 0;
-  if (const char* e = getenv("WL_DIVRES_UNI")) h->divres_uni = atoi(e) != 0;
-  if (const char* e = getenv("WL_JACOBI2")) h->jacobi2 = atoi(e) != 0;
-  if (const char* e = getenv("WL_SPEC_CORRECT")) h->spec_allowed = atoi(e) != 0;
-  if (const char* e = getenv("WL_SLAB_MIN_PLANES")) h->slab_min_planes = std::max(4, atoi(e));
-  if (const char* e = getenv("WL_SLAB_MIN_CELLS")) h->slab_min_cells = atof(e);
-  if (const char* e = getenv("WL_CONV4_ZCHUNK")) h->conv4_zchunk = std::max(1, atoi(e));
+  // A/B switches between kernel variants that compute the same bits (debugging aids, part of the ABI: wl_config.flags)
+  h->vsmooth = !(cfg->flags & WL_FLAG_NO_VSMOOTH);
+  h->conv4 = !(cfg->flags & WL_FLAG_NO_CONV4);
+  h->semi_on = !(cfg->flags & WL_FLAG_NO_SEMI);
+  h->fuse_cfl = h->divres_uni = h->jacobi2 = !(cfg->flags & WL_FLAG_NO_FUSED_UNI);
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
   int N[3];
@@ -1701,10 +1642,20 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       if (cfg->pois_kind != WL_POIS_MULTILEVEL) { rc = fail("z-slab decomposition supports the MultiLevelPoisson solver only"); break; }
       const char* why = "";
       if (!g_nccl.load(&why)) { rc = fail("NCCL unavailable: %s", why); break; }
-      ncclUniqueId id;
-      memcpy(&id, nccl_id, sizeof id);
-      int e = g_nccl.CommInitRank(&h->dist.comm, nranks, id, rank);
-      if (e != 0) { rc = fail("ncclCommInitRank: %s", g_nccl.GetErrorString(e)); break; }
+      // One communicator per (device, rank, size) and process: ncclCommInitRank costs 0.3–3 s (it dominated the set-up of every
+      // further Simulation of a multi-GPU host program), so later handles reuse the first one's and ignore their own id.  Every
+      // rank creates its handles in the same order, so all ranks take the same decision.
+      const auto key = std::make_tuple(cfg->device, rank, nranks);
+      auto it = g_comm_cache.find(key);
+      if (it != g_comm_cache.end()) {
+        h->dist.comm = it->second;
+      } else {
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        int e = g_nccl.CommInitRank(&h->dist.comm, nranks, id, rank);
+        if (e != 0) { rc = fail("ncclCommInitRank: %s", g_nccl.GetErrorString(e)); break; }
+        g_comm_cache[key] = h->dist.comm;
+      }
       h->dist.rank = rank;
       h->dist.P = nranks;
       h->dist.up = rank + 1 < nranks ? rank + 1 : (h->perz_global ? 0 : -1);
@@ -1759,9 +1710,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         if (!coop || per_sm < 1) {
           h->small_from = 0;
         } else {
-          int want = 2;
-          if (const char* e = getenv("WL_SMALL_PER_SM")) want = std::max(1, atoi(e));
-          h->small_grid = nsm * std::min(per_sm, want);
+          h->small_grid = nsm * std::min(per_sm, 2);
           void* q = nullptr;
           if (cudaMalloc(&q, 256 * sizeof(SmallOp)) != cudaSuccess) { rc = fail("cudaMalloc ops"); break; }
           h->d_ops = (SmallOp*)q;
@@ -1830,7 +1779,7 @@ int wl_destroy(wl_handle* h) {
         if (q) cudaIpcCloseMemHandle(q);
     }
   }
-  if (h->dist.comm) g_nccl.CommDestroy(h->dist.comm);
+  // (the communicator belongs to the process-wide cache and outlives the handle)
   for (void* q : h->allocs) cudaFree(q);
   if (h->stage) cudaFree(h->stage);
   if (h->d_dthist) cudaFree(h->d_dthist);
@@ -1848,7 +1797,7 @@ int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
   float* p;
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
-  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false;  // until the next wl_update
+  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false, h->pois_dirty = true;  // rebuilt by wl_update or lazily
   return copy_in(h, h->g, p, src, nc, src_is_device);  // z slabs: the caller's slab carries its own ghost planes
 }
 
@@ -1860,7 +1809,7 @@ int wl_upload_component(wl_handle* h, int field, int comp, const float* src, int
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
   if (comp < 0 || comp >= nc) return fail("component %d out of range (field has %d)", comp, nc);
-  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false;
+  if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false, h->pois_dirty = true;
   return copy_in(h, h->g, p + (size_t)comp * h->g.sc, src, 1, src_is_device);
 }
 
@@ -1872,7 +1821,8 @@ int wl_download(wl_handle* h, int field, float* dst, int dst_is_device) {
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
   if (field == WL_P) launch_perbc(h, h->g, h->p);  // perBC!(p.x) at the end of solver! (ghosts are materialised lazily)
-  return copy_out(h, h->g, dst, p, nc, dst_is_device);
+  TRY(copy_out(h, h->g, dst, p, nc, dst_is_device));
+  return dst_is_device ? 0 : check_flags(h);
 }
 
 int wl_apply_bc(wl_handle* h) {
@@ -1911,22 +1861,31 @@ int wl_update(wl_handle* h) {
 int wl_mom_step(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
-  return mom_step(h);
+  TRY(mom_step(h));
+  return check_flags(h);
 }
 
 int wl_sim_step_n(wl_handle* h, int nsteps) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
-  for (int i = 0; i < nsteps; i++) TRY(mom_step(h));
-  return 0;
+  for (int i = 0; i < nsteps; i++) {
+    TRY(mom_step(h));
+    if ((i & 63) == 63) TRY(check_flags(h));  // a diverged field or a dead peer stops the loop within 64 steps
+  }
+  return check_flags(h);
 }
 
+// time(a) = sum(@view a.Δt[1:end-1]) (src/Flow.jl:174).  Julia's Float32 `sum` is pairwise in blocks of 1024 with a @simd inner loop:
+// its rounding depends on the vector width (unpinned), but it stays within a few ulp of the exact sum for any length.  Here the
+// sum is accumulated incrementally in double (O(1) per step; the running Float32 loop this replaces was O(n) per call and drifted
+// by O(n·eps) from the reference after thousands of steps) and rounded to Float32 once, i.e. the Float32 nearest to the exact sum.
 int wl_time(wl_handle* h, double* t) {
   if (!h || !t) return fail("null argument");
   TRY(sync_dt(h));
-  float s = 0.f;  // Float32 running sum like sum(@view(a.Δt[1:end-1]))
-  for (size_t i = 0; i + 1 < h->dt.size(); i++) s += h->dt[i];
-  *t = (double)s;
+  const size_t n = h->dt.empty() ? 0 : h->dt.size() - 1;
+  if (h->tsum_n > n) h->tsum_n = 0, h->tsum = 0.0;
+  for (; h->tsum_n < n; h->tsum_n++) h->tsum += (double)h->dt[h->tsum_n];
+  *t = (double)(float)h->tsum;
   return 0;
 }
 
@@ -1939,6 +1898,7 @@ int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t ma
     TRY(wl_time(h, &t));
     if (!(t * U / L < t_end) || k >= max_steps) break;
     TRY(mom_step(h));
+    TRY(check_flags(h));
     k++;
   }
   if (steps_taken) *steps_taken = k;
@@ -1949,6 +1909,7 @@ int wl_project(wl_handle* h, float w) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   flush_ghosts(h);
+  TRY(ensure_hierarchy(h));
   return project(h, w);
 }
 
@@ -1976,6 +1937,7 @@ int wl_pois_mult(wl_handle* h) {
   if (!h) return fail("null handle");
   if (h->dist.on()) return fail("standalone mult! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_hierarchy(h));
   Level& l = h->levels[0];
   CK(cudaMemsetAsync(l.z, 0, l.cells() * sizeof(float), h->st));
   dim3 b = blk(h->D);
@@ -1999,6 +1961,7 @@ static int store_x_to_p(wl_handle* h) {
 int wl_pois_residual(wl_handle* h, float* r2_out) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_hierarchy(h));
   TRY(load_x_from_p(h));
   float r2;
   TRY(residual(h, 0, 1.f, &r2));
@@ -2010,6 +1973,7 @@ int wl_pois_solve(wl_handle* h, int* iters_out) {
   if (!h) return fail("null handle");
   if (h->dist.on()) return fail("standalone solver! is not available with z-slab decomposition");
   CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_hierarchy(h));
   TRY(load_x_from_p(h));
   float r2;
   TRY(residual(h, 0, 1.f, &r2));
@@ -2024,6 +1988,7 @@ int wl_pois_smooth(wl_handle* h, int level, int kind, float omega) {
   if (!h) return fail("null handle");
   if (level < 0 || level >= (int)h->levels.size()) return fail("level %d out of range", level);
   CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_hierarchy(h));
   Level& l = h->levels[level];
   set_scalar(h, 0, omega);
   if (kind == 0)
@@ -2040,6 +2005,7 @@ int wl_pois_vcycle(wl_handle* h, float omega) {
   if (!h) return fail("null handle");
   if (h->levels.size() < 2) return fail("single-level Poisson has no V-cycle");
   CK(cudaSetDevice(h->cfg.device));
+  TRY(ensure_hierarchy(h));
   set_scalar(h, 0, omega);
   TRY(vcycle(h, 0, h->d_scal + 0));
   CK(cudaGetLastError());
@@ -2080,6 +2046,7 @@ int wl_download_level(wl_handle* h, int level, int which, float* dst) {
   float* p;
   int nc;
   TRY(level_ptr(h, level, which, &p, &nc));
+  if (which == WL_LVL_L || which == WL_LVL_D || which == WL_LVL_ID) TRY(ensure_hierarchy(h));
   return copy_out(h, h->levels[level].g, dst, p, nc, 0);
 }
 int wl_upload_level(wl_handle* h, int level, int which, const float* src) {
@@ -2088,6 +2055,7 @@ int wl_upload_level(wl_handle* h, int level, int which, const float* src) {
   float* p;
   int nc;
   TRY(level_ptr(h, level, which, &p, &nc));
+  if (which == WL_LVL_L && level == 0) h->nobody_valid = false, h->pois_dirty = true;
   return copy_in(h, h->levels[level].g, p, src, nc, 0);
 }
 
@@ -2107,6 +2075,7 @@ int wl_set_dt(wl_handle* h, const float* buf, int len) {
   CK(cudaSetDevice(h->cfg.device));
   TRY(ensure_dt_capacity(h, (size_t)len + 1));
   h->dt.assign(buf, buf + len);
+  h->tsum_n = 0, h->tsum = 0.0;
   CK(cudaMemcpyAsync(h->d_dthist, h->dt.data(), len * sizeof(float), cudaMemcpyHostToDevice, h->st));
   CK(cudaStreamSynchronize(h->st));
   h->dt_dev_len = len;
@@ -2221,6 +2190,14 @@ int wl_get_timings(wl_handle* h, char* buf, int* len) {
     out.clear();
   }
   *len = need;
+  return 0;
+}
+
+int wl_set_tuning(wl_handle* h, const char* key, int value) {
+  if (!h || !key) return fail("null argument");
+  if (!strcmp(key, "vs_nz")) h->vs_nz = value;
+  else if (!strcmp(key, "conv4_zchunk")) h->conv4_zchunk = std::max(1, value);
+  else return fail("unknown tuning key '%s'", key);
   return 0;
 }
 

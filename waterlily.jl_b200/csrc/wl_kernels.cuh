@@ -771,7 +771,7 @@ __global__ void k_cfl_final(RedBuf R, int slot_a, int slot_b, float nu, float* d
 // [5] error) and carry the exchange's sequence number, identical on every rank.
 //   A. tell both neighbours "my ghost planes may be overwritten" (everything that read them is earlier in this stream);
 //   B. wait until both neighbours said so;            C. copy;            D. fence, tell them "arrived", wait for theirs.
-// Every wait is bounded (≈2 s): a lost partner raises the error flag instead of hanging the GPU.
+// Every wait is bounded (≈30 s): a lost partner raises the error word on the whole ring instead of hanging the GPU.
 // ------------------------------------------------------------------------------------------------
 struct HaloSegs {
   int nseg;
@@ -787,32 +787,36 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 __device__ __forceinline__ void st_flag_sys(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int seq, int* my, int* peer_lo, int* peer_hi, long long timeout) {
+  // A timeout is FATAL for the whole ring: the rank that gave up raises the error word of its own mailbox and of both neighbours'
+  // (my[5]), never copies and never signals `arrived`, and every later exchange on a rank whose error word is set returns at once;
+  // the host reads the word after every step (check_flags) and fails the call.  NCCL collectives block without a bound anyway,
+  // so the bound (≈30 s) only has to catch a dead peer.
   __shared__ int ok;
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
+    int good = ld_flag(my + 5) == 0;
+    if (good && blockIdx.x == 0) {
       __threadfence_system();
       if (peer_lo) st_flag_sys(peer_lo + 1, seq);  // I am the upper neighbour of my lower neighbour
       if (peer_hi) st_flag_sys(peer_hi + 0, seq);
     }
     const long long t0 = clock64();
-    int good = 1;
-    while ((peer_lo && ld_flag(my + 0) < seq) || (peer_hi && ld_flag(my + 1) < seq)) {
-      if (clock64() - t0 > timeout) {
-        good = 0;
-        st_flag_sys(my + 5, 1);
-        break;
-      }
+    while (good && ((peer_lo && ld_flag(my + 0) < seq) || (peer_hi && ld_flag(my + 1) < seq))) {
+      if (clock64() - t0 > timeout || ld_flag(my + 5) != 0) good = 0;
+    }
+    if (!good) {
+      st_flag_sys(my + 5, 1);
+      if (peer_lo) st_flag_sys(peer_lo + 5, 1);
+      if (peer_hi) st_flag_sys(peer_hi + 5, 1);
     }
     ok = good;
   }
   __syncthreads();
-  if (ok) {
-    const long long total = (long long)segs.nseg * cnt4;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-      const int sgi = (int)(q / cnt4);
-      const int e = (int)(q - (long long)sgi * cnt4);
-      reinterpret_cast<float4*>(segs.dst[sgi])[e] = reinterpret_cast<const float4*>(segs.src[sgi])[e];
-    }
+  if (!ok) return;
+  const long long total = (long long)segs.nseg * cnt4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int sgi = (int)(q / cnt4);
+    const int e = (int)(q - (long long)sgi * cnt4);
+    reinterpret_cast<float4*>(segs.dst[sgi])[e] = reinterpret_cast<const float4*>(segs.src[sgi])[e];
   }
   __threadfence_system();
   __syncthreads();
@@ -825,8 +829,10 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int 
       if (peer_hi) st_flag_sys(peer_hi + 2, seq);
       const long long t0 = clock64();
       while ((peer_lo && ld_flag(my + 2) < seq) || (peer_hi && ld_flag(my + 3) < seq)) {
-        if (clock64() - t0 > timeout) {
+        if (clock64() - t0 > timeout || ld_flag(my + 5) != 0) {
           st_flag_sys(my + 5, 1);
+          if (peer_lo) st_flag_sys(peer_lo + 5, 1);
+          if (peer_hi) st_flag_sys(peer_hi + 5, 1);
           break;
         }
       }

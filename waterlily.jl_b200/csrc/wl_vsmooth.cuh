@@ -65,16 +65,6 @@ struct VsArgs {
   int slab, cslab, zoff, n2g;
   const float* rext;
   const float* cxext;
-  // CORR (level 1 on one GPU, inside mom_project!): the increment also applies the velocity correction and the pressure unscale
-  // of mom_project! (src/Flow.jl:227-230) with the x it has just formed — u_d −= L_d·(x − x[I−δ_d]) → uo, p = x/dt — so that the
-  // projection needs no further pass when this V-cycle turns out to be the last one.  x is then written out of place (xo): the
-  // x² of the neighbouring cells is re-evaluated from their old x.
-  float* xo;
-  const float* u;
-  float* uo;
-  float* p;
-  const float* dtp;
-  float wdt;
 };
 
 __device__ __forceinline__ float4 mul4s(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -101,7 +91,19 @@ __constant__ VsLut vs_lut = vs_make_lut();
 // array.  The neighbour offsets are immediates: the rings are padded so that the tile's edge elements read garbage in bounds.
 // stS/mS: the x neighbour S lies across the periodic face (read r¹, times mS = iD; mS = 1 otherwise); anyYZ: some y or z
 // neighbour does (rare: one branch around the general form).
-template <bool TE>
+// Σ of the two face terms of one direction, ϵ₋·L + ϵ₊·L with the level's uniform face coefficient L.
+// LM = 1: L == 1 (the finest level): the products are the operands themselves, ϵ₋ + ϵ₊ is the same Float32 value.
+// LM = 2: L a power of two ≥ 1 (fully coarsened uniform levels, L = 2^level): scaling by 2^k commutes with rounding
+//         (no overflow at these magnitudes; sums in the subnormal range are exact), so (ϵ₋ + ϵ₊)·L has the bits of ϵ₋·L + ϵ₊·L.
+// LM = 0: the expression as the reference writes it (src/Poisson.jl:63-69,116-122).
+template <int LM>
+__device__ __forceinline__ float vs_pair(float a, float b, float L) {
+  if (LM == 1) return a + b;
+  if (LM == 2) return (a + b) * L;
+  return a * L + b * L;
+}
+
+template <bool TE, int LM>
 __device__ __forceinline__ void vs_sweep(float* sb, int eq, int eqm, int eqp, int rq, int rqm, int rqp, bool stS, float mS, bool anyYZ, bool stYm,
                                          bool stYp, bool stZm, bool stZp, const VsArgs& a) {
   constexpr int tg = TE ? 0 : VS_AF, ot = TE ? VS_AF : 0;
@@ -132,46 +134,47 @@ __device__ __forceinline__ void vs_sweep(float* sb, int eq, int eqm, int eqp, in
     lf = V;
     rt = make_float4(V.y, V.z, V.w, S);
   }
-  s.x -= lf.x * L0 + rt.x * L0;
-  s.x -= ym.x * L1 + yp.x * L1;
-  s.x -= zm.x * L2 + zp.x * L2;
-  s.y -= lf.y * L0 + rt.y * L0;
-  s.y -= ym.y * L1 + yp.y * L1;
-  s.y -= zm.y * L2 + zp.y * L2;
-  s.z -= lf.z * L0 + rt.z * L0;
-  s.z -= ym.z * L1 + yp.z * L1;
-  s.z -= zm.z * L2 + zp.z * L2;
-  s.w -= lf.w * L0 + rt.w * L0;
-  s.w -= ym.w * L1 + yp.w * L1;
-  s.w -= zm.w * L2 + zp.w * L2;
+  s.x -= vs_pair<LM>(lf.x, rt.x, L0);
+  s.x -= vs_pair<LM>(ym.x, yp.x, L1);
+  s.x -= vs_pair<LM>(zm.x, zp.x, L2);
+  s.y -= vs_pair<LM>(lf.y, rt.y, L0);
+  s.y -= vs_pair<LM>(ym.y, yp.y, L1);
+  s.y -= vs_pair<LM>(zm.y, zp.y, L2);
+  s.z -= vs_pair<LM>(lf.z, rt.z, L0);
+  s.z -= vs_pair<LM>(ym.z, yp.z, L1);
+  s.z -= vs_pair<LM>(zm.z, zp.z, L2);
+  s.w -= vs_pair<LM>(lf.w, rt.w, L0);
+  s.w -= vs_pair<LM>(ym.w, yp.w, L1);
+  s.w -= vs_pair<LM>(zm.w, zp.w, L2);
   st4(sb + eq + tg, mul4s(s, iD));
 }
 
 // A ϵ at the 4 cells of one parity array (mult_uni order: ϵ·D, + x pair, + y pair, + z pair)
+template <int LM>
 __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, const float4& rt, const float4& ym, const float4& yp, const float4& zm,
                                           const float4& zp, const VsArgs& a) {
   const float L0 = a.L0, L1 = a.L1, L2 = a.L2, D = a.D;
   float4 s;
   s.x = c.x * D;
-  s.x += lf.x * L0 + rt.x * L0;
-  s.x += ym.x * L1 + yp.x * L1;
-  s.x += zm.x * L2 + zp.x * L2;
+  s.x += vs_pair<LM>(lf.x, rt.x, L0);
+  s.x += vs_pair<LM>(ym.x, yp.x, L1);
+  s.x += vs_pair<LM>(zm.x, zp.x, L2);
   s.y = c.y * D;
-  s.y += lf.y * L0 + rt.y * L0;
-  s.y += ym.y * L1 + yp.y * L1;
-  s.y += zm.y * L2 + zp.y * L2;
+  s.y += vs_pair<LM>(lf.y, rt.y, L0);
+  s.y += vs_pair<LM>(ym.y, yp.y, L1);
+  s.y += vs_pair<LM>(zm.y, zp.y, L2);
   s.z = c.z * D;
-  s.z += lf.z * L0 + rt.z * L0;
-  s.z += ym.z * L1 + yp.z * L1;
-  s.z += zm.z * L2 + zp.z * L2;
+  s.z += vs_pair<LM>(lf.z, rt.z, L0);
+  s.z += vs_pair<LM>(ym.z, yp.z, L1);
+  s.z += vs_pair<LM>(zm.z, zp.z, L2);
   s.w = c.w * D;
-  s.w += lf.w * L0 + rt.w * L0;
-  s.w += ym.w * L1 + yp.w * L1;
-  s.w += zm.w * L2 + zp.w * L2;
+  s.w += vs_pair<LM>(lf.w, rt.w, L0);
+  s.w += vs_pair<LM>(ym.w, yp.w, L1);
+  s.w += vs_pair<LM>(zm.w, zp.w, L2);
   return s;
 }
 
-template <bool WITH_L2, bool SLAB, bool CORR>
+template <bool WITH_L2, bool SLAB, int LM>
 __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
   extern __shared__ float4 vs_smem4[];
   // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
@@ -213,7 +216,6 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
   const int dcl = ((wrap(xs - 1, n0) + 1) >> 1) - cx, dcr = ((wrap(xs + 8, n0) + 1) >> 1) - cx;
   const float w = *a.wp;
   const float iD = a.iD;
-  const float cdt = CORR ? a.wdt * (*a.dtp) : 1.f;
   double l2 = 0.0;
 
   // global loads are issued one step ahead of their use (the block's warps run in lockstep between barriers, nothing else
@@ -260,11 +262,6 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
       xi0 = ld4(a.x + o);
       xi1 = ld4(a.x + o + 4);
       xiC = ld4(cplane(q) + cinx + gc.px * cy);
-      if (CORR) {  // the velocity the increment of the next step corrects: bring its lines into L2 (no registers to hold them a step)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + g.sc + o));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.u + 2 * g.sc + o));
-      }
     }
   };
 
@@ -282,9 +279,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
       // fine cell j of the group sits in coarse cell j/2; its x neighbour outside that coarse cell is on the left for even j
       auto Aec = [&](float c0, float xo, float yo, float zo) -> float {
         float s = c0 * D;
-        s += c0 * L0 + xo * L0;
-        s += c0 * L1 + yo * L1;
-        s += c0 * L2 + zo * L2;
+        s += vs_pair<LM>(c0, xo, L0);
+        s += vs_pair<LM>(c0, yo, L1);
+        s += vs_pair<LM>(c0, zo, L2);
         return s;
       };
       float4 re, ro;  // r¹ at even / odd positions
@@ -316,9 +313,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
         const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
         else
-          vs_sweep<false>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
       }
     }
     __syncthreads();
@@ -334,9 +331,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         const bool te = ((1 + ypar + q) & 1) == 1;
         const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
         else
-          vs_sweep<false>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
       }
     }
     // ---- increment!: r² = r¹ − ω·A ϵ⁴ ; x² = (x + ω·ϵc) + ω·ϵ⁴ on plane t−7, core cells only ----
@@ -350,8 +347,8 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         const float4 ce = ld4(Eq), co = ld4(Eq + VS_AF);
         const float sl = Eq[VS_AF - 1], sr_ = Eq[4];
         const float4 yme = ld4(Eq - oY), ymo = ld4(Eq + VS_AF - oY), zme = ld4(Eqm), zmo = ld4(Eqm + VS_AF);
-        const float4 Ae = vs_mult(ce, make_float4(sl, co.x, co.y, co.z), co, yme, ld4(Eq + oY), zme, ld4(Eqp), a);
-        const float4 Ao = vs_mult(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ymo, ld4(Eq + VS_AF + oY), zmo, ld4(Eqp + VS_AF), a);
+        const float4 Ae = vs_mult<LM>(ce, make_float4(sl, co.x, co.y, co.z), co, yme, ld4(Eq + oY), zme, ld4(Eqp), a);
+        const float4 Ao = vs_mult<LM>(co, ce, make_float4(ce.y, ce.z, ce.w, sr_), ymo, ld4(Eq + VS_AF + oY), zmo, ld4(Eqp + VS_AF), a);
         const float4 re = ld4(Rq), ro = ld4(Rq + VS_AF);
         const float4 ne = make_float4(re.x - w * Ae.x, re.y - w * Ae.y, re.z - w * Ae.z, re.w - w * Ae.w);
         const float4 no = make_float4(ro.x - w * Ao.x, ro.y - w * Ao.y, ro.z - w * Ao.z, ro.w - w * Ao.w);
@@ -368,64 +365,8 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         x1.y = (x1.y + w * C.z) + w * co.z;
         x1.z = (x1.z + w * C.w) + w * ce.w;
         x1.w = (x1.w + w * C.w) + w * co.w;
-        float* const xout = CORR ? a.xo : a.x;
-        st4(xout + o, x0);
-        st4(xout + o + 4, x1);
-        if (CORR) {
-          // x² at the row below, the plane below and the cell to the left: the expression their owners evaluate, on the old x
-          const int ymr = wrap(yr - 1, n1), qm = wrap(q - 1, n2);
-          const int ginm = g.xo + xs + g.px * ymr;
-          const float* xq = a.x + g.s[2] * q;
-          float4 m0 = ld4(xq + ginm), m1 = ld4(xq + ginm + 4);
-          float4 z0 = ld4(a.x + g.s[2] * qm + gin), z1_ = ld4(a.x + g.s[2] * qm + gin + 4);
-          float xl = xq[g.xo + wrap(xs - 1, n0) + g.px * yr];
-          const float* cq = cplane(q) + cinx;
-          const float4 Cm = ld4(cq + gc.px * ((ymr + 1) >> 1));
-          const float4 Cz = ld4(cplane(q - 1) + cinx + gc.px * cy);
-          const float cl = cq[gc.px * cy + dcl];
-          const float4 u00 = ld4(a.u + o), u01 = ld4(a.u + o + 4);
-          const float4 u10 = ld4(a.u + g.sc + o), u11 = ld4(a.u + g.sc + o + 4);
-          const float4 u20 = ld4(a.u + 2 * g.sc + o), u21 = ld4(a.u + 2 * g.sc + o + 4);
-          xl = (xl + w * cl) + w * sl;
-          m0.x = (m0.x + w * Cm.x) + w * yme.x;
-          m0.y = (m0.y + w * Cm.x) + w * ymo.x;
-          m0.z = (m0.z + w * Cm.y) + w * yme.y;
-          m0.w = (m0.w + w * Cm.y) + w * ymo.y;
-          m1.x = (m1.x + w * Cm.z) + w * yme.z;
-          m1.y = (m1.y + w * Cm.z) + w * ymo.z;
-          m1.z = (m1.z + w * Cm.w) + w * yme.w;
-          m1.w = (m1.w + w * Cm.w) + w * ymo.w;
-          z0.x = (z0.x + w * Cz.x) + w * zme.x;
-          z0.y = (z0.y + w * Cz.x) + w * zmo.x;
-          z0.z = (z0.z + w * Cz.y) + w * zme.y;
-          z0.w = (z0.w + w * Cz.y) + w * zmo.y;
-          z1_.x = (z1_.x + w * Cz.z) + w * zme.z;
-          z1_.y = (z1_.y + w * Cz.z) + w * zmo.z;
-          z1_.z = (z1_.z + w * Cz.w) + w * zme.w;
-          z1_.w = (z1_.w + w * Cz.w) + w * zmo.w;
-          const float L0 = a.L0, L1 = a.L1, L2 = a.L2;
-          float4 v0, v1;  // u_x −= L·(x − x[I−δ_x])
-          v0.x = u00.x - L0 * (x0.x - xl);
-          v0.y = u00.y - L0 * (x0.y - x0.x);
-          v0.z = u00.z - L0 * (x0.z - x0.y);
-          v0.w = u00.w - L0 * (x0.w - x0.z);
-          v1.x = u01.x - L0 * (x1.x - x0.w);
-          v1.y = u01.y - L0 * (x1.y - x1.x);
-          v1.z = u01.z - L0 * (x1.z - x1.y);
-          v1.w = u01.w - L0 * (x1.w - x1.z);
-          st4(a.uo + o, v0);
-          st4(a.uo + o + 4, v1);
-          v0 = make_float4(u10.x - L1 * (x0.x - m0.x), u10.y - L1 * (x0.y - m0.y), u10.z - L1 * (x0.z - m0.z), u10.w - L1 * (x0.w - m0.w));
-          v1 = make_float4(u11.x - L1 * (x1.x - m1.x), u11.y - L1 * (x1.y - m1.y), u11.z - L1 * (x1.z - m1.z), u11.w - L1 * (x1.w - m1.w));
-          st4(a.uo + g.sc + o, v0);
-          st4(a.uo + g.sc + o + 4, v1);
-          v0 = make_float4(u20.x - L2 * (x0.x - z0.x), u20.y - L2 * (x0.y - z0.y), u20.z - L2 * (x0.z - z0.z), u20.w - L2 * (x0.w - z0.w));
-          v1 = make_float4(u21.x - L2 * (x1.x - z1_.x), u21.y - L2 * (x1.y - z1_.y), u21.z - L2 * (x1.z - z1_.z), u21.w - L2 * (x1.w - z1_.w));
-          st4(a.uo + 2 * g.sc + o, v0);
-          st4(a.uo + 2 * g.sc + o + 4, v1);
-          st4(a.p + o, make_float4(x0.x / cdt, x0.y / cdt, x0.z / cdt, x0.w / cdt));
-          st4(a.p + o + 4, make_float4(x1.x / cdt, x1.y / cdt, x1.z / cdt, x1.w / cdt));
-        }
+        st4(a.x + o, x0);
+        st4(a.x + o + 4, x1);
         if (WITH_L2) {
           l2 += (double)ne.x * ne.x + (double)no.x * no.x + (double)ne.y * ne.y + (double)no.y * no.y;
           l2 += (double)ne.z * ne.z + (double)no.z * no.z + (double)ne.w * ne.w + (double)no.w * no.w;
