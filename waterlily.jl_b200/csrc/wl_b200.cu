@@ -172,11 +172,10 @@ struct wl_handle {
   // persistent coarse-level kernel: levels >= small_from run inside one cooperative launch per V-cycle (0 = disabled)
   int small_from = 0;
   int small_grid = 0;
-  int* d_flags = nullptr;  // [0]: the uniform-mode flux kernel met a non-finite velocity (or |u| > 1e37)
+  int* d_flags = nullptr;  // [0]: a velocity field holds a non-finite value (or |u| > 1e37); [2]: range word of the current u, [3]: its ticket (range_note)
   float* stage = nullptr;  // dense staging buffer of one component for host transfers
   size_t stage_cap = 0;
-  int* d_redo = nullptr;   // fm_conv4: blocks to recompute with the IEEE division (see div6_chk)
-  size_t redo_cap = 0;
+  bool range_checked = false;  // the current u was range-checked by the kernel that wrote it (range_note, wl_common.cuh)
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
   std::vector<SmallOp> ops;  // coarser levels with fewer planes per rank are replicated on every rank (exchange latency > redundant work)
@@ -316,7 +315,7 @@ struct PlaneMove {
   int side;
   const float* dst_local;
 };
-static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n) {
+static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, bool carries_u = false) {
   HaloSegs segs;
   memset(&segs, 0, sizeof segs);
   const Dist& d = h->dist;
@@ -337,7 +336,10 @@ static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n) {
   const long long total4 = (long long)m * cnt4;
   const int nb = (int)std::max<long long>(1, std::min<long long>(128, (total4 + 2047) / 2048));
   prof_begin(h, "halo_exchange_p2p");
-  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 60000000000LL);
+  const int* myf = carries_u ? h->d_flags : nullptr;
+  int* flo = carries_u && d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)h->d_flags) : nullptr;
+  int* fhi = carries_u && d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)h->d_flags) : nullptr;
+  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 60000000000LL, myf, flo, fhi);
   prof_end(h);
   h->launches++;
   return 0;
@@ -429,7 +431,7 @@ static int exch_u(wl_handle* h, float* u, float* p = nullptr) {
       mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};
       mv[n++] = {b + g.s[2] * 2, 0, ehi};
     }
-    return p2p_push(h, g, mv, n);
+    return p2p_push(h, g, mv, n, true);
   }
   prof_begin(h, "halo_exchange_u");
   NCK(g_nccl.GroupStart());
@@ -1259,19 +1261,23 @@ static int fconv_launch(wl_handle* h, const float* ua, float* out, int corrector
       cudaFuncSetAttribute(fm_conv4<LAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4SMEM);
       attr = true;
     }
-    const int zc = std::min(h->conv4_zchunk, g.N[2] - 2);
+    int zc = std::min(h->conv4_zchunk, g.N[2] - 2);
+    // small grids: shorter z chunks (each pays one extra plane of fluxes) until every SM has two blocks
+    while (zc > 8 && (long)cdiv(g.N[0] - 2, 128) * cdiv(g.N[1] - 2, C4TY) * cdiv(g.N[2] - 2, zc) < 2 * 148) zc /= 2;
     dim3 g4(cdiv(g.N[0] - 2, 128), cdiv(g.N[1] - 2, C4TY), cdiv(g.N[2] - 2, zc));
-    if ((size_t)g4.x * g4.y * g4.z + 1 > h->redo_cap) return fail("fm_conv4: grid of %u×%u×%u blocks is larger than the redo list", g4.x, g4.y, g4.z);
+    // a field nobody range-checked while writing it (upload, BC kernels, the unfused correction) is checked now (range_note)
+    if (!h->range_checked) {
+      LAUNCH(h, k_range_check, 592, 256, reinterpret_cast<const float4*>(ua), (long long)(g.sc * 3 / 4), h->d_flags);
+      if (h->dist.on()) LAUNCH(h, k_range_check, 64, 256, reinterpret_cast<const float4*>(h->uext), (long long)(g.s[2] * 6 / 4), h->d_flags);
+    }
+    h->range_checked = false;  // `out` is a new field
+    // the fast-division instance, then the IEEE-division instance on the same grid: the device-side range word picks the one that
+    // runs (the other returns at once), so no host decision and no second pass over marked blocks
     prof_begin(h, "fm_conv4");
-    // fast x/6 everywhere; then the blocks that met an input outside its proven range (none, normally: that launch exits at once)
-    // again with the IEEE division
-    cudaMemsetAsync(h->d_redo, 0, sizeof(int), h->st);
-    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags,
-                                                               h->d_redo, (int)g4.x, (int)g4.y);
+    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2);
     prof_end(h);
     prof_begin(h, "fm_conv4_exact");
-    fm_conv4<LAM, true><<<dim3(2 * 148), dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext,
-                                                                         h->d_flags, h->d_redo, (int)g4.x, (int)g4.y);
+    fm_conv4<LAM, true><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2);
     prof_end(h);
     h->launches += 2;
     return 0;
@@ -1368,7 +1374,8 @@ static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_don
   if (l.fast && h->uni && dt_cfl && lazy_bc(h) && h->fuse_cfl) {
     const int fin = h->dist.on() ? 0 : 1;
     LAUNCH(h, f_correct_cfl<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
-           h->cfg.nu, dt_cfl, h->red, SLOT_CFLINT, SLOT_PHIMAX, fin);
+           h->cfg.nu, dt_cfl, h->red, SLOT_CFLINT, SLOT_PHIMAX, fin, h->d_flags);
+    h->range_checked = true;
     std::swap(h->u, h->f);
     if (h->dist.on()) {
       allreduce_slot(h, SLOT_PHIMAX, WL_NCCL_MAX, 2);
@@ -1377,7 +1384,8 @@ static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_don
     if (cfl_done) *cfl_done = true;
   } else if (l.fast && h->uni && lazy_bc(h) && h->fuse_cfl) {  // out of place into f (free in uniform mode), then the two swap roles
     LAUNCH(h, f_correct_cfl<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
-           h->cfg.nu, (float*)nullptr, h->red, SLOT_CFLINT, SLOT_PHIMAX, 0);
+           h->cfg.nu, (float*)nullptr, h->red, SLOT_CFLINT, SLOT_PHIMAX, 0, h->d_flags);
+    h->range_checked = true;
     std::swap(h->u, h->f);
   } else if (l.fast) {
     if (h->uni)
@@ -1684,9 +1692,6 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       float* q = nullptr;
       if ((rc = dalloc(h, &q, 8))) break;
       h->d_flags = (int*)q;
-      h->redo_cap = (size_t)1 << 18;
-      if ((rc = dalloc(h, &q, h->redo_cap))) break;
-      h->d_redo = (int*)q;
     }
     if ((rc = build_levels(h))) break;
     if (h->D == 3 && h->cfg.pois_kind == WL_POIS_MULTILEVEL && h->cfg.smoother == WL_SMOOTH_GSRB && !(cfg->flags & WL_FLAG_NO_PERSISTENT)) {
@@ -1798,6 +1803,7 @@ int wl_upload(wl_handle* h, int field, const float* src, int src_is_device) {
   int nc;
   TRY(field_ptr(h, field, &p, &nc));
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false, h->pois_dirty = true;  // rebuilt by wl_update or lazily
+  if (field == WL_U || field == WL_U0) h->range_checked = false;
   return copy_in(h, h->g, p, src, nc, src_is_device);  // z slabs: the caller's slab carries its own ghost planes
 }
 
@@ -1810,6 +1816,7 @@ int wl_upload_component(wl_handle* h, int field, int comp, const float* src, int
   TRY(field_ptr(h, field, &p, &nc));
   if (comp < 0 || comp >= nc) return fail("component %d out of range (field has %d)", comp, nc);
   if (field == WL_V || field == WL_MU0 || field == WL_MU1) h->nobody_valid = false, h->pois_dirty = true;
+  if (field == WL_U || field == WL_U0) h->range_checked = false;
   return copy_in(h, h->g, p + (size_t)comp * h->g.sc, src, 1, src_is_device);
 }
 
@@ -1829,6 +1836,7 @@ int wl_apply_bc(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   flush_ghosts(h);
+  h->range_checked = false;
   launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, h->u);
   TRY(launch_exitbc(h, h->u, h->u, 0.f));
   TRY(exch_u(h, h->u));

@@ -69,6 +69,80 @@ __device__ __forceinline__ void nbr_offsets(const Grid& g, const int I[3], i64 l
   }
 }
 
+// ---- packed Float32 pairs (sm_100 FADD2 / FMUL2 / FFMA2) ---------------------------------------------------------------
+// Blackwell issues one instruction for two independent IEEE round-to-nearest Float32 operations on a 64-bit register pair
+// (PTX add/sub/mul/fma.rn.f32x2).  Each half is the ordinary scalar operation — same bits as FADD/FMUL/FFMA — so kernels that are
+// bound by instruction issue (the flux kernel: one thread owns four x cells = two pairs) halve their FP32 instruction count
+// without giving up the reference's association order.
+// CONTRACTION HAZARD: ptxas 12.9 fuses a packed multiplication that feeds a packed addition / subtraction into FFMA2 even for
+// .rn operands and under --fmad=false (it honours the flag for scalar code only) — one rounding instead of two, different bits.
+// Rule for every kernel of this library: a packed add2 / sub2 NEVER takes a packed product as an operand; such sums are formed
+// with add2x / sub2x (two scalar FADD on the halves, which ptxas leaves alone).  fma2 is used only where the scalar code already
+// used __fmaf_rn (the proven two-FMA x/6).
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(const float2 a, const float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// exact (uncontracted) sum / difference when an operand is a packed product
+__device__ __forceinline__ float2 add2x(const float2 a, const float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 sub2x(const float2 a, const float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat2(const float2 a, const float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+
+// ---- range of a velocity field (range_note) -------------------------------------------------------------------------------
+// The uniform-mode flux kernel (fm_conv4) divides by 6 with two FMAs, exact when every velocity it reads is 0 or 2^-77 ≤ |v| ≤ 1e37
+// (wl_conv4.cuh).  Instead of testing every flux input, the kernel that WRITES a velocity field tests what it writes (it is
+// HBM-bound and has the issue slots to spare) and raises flags[2] when a value falls outside; fm_conv4 then runs its IEEE-division
+// instance on that field.  |v| > 1e37, Inf and NaN — a diverged run — also raise the error word flags[0], which the host reports.
+// Unsigned integer min / max of the magnitude bits: 0 maps to 0xffffffff in the min (b − 1), so zeros never count as small.
+#define WL_RANGE_LO 0x19000000u  // bits of 2^-77
+#define WL_RANGE_HI 0x7cf0bdc2u  // bits of 1e37
+struct RangeAcc {
+  unsigned mn = 0xffffffffu, mx = 0u;
+  __device__ __forceinline__ void add(float v) {
+    const unsigned b = __float_as_uint(v) & 0x7fffffffu;
+    mn = min(mn, b - 1u);
+    mx = max(mx, b);
+  }
+  __device__ __forceinline__ void add4(const float4& v) {
+    add(v.x);
+    add(v.y);
+    add(v.z);
+    add(v.w);
+  }
+  __device__ __forceinline__ void publish(int* flags) const {
+    const bool small = mn < WL_RANGE_LO - 1u, big = mx > WL_RANGE_HI;
+    if (small || big) flags[2] = 1;  // (benign race: every writer stores the same value)
+    if (big) flags[0] = 1;
+  }
+};
+
 // ---- deterministic single-pass grid reduction ------------------------------------------
 // Every block reduces its values in double with a fixed shuffle tree, writes one partial
 // per value, and the last block to arrive (atomic ticket) folds all partials in a fixed

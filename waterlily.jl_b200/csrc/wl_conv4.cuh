@@ -25,28 +25,30 @@
 #define C4FILL ((C4H * C4Q + 32 * C4TY - 1) / (32 * C4TY))
 #define C4SMEM ((C4RING * C4PS + 2 * 3 * (C4TY + 1) * 32 * 4) * 4)
 
-// x/6, exact for every input.  Fast form (SAFE=false): the two FMAs of wl_kernels.cuh, proven equal to the IEEE division for
-// 2^-100 ≤ |x| ≤ 3e38; ±0 → ±0; a non-zero input below that range (the 1e-34 far-field velocities of a flow starting from rest)
-// raises `tiny`: the block then marks itself in the `redo` list and the SAFE=true instance of the kernel, launched right behind,
-// recomputes exactly the marked blocks with the IEEE division.  The upper end of the range is covered by the kernel's |u| ≤ 1e37
-// test (|5c+2d−u| ≤ 8e37), which also reports a diverged (non-finite) field.
-// SAFE: 0 = fast form, `tiny` raised outside its range; 1 = IEEE division; 2 = fast form with the IEEE division taken in place
-// outside its range (general mode: a wake's far field keeps denormal velocities for many steps, a second pass would run every step)
-template <int SAFE>
-__device__ __forceinline__ float div6_chk(float x, bool& tiny) {
-  if (SAFE == 1) return x / 6.f;
+// x/6.  Fast form (EXACT=false): the two FMAs of wl_kernels.cuh, proven equal to the IEEE division for 2^-100 ≤ |x| ≤ 3e38 by
+// the exhaustive on-device test (wl_selftest_div6); x = ±0 gives 0.  The kernel never sees an input outside that range: the
+// velocity field it reads was range-checked by the kernel that wrote it (f_correct_cfl, k_range_check, the halo push): every
+// value is 0 or 2^-77 ≤ |v| ≤ 1e37.  Then 5c+2d−u — sums of multiples of the quantum 2^(−77−23) — is 0 or at least 2^-100 in
+// magnitude, and below 8e37.  A field that fails the check (the 1e-34 far-field velocities of a flow starting from rest, denormals)
+// is routed, whole, to the EXACT=true instance of the kernel, which divides; see fm_conv4 below.
+template <bool EXACT>
+__device__ __forceinline__ float div6_c4(float x) {
+  if (EXACT) return x / 6.f;
   const float C = 0.16666667163372039794921875f;
   const float q0 = x * C;
   const float r = __fmaf_rn(-6.f, q0, x);
-  const float q = __fmaf_rn(r, C, q0);
-  const bool inr = fabsf(x) >= 7.888609052210118e-31f;
-  if (SAFE == 2) {
-    if (!inr && x != 0.f) return div6_slow(x);
-    return inr ? q : q0;
-  }
-  tiny = tiny || (!inr && x != 0.f);
-  return inr ? q : q0;  // ±0 → ±0 (= q0)
+  return __fmaf_rn(r, C, q0);
 }
+template <bool EXACT>
+__device__ __forceinline__ float2 div6_c4(const float2 x) {
+  if (EXACT) return make_float2(x.x / 6.f, x.y / 6.f);
+  const float2 C = splat2(0.16666667163372039794921875f);
+  const float2 q0 = mul2(x, C);
+  const float2 r = fma2(splat2(-6.f), q0, x);
+  return fma2(r, C, q0);
+}
+__device__ __forceinline__ float sign_one(float v) { return __uint_as_float((__float_as_uint(v) & 0x80000000u) | 0x3f800000u); }
+
 // ϕu(j, CI(I,i), u, û, λ) − ν ∂(j, CI(I,i), u) for an inner / periodic face (src/Flow.jl:8-11,52)
 //
 // quick(u,c,d) = median((5c+2d−u)/6, c, median(10c−9u, c, d))  (src/Flow.jl:6) is evaluated as a clamp: with a = (5c+2d−u)/6 and
@@ -55,17 +57,19 @@ __device__ __forceinline__ float div6_chk(float x, bool& tiny) {
 // mirroring (multiplying the three inputs by s = −1) is exact in IEEE arithmetic, so one code path serves both:
 // λ = s·min(max(min(a',b'), s·c), s·d) with s = sign(d−c).  d−c is ±(u[I]−u[I−δ]) with the sign of û, so s = sign(t·û).
 // (û = 0 gives conv = 0·λ = 0 whatever s is.)  min/max run on the half-rate ALU pipe, the multiplications on the FMA pipe.
-template <int LAM, int SAFE>
-__device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu, bool& bad) {
+// (±0: a clamp may return −0 where the nested median returns +0 and x/6 of −0 is +0 here; no later operation distinguishes
+// the two zeros, and they compare equal.)
+template <int LAM, bool EXACT>
+__device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0c, float up1, float nu) {
   const float t = u0c - um1;
   const float diff = nu * t;
   const bool pos = uf > 0.f;
   const float u = pos ? um2 : up1, c = pos ? um1 : u0c, d = pos ? u0c : um1;
   float lam;
   if (LAM == 0) {
-    const float s = __uint_as_float((__float_as_uint(t * uf) & 0x80000000u) | 0x3f800000u);
+    const float s = sign_one(t * uf);
     const float cs = c * s, ds = d * s, us = u * s;
-    const float a = div6_chk<SAFE>(5.f * cs + 2.f * ds - us, bad);
+    const float a = div6_c4<EXACT>(5.f * cs + 2.f * ds - us);
     const float b = 10.f * cs - 9.f * us;
     lam = s * fminf(fmaxf(fminf(a, b), cs), ds);
   } else if (LAM == 1) {
@@ -75,30 +79,69 @@ __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0
   }
   return uf * lam - diff;
 }
-template <int LAM, int SAFE>
-__device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, float nu,
-                                          bool& bad) {
-  return make_float4(flux_p<LAM, SAFE>(uf.x, um2.x, um1.x, u0c.x, up1.x, nu, bad), flux_p<LAM, SAFE>(uf.y, um2.y, um1.y, u0c.y, up1.y, nu, bad),
-                     flux_p<LAM, SAFE>(uf.z, um2.z, um1.z, u0c.z, up1.z, nu, bad), flux_p<LAM, SAFE>(uf.w, um2.w, um1.w, u0c.w, up1.w, nu, bad));
+// The same for two cells at once: every Float32 operation of flux_p on both halves of a register pair (add2/mul2/fma2 are the
+// scalar IEEE operations, issued once for two cells); selections, min/max and the sign stay scalar (no packed forms exist).
+template <int LAM, bool EXACT>
+__device__ __forceinline__ float2 flux_p2(const float2 uf, const float2 um2, const float2 um1, const float2 u0c, const float2 up1, const float2 nu2) {
+  const float2 t = sub2(u0c, um1);
+  const float2 diff = mul2(nu2, t);
+  const bool px = uf.x > 0.f, py = uf.y > 0.f;
+  const float2 u = make_float2(px ? um2.x : up1.x, py ? um2.y : up1.y);
+  const float2 c = make_float2(px ? um1.x : u0c.x, py ? um1.y : u0c.y);
+  const float2 d = make_float2(px ? u0c.x : um1.x, py ? u0c.y : um1.y);
+  float2 lam;
+  if (LAM == 0) {
+    const float2 tu = mul2(t, uf);
+    const float2 s = make_float2(sign_one(tu.x), sign_one(tu.y));
+    const float2 cs = mul2(c, s), ds = mul2(d, s), us = mul2(u, s);
+    const float2 a = div6_c4<EXACT>(sub2(add2x(mul2(splat2(5.f), cs), mul2(splat2(2.f), ds)), us));  // add2x / sub2x: see the contraction hazard
+    const float2 b = sub2x(mul2(splat2(10.f), cs), mul2(splat2(9.f), us));                             // in wl_common.cuh
+    lam = mul2(s, make_float2(fminf(fmaxf(fminf(a.x, b.x), cs.x), ds.x), fminf(fmaxf(fminf(a.y, b.y), cs.y), ds.y)));
+  } else if (LAM == 1) {
+    lam = mul2(add2(c, d), splat2(0.5f));  // cds: (c+d)/2
+  } else {
+    lam.x = (c.x <= fminf(u.x, d.x) || c.x >= fmaxf(u.x, d.x)) ? c.x : c.x + (d.x - c.x) * (c.x - u.x) / (d.x - u.x);  // vanLeer
+    lam.y = (c.y <= fminf(u.y, d.y) || c.y >= fmaxf(u.y, d.y)) ? c.y : c.y + (d.y - c.y) * (c.y - u.y) / (d.y - u.y);
+  }
+  return sub2x(mul2(uf, lam), diff);
 }
+template <int LAM, bool EXACT>
+__device__ __forceinline__ float4 flux_p4(const float4& uf, const float4& um2, const float4& um1, const float4& u0c, const float4& up1, const float2 nu2) {
+  return cat2(flux_p2<LAM, EXACT>(lo2(uf), lo2(um2), lo2(um1), lo2(u0c), lo2(up1), nu2),
+              flux_p2<LAM, EXACT>(hi2(uf), hi2(um2), hi2(um1), hi2(u0c), hi2(up1), nu2));
+}
+// (a + b)/2 on four cells (û of a face, src/Flow.jl:3): /2 is the exact multiplication by 0.5
 __device__ __forceinline__ float4 avg4(const float4& a, const float4& b) {
-  return make_float4((a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f, (a.w + b.w) / 2.f);
+  const float2 h = splat2(0.5f);
+  return cat2(mul2(add2(lo2(a), lo2(b)), h), mul2(add2(hi2(a), hi2(b)), h));
+}
+// û of the x component's flux: the x-shifted average ((a.x + left)/2, (a.y + a.x)/2, (a.z + a.y)/2, (a.w + a.z)/2)
+__device__ __forceinline__ float4 avg4_shift(const float4& a, float left) {
+  const float2 h = splat2(0.5f);
+  return cat2(mul2(add2(lo2(a), make_float2(left, a.x)), h), mul2(add2(hi2(a), make_float2(a.y, a.z)), h));
+}
+__device__ __forceinline__ void acc_add(float4& r, const float4& f) {
+  const float2 a = add2(lo2(r), lo2(f)), b = add2(hi2(r), hi2(f));
+  r = cat2(a, b);
+}
+__device__ __forceinline__ void acc_sub(float4& r, const float4& f) {
+  const float2 a = sub2(lo2(r), lo2(f)), b = sub2(hi2(r), hi2(f));
+  r = cat2(a, b);
 }
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
 
-template <int LAM, bool SAFE>
+// rflag[0]: the velocity field `ua` holds a value outside the fast division's input range (set by the kernel that wrote the field,
+// cleared here).  The two instances of the kernel are launched back to back on the same grid: the one whose EXACT does not match the
+// flag returns at once (≈3 µs), so the host never has to look at the flag.  rflag[1]: block ticket of the EXACT instance.
+template <int LAM, bool EXACT>
 __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__ Grid g, const float* __restrict__ ua, const float* __restrict__ u0,
                                                          float* __restrict__ out, const float* __restrict__ dtp, float nu, int zchunk, int corrector, RedBuf R,
-                                                         int slot, const float* __restrict__ uext, int* __restrict__ flag, int* __restrict__ redo, int vgx,
-                                                         int vgy) {
-  // redo[0] = number of marked blocks, redo[1…] = their linear indices.  The fast launch runs one block per tile; the SAFE launch
-  // is a small persistent grid that walks the list (normally empty: it exits at once).
-  for (int it = SAFE ? (int)blockIdx.x : 0; it < (SAFE ? redo[0] : 1); it += SAFE ? (int)gridDim.x : 1) {
-  const int blin = SAFE ? redo[1 + it] : (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-  const int vbx = SAFE ? blin % vgx : (int)blockIdx.x, vby = SAFE ? (blin / vgx) % vgy : (int)blockIdx.y, vbz = SAFE ? blin / (vgx * vgy) : (int)blockIdx.z;
+                                                         int slot, const float* __restrict__ uext, int* __restrict__ rflag) {
+  if ((*reinterpret_cast<volatile int*>(rflag) != 0) != EXACT) return;
+  const int vbx = blockIdx.x, vby = blockIdx.y, vbz = blockIdx.z;
   extern __shared__ float4 smem4[];
   float* const T = reinterpret_cast<float*>(smem4);      // [C4RING][3][C4H][C4W]
   float* const Fy = T + C4RING * C4PS;                    // [2][3][C4TY+1][32] float4: lower y fluxes of planes z, z+1 (row C4TY: the block's upper edge)
@@ -109,7 +152,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
   const int z0 = 1 + zchunk * vbz, z1 = min(z0 + zchunk, g.N[2] - 1);
   const bool on = x0 <= g.N[0] - 2 && y <= g.N[1] - 2;
   const float dt = *dtp;
-  bool bad = false, tiny = false;
+  const float2 nu2 = splat2(nu), dt2 = splat2(dt);
 
   // ---- tile fill: every plane is fetched with the same per-thread float4 elements ----
   int gof[C4FILL], sof[C4FILL];  // in-plane global offset / offset inside a component plane of the tile (-1: none)
@@ -218,7 +261,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
           other = src[g.xo + min(xx, g.N[0] - 2) + (i64)g.px * min(y, g.N[1] - 2)];
         }
         const float* ei = e + lane * C4CS;
-        fex = flux_p<LAM, SAFE>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu, tiny);
+        fex = flux_p<LAM, EXACT>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -227,10 +270,14 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
         const float rr = p0[c * C4CS + 4];
         own[c] = a;
         float4 uf;
-        if (c == 0) uf = make_float4((a0.x + l2.y) / 2.f, (a0.y + a0.x) / 2.f, (a0.z + a0.y) / 2.f, (a0.w + a0.z) / 2.f);
+        if (c == 0) uf = avg4_shift(a0, l2.y);
         else if (c == 1) uf = avg4(a0, b1);
         else uf = avg4(a0, m1[0]);
-        const float4 lo = flux_p4<LAM, SAFE>(uf, make_float4(l2.x, l2.y, a.x, a.y), make_float4(l2.y, a.x, a.y, a.z), a, make_float4(a.y, a.z, a.w, rr), nu, tiny);
+        // the x stencil of the four cells out of six distinct pairs: (l2), (l2.y,a.x), (a.x,a.y), (a.y,a.z), (a.z,a.w), (a.w,rr)
+        const float2 sA = make_float2(l2.y, a.x), sB = make_float2(a.y, a.z), sC = make_float2(a.w, rr);
+        const float2 f01 = flux_p2<LAM, EXACT>(lo2(uf), l2, sA, lo2(a), sB, nu2);
+        const float2 f23 = flux_p2<LAM, EXACT>(hi2(uf), lo2(a), sB, hi2(a), sC, nu2);
+        const float4 lo = cat2(f01, f23);
         float hi = __shfl_down_sync(FULLMASK, lo.x, 1);
         const float e = __shfl_sync(FULLMASK, fex, c);
         if (lane == 31) hi = e;
@@ -245,9 +292,6 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 3; c++) own[c] = ld4(p0 + c * C4CS);
     }
-#pragma unroll
-    for (int c = 0; c < 3; c++)  // keeps |5c+2d−u| below the upper end of div6_chk's proven range; catches NaN and Inf (a diverged run)
-      bad = bad || !(fabsf(own[c].x) <= 1e37f) || !(fabsf(own[c].y) <= 1e37f) || !(fabsf(own[c].z) <= 1e37f) || !(fabsf(own[c].w) <= 1e37f);
     // ---- y fluxes: lower flux of the own row from the previous step, upper flux = next row's lower flux ----
     float4 Fy2lo = f4zero();
     if (live) {
@@ -255,14 +299,8 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       for (int c = 0; c < 3; c++) {
         const float4 lo = *fy4(z & 1, c, ty);
         const float4 hi = *fy4(z & 1, c, lastrow ? C4TY : ty + 1);
-        r[c].x += lo.x;
-        r[c].y += lo.y;
-        r[c].z += lo.z;
-        r[c].w += lo.w;
-        r[c].x -= hi.x;
-        r[c].y -= hi.y;
-        r[c].z -= hi.z;
-        r[c].w -= hi.w;
+        acc_add(r[c], lo);
+        acc_sub(r[c], hi);
         if (c == 2) Fy2lo = lo;
       }
     }
@@ -276,19 +314,13 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
         const float4 a1 = c == 2 ? w1 : ld4(p1 + c * C4CS);
         const float4 a2 = ld4(p2 + c * C4CS);
         float4 uf;
-        if (c == 0) uf = make_float4((w1.x + wl) / 2.f, (w1.y + w1.x) / 2.f, (w1.z + w1.y) / 2.f, (w1.w + w1.z) / 2.f);
+        if (c == 0) uf = avg4_shift(w1, wl);
         else if (c == 1) uf = avg4(w1, wd);
         else uf = avg4(w1, own[2]);
-        const float4 hi = flux_p4<LAM, SAFE>(uf, m1[c], own[c], a1, a2, nu, tiny);
+        const float4 hi = flux_p4<LAM, EXACT>(uf, m1[c], own[c], a1, a2, nu2);
         if (live) {
-          r[c].x += Fz[c].x;
-          r[c].y += Fz[c].y;
-          r[c].z += Fz[c].z;
-          r[c].w += Fz[c].w;
-          r[c].x -= hi.x;
-          r[c].y -= hi.y;
-          r[c].z -= hi.z;
-          r[c].w -= hi.w;
+          acc_add(r[c], Fz[c]);
+          acc_sub(r[c], hi);
         }
         if (live && c == 2) {
           // periodic images of the stale Φ the reference leaves on the upper ghost cells of σ (they enter maximum(σ) in CFL,
@@ -311,9 +343,12 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const float4 b = corrector ? ub[c] : own[c];  // predictor: ua is u⁰ itself, already in the tile
-        float4 f = make_float4(b.x + dt * r[c].x, b.y + dt * r[c].y, b.z + dt * r[c].z, b.w + dt * r[c].w);
-        if (corrector) f = make_float4((own[c].x + f.x) * 0.5f, (own[c].y + f.y) * 0.5f, (own[c].z + f.z) * 0.5f, (own[c].w + f.w) * 0.5f);
-        st4(out + o + c * g.sc, f);
+        float2 f01 = add2x(lo2(b), mul2(dt2, lo2(r[c]))), f23 = add2x(hi2(b), mul2(dt2, hi2(r[c])));
+        if (corrector) {
+          f01 = mul2(add2(lo2(own[c]), f01), splat2(0.5f));
+          f23 = mul2(add2(hi2(own[c]), f23), splat2(0.5f));
+        }
+        st4(out + o + c * g.sc, cat2(f01, f23));
       }
     }
     // ---- lower y fluxes of plane z+1 for the next step (the block's last row also computes its upper flux) ----
@@ -333,10 +368,10 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
           const float4 s0 = c == 1 ? v1 : ld4(q1 + c * C4CS);
           const float4 sp = ld4(q1 + c * C4CS + C4W);
           float4 uf;
-          if (c == 0) uf = make_float4((v1.x + vl) / 2.f, (v1.y + v1.x) / 2.f, (v1.z + v1.y) / 2.f, (v1.w + v1.z) / 2.f);
+          if (c == 0) uf = avg4_shift(v1, vl);
           else if (c == 1) uf = avg4(v1, vd);
           else uf = avg4(v1, vz);
-          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM, SAFE>(uf, s2, s1, s0, sp, nu, tiny);
+          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM, EXACT>(uf, s2, s1, s0, sp, nu2);
         }
       }
     }
@@ -345,22 +380,16 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
     cp_async_wait_all();
     __syncthreads();
   }
-  if (bad) *flag = 1;
-  if (!SAFE) {
-    // a block that met an input outside the fast division's range leaves its results to the SAFE launch (and keeps its Φ maximum out
-    // of this launch's reduction)
-    const int any = __syncthreads_or(tiny ? 1 : 0);
-    if (any && tid == 0) redo[1 + atomicAdd(redo, 1)] = blin;
-    double v[1] = {any ? 0.0 : (double)gmax}, fin[1];
+  {
+    double v[1] = {(double)gmax}, fin[1];
     grid_reduce<RED_MAX, 1>(v, R, slot, fin);
-  } else {
-    // the maximum of non-negative doubles is the maximum of their bit patterns: merge into the fast launch's result
-    float m = gmax;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(FULLMASK, m, o));
-    if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(R.out + slot), (unsigned long long)__double_as_longlong((double)m));
-    if (tid == 0) atomicAdd(flag + 1, 1);  // [1] counts the recomputed blocks (diagnostics)
-    __syncthreads();                       // the next listed block reuses the shared-memory ring
   }
+  if (EXACT && tid == 0) {  // the last block of the EXACT instance re-arms the fast path for the next field
+    __threadfence();
+    const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(reinterpret_cast<unsigned*>(rflag + 1), 1u) == nb - 1) {
+      rflag[1] = 0;
+      rflag[0] = 0;
+    }
   }
 }

@@ -734,11 +734,12 @@ template <bool CFLQ>
 __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ x,
                                                             const float* __restrict__ ui, float* __restrict__ uo, float* __restrict__ p,
                                                             const float* __restrict__ dtp, float wdt, int zchunk, float nu, float* __restrict__ dt_out,
-                                                            RedBuf R, int slot, int slot_ghost, int finalize) {
+                                                            RedBuf R, int slot, int slot_ghost, int finalize, int* __restrict__ flags) {
   const Frame f = make_frame(g, zchunk);
   const float dt = wdt * (*dtp);
   const float L0 = c.Lc[0], L1 = c.Lc[1], L2 = c.Lc[2];
   double m = 0.0;
+  RangeAcc ra;  // range of the velocities this thread writes (the next reader is the flux kernel, see range_note)
   float4 zm = f4zero(), xc = f4zero(), uz = f4zero();
   if (f.on) {
     zm = ld4(x + f.row + g.s[2] * zwrap_lo(g, f.z0) + f.x0);
@@ -797,6 +798,9 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_consta
       st4(uo + o, a);
       st4(uo + g.sc + o, b);
       st4(uo + 2 * g.sc + o, d);
+      ra.add4(a);
+      ra.add4(b);
+      ra.add4(d);
       st4(p + o, make_float4(xc.x / dt, xc.y / dt, xc.z / dt, xc.w / dt));
       float4 s = f4zero();  // flux_out (f_cfl)
       if (CFLQ) {
@@ -819,6 +823,7 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_consta
     xc = xzp;
     uz = uzp;
   }
+  ra.publish(flags);
   if (!CFLQ) return;  // plain out-of-place correction (predictor): measurably faster than correcting u in place
   double v[1] = {m}, fin[1];
   if (grid_reduce<RED_MAX, 1>(v, R, slot, fin) && finalize) {

@@ -786,7 +786,8 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 }
 __device__ __forceinline__ void st_flag_sys(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int seq, int* my, int* peer_lo, int* peer_hi, long long timeout) {
+__global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int seq, int* my, int* peer_lo, int* peer_hi, long long timeout,
+                                                   const int* myflags, int* flags_lo, int* flags_hi) {
   // A timeout is FATAL for the whole ring: the rank that gave up raises the error word of its own mailbox and of both neighbours'
   // (my[5]), never copies and never signals `arrived`, and every later exchange on a rank whose error word is set returns at once;
   // the host reads the word after every step (check_flags) and fails the call.  NCCL collectives block without a bound anyway,
@@ -795,6 +796,12 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int 
   if (threadIdx.x == 0) {
     int good = ld_flag(my + 5) == 0;
     if (good && blockIdx.x == 0) {
+      // velocity planes: a field that failed its range check (range_note, wl_common.cuh) fails it for the neighbours that read
+      // its halo planes too — the word lands before `arrived`, i.e. before the receiver's flux kernel can start
+      if (myflags && ld_flag(myflags + 2) != 0) {
+        if (flags_lo) st_flag_sys(flags_lo + 2, 1);
+        if (flags_hi) st_flag_sys(flags_hi + 2, 1);
+      }
       __threadfence_system();
       if (peer_lo) st_flag_sys(peer_lo + 1, seq);  // I am the upper neighbour of my lower neighbour
       if (peer_hi) st_flag_sys(peer_hi + 0, seq);
@@ -839,4 +846,12 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int 
       __threadfence_system();
     }
   }
+}
+
+// Range check of a velocity field the library did not write itself (uploads, wl_apply_bc, kernels without the built-in check):
+// raises flags[2] / flags[0] as described at range_note (wl_common.cuh).  n4 = number of float4 to scan.
+__global__ void __launch_bounds__(256) k_range_check(const float4* __restrict__ a, long long n4, int* __restrict__ flags) {
+  RangeAcc ra;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) ra.add4(a[i]);
+  ra.publish(flags);
 }
