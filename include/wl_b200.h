@@ -69,6 +69,7 @@ enum {
   WL_FLAG_NO_VSMOOTH = 16,   /* constant-coefficient mode: separate prolongation / GaussSeidelRB! / increment launches instead of f_vsmooth */
   WL_FLAG_NO_CONV4 = 32,     /* constant-coefficient mode: the one-cell-per-thread flux kernel fm_conv instead of fm_conv4 */
   WL_FLAG_NO_FUSED_UNI = 64, /* constant-coefficient mode: f_div_residual / f_jacobi / f_correct + f_cfl instead of their fused forms */
+  WL_FLAG_NO_TINY = 256,     /* run the coarsest levels (≤ 8192 cells) inside the cooperative coarse-level kernel instead of the one-block kernel */
   WL_FLAG_NO_SEMI = 128,     /* general mode: always read the face coefficients L (no semi-uniform march blocks, no body-free BDIM blocks) */
 };
 

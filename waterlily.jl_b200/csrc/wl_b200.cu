@@ -187,6 +187,9 @@ struct wl_handle {
   // V, μ₀ or μ₁ were written through the ABI since the hierarchy was built: every entry point that solves or steps rebuilds it
   // first (update!(pois), src/MultiLevelPoisson.jl:79-86), so a host that forgets wl_update cannot step with stale D/iD/coarse L
   bool pois_dirty = false;
+  bool tiny_on = true;     // uniform mode: levels ≤ 8192 cells on one block in shared memory (k_tiny_uni); WL_FLAG_NO_TINY: all in k_small_levels
+  int tiny_from = 0;       // first level k_tiny_uni can take (0 = none): fully coarsened chain of 3-D periodic levels of ≤ 8192 cells
+  bool attr_tiny = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
   bool jacobi2 = true;     // uniform mode, level 1: f_jacobi_uni2 (WL_JACOBI2=0: f_jacobi<true>)
   bool divres_uni = true;  // uniform mode: f_divres_uni (WL_DIVRES_UNI=0: f_div_residual<true>)
@@ -1018,7 +1021,8 @@ static void emit_gs(wl_handle* h, Level& l, int x_is_zero) {
   o.x_is_zero = x_is_zero;
   h->ops.push_back(o);
 }
-static void emit_vcycle(wl_handle* h, size_t li) {
+// `tiny` > 0: levels ≥ tiny are run by k_tiny_uni: the recursion stops above them and *split marks the place in the list
+static void emit_vcycle(wl_handle* h, size_t li, int tiny, int* split) {
   Level& fine = h->levels[li];
   Level& coarse = h->levels[li + 1];
   // Jacobi! (+ restrict!)
@@ -1044,8 +1048,12 @@ static void emit_vcycle(wl_handle* h, size_t li) {
     h->ops.push_back(o);
   }
   const bool last = (li + 2 >= h->levels.size());
-  if (!last) emit_vcycle(h, li + 1);
-  emit_gs(h, coarse, last ? 1 : 0);
+  if (tiny > 0 && (int)li + 1 == tiny) {
+    *split = (int)h->ops.size();  // Vcycle!(l=tiny) and smooth!(levels[tiny]) happen here, in k_tiny_uni
+  } else {
+    if (!last) emit_vcycle(h, li + 1, tiny, split);
+    emit_gs(h, coarse, last ? 1 : 0);
+  }
   {
     const bool fp = fine.fast && coarse.fullc;
     SmallOp o = op_base(h, fine, fp ? OP_F_PROLONG : OP_K_PROLONG);
@@ -1055,27 +1063,71 @@ static void emit_vcycle(wl_handle* h, size_t li) {
     h->ops.push_back(o);
   }
 }
-// Runs "Vcycle!(ml; l=small_from) ; smooth!(levels[small_from])" — everything a V-cycle does at and below level small_from.
+static int launch_tiny(wl_handle* h, const float* wp) {
+  TinyArgs a;
+  memset(&a, 0, sizeof a);
+  const size_t T = (size_t)h->tiny_from;
+  a.nlev = (int)(h->levels.size() - T);
+  size_t floats = 0;
+  for (int q = 0; q < a.nlev; q++) {
+    const Level& l = h->levels[T + q];
+    const Coef k = l.coef(true);
+    for (int d = 0; d < 3; d++) {
+      a.n[q][d] = l.g.N[d] - 2;
+      a.L[q][d] = k.Lc[d];
+    }
+    a.D[q] = k.Dc;
+    a.iD[q] = k.iDc;
+    floats += (size_t)3 * a.n[q][0] * a.n[q][1] * a.n[q][2];
+  }
+  Level& l0 = h->levels[T];
+  a.g0 = l0.g;
+  a.r0 = l0.r;
+  a.x0 = l0.x;
+  a.r0out = l0.r;
+  a.wp = wp;
+  if (!h->attr_tiny) {
+    cudaFuncSetAttribute(k_tiny_uni, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    h->attr_tiny = true;
+  }
+  prof_begin(h, "k_tiny_uni");
+  k_tiny_uni<<<1, 1024, floats * sizeof(float), h->st>>>(a);
+  prof_end(h);
+  h->launches++;
+  return 0;
+}
+// Runs "Vcycle!(ml; l=small_from) ; smooth!(levels[small_from])" — everything a V-cycle does at and below level small_from:
+// the levels ≥ small_from in the cooperative k_small_levels, except (uniform mode) the innermost levels ≥ tiny_from, which
+// k_tiny_uni runs on one block in shared memory between the two halves of the list.
 static int run_small_levels(wl_handle* h, const float* wp) {
   const size_t ls = (size_t)h->small_from;
+  const int tiny = (h->uni && h->tiny_on) ? h->tiny_from : 0;
+  if (tiny > 0 && (size_t)tiny <= ls) return launch_tiny(h, wp);  // the whole coarse end is tiny
   h->ops.clear();
+  int split = -1;
   const bool last = (ls + 1 >= h->levels.size());
-  if (!last) emit_vcycle(h, ls);
+  if (!last) emit_vcycle(h, ls, tiny, &split);
   emit_gs(h, h->levels[ls], last ? 1 : 0);
   const int nops = (int)h->ops.size();
   if (nops > 256) return fail("too many coarse-level operations (%d)", nops);
   memcpy(h->h_ops, h->ops.data(), nops * sizeof(SmallOp));
   CK(cudaMemcpyAsync(h->d_ops, h->h_ops, nops * sizeof(SmallOp), cudaMemcpyHostToDevice, h->st));
-  const SmallOp* dops = h->d_ops;
-  int n = nops;
-  void* args[] = {(void*)&dops, (void*)&n, (void*)&wp};
-  prof_begin(h, "k_small_levels");
-  cudaError_t e = h->uni ? cudaLaunchCooperativeKernel((void*)k_small_levels<true>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st)
-                         : cudaLaunchCooperativeKernel((void*)k_small_levels<false>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st);
-  prof_end(h);
-  h->launches++;
-  if (e != cudaSuccess) return fail("cooperative launch of k_small_levels: %s", cudaGetErrorString(e));
-  return 0;
+  auto coop = [&](int first, int n) -> int {
+    if (n <= 0) return 0;
+    const SmallOp* dops = h->d_ops + first;
+    void* args[] = {(void*)&dops, (void*)&n, (void*)&wp};
+    prof_begin(h, "k_small_levels");
+    cudaError_t e = h->uni ? cudaLaunchCooperativeKernel((void*)k_small_levels<true>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st)
+                           : cudaLaunchCooperativeKernel((void*)k_small_levels<false>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st);
+    prof_end(h);
+    h->launches++;
+    if (e != cudaSuccess) return fail("cooperative launch of k_small_levels: %s", cudaGetErrorString(e));
+    return 0;
+  };
+  if (split < 0) return coop(0, nops);
+  TRY(coop(0, split));
+  TRY(launch_tiny(h, wp));
+  return coop(split, nops - split);
 }
 
 // Vcycle!(ml;l,ω)  src/MultiLevelPoisson.jl:88-101
@@ -1632,6 +1684,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->vsmooth = !(cfg->flags & WL_FLAG_NO_VSMOOTH);
   h->conv4 = !(cfg->flags & WL_FLAG_NO_CONV4);
   h->semi_on = !(cfg->flags & WL_FLAG_NO_SEMI);
+  h->tiny_on = !(cfg->flags & WL_FLAG_NO_TINY);
   h->fuse_cfl = h->divres_uni = h->jacobi2 = !(cfg->flags & WL_FLAG_NO_FUSED_UNI);
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);
@@ -1702,6 +1755,16 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
           h->small_from = (int)i;
           break;
         }
+      }
+      if (h->small_from > 0) {
+        const int nl = (int)h->levels.size();
+        int t = nl;  // grow the tiny range upwards from the coarsest level while the chain stays fully coarsened, periodic and whole
+        auto ok = [&](int q) {
+          const Level& l = h->levels[q];
+          return !l.slab && l.g.per[0] && l.g.per[1] && l.g.per[2] && (i64)l.g.N[0] * l.g.N[1] * l.g.N[2] <= 8192;
+        };
+        while (t - 1 >= h->small_from && t - 1 >= 1 && nl - (t - 1) <= TINY_MAXLEV && ok(t - 1) && (t == nl || h->levels[t].fullc)) t--;
+        h->tiny_from = t < nl ? t : 0;
       }
       if (h->small_from > 0) {
         int dev = 0, nsm = 0, coop = 0, per_sm = 0;

@@ -53,7 +53,7 @@ __device__ __forceinline__ float sign_one(float v) { return __uint_as_float((__f
 //
 // quick(u,c,d) = median((5c+2d−u)/6, c, median(10c−9u, c, d))  (src/Flow.jl:6) is evaluated as a clamp: with a = (5c+2d−u)/6 and
 // b = 10c−9u the nested median equals min(max(min(a,b), c), d) when c ≤ d and max(min(max(a,b), c), d) when d ≤ c (lattice
-// identities on ordered values: same value, three min/max instead of eight).  The second case is the first one mirrored, and
+// identities on ordered values: same value, three min/max instead of eight; min(max(X,c),d) = max(min(X,d),c) for c ≤ d).  The second case is the first one mirrored, and
 // mirroring (multiplying the three inputs by s = −1) is exact in IEEE arithmetic, so one code path serves both:
 // λ = s·min(max(min(a',b'), s·c), s·d) with s = sign(d−c).  d−c is ±(u[I]−u[I−δ]) with the sign of û, so s = sign(t·û).
 // (û = 0 gives conv = 0·λ = 0 whatever s is.)  min/max run on the half-rate ALU pipe, the multiplications on the FMA pipe.
@@ -71,7 +71,7 @@ __device__ __forceinline__ float flux_p(float uf, float um2, float um1, float u0
     const float cs = c * s, ds = d * s, us = u * s;
     const float a = div6_c4<EXACT>(5.f * cs + 2.f * ds - us);
     const float b = 10.f * cs - 9.f * us;
-    lam = s * fminf(fmaxf(fminf(a, b), cs), ds);
+    lam = s * fmaxf(fminf(fminf(a, b), ds), cs);  // clamp(min(a,b), cs, ds) with cs ≤ ds, as max(min3(a,b,ds), cs): FMNMX3 + FMNMX
   } else if (LAM == 1) {
     lam = (c + d) / 2.f;  // cds
   } else {
@@ -96,7 +96,8 @@ __device__ __forceinline__ float2 flux_p2(const float2 uf, const float2 um2, con
     const float2 cs = mul2(c, s), ds = mul2(d, s), us = mul2(u, s);
     const float2 a = div6_c4<EXACT>(sub2(add2x(mul2(splat2(5.f), cs), mul2(splat2(2.f), ds)), us));  // add2x / sub2x: see the contraction hazard
     const float2 b = sub2x(mul2(splat2(10.f), cs), mul2(splat2(9.f), us));                             // in wl_common.cuh
-    lam = mul2(s, make_float2(fminf(fmaxf(fminf(a.x, b.x), cs.x), ds.x), fminf(fmaxf(fminf(a.y, b.y), cs.y), ds.y)));
+    // clamp(min(a,b), cs, ds) with cs ≤ ds written as max(min3(a, b, ds), cs): one three-input FMNMX3 and one FMNMX
+    lam = mul2(s, make_float2(fmaxf(fminf(fminf(a.x, b.x), ds.x), cs.x), fmaxf(fminf(fminf(a.y, b.y), ds.y), cs.y)));
   } else if (LAM == 1) {
     lam = mul2(add2(c, d), splat2(0.5f));  // cds: (c+d)/2
   } else {
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
 
   float4 Fz[3] = {f4zero(), f4zero(), f4zero()};  // lower z fluxes of the current plane
   float gmax = 0.f;
+  float e0prev = 0.f;  // u_x of the cell beyond the warp's segment (xb+128, y) on the previous plane: û of lane 2's extra z-momentum face
   const bool lastrow = ty == C4TY - 1;
   for (int z = z0 - 1; z < z1; z++) {
     const bool live = z >= z0;
@@ -249,17 +251,8 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       float fex = 0.f;                                // the face beyond the warp's last cell: lanes 0-2 compute one component each
       if (lane < 3) {
         const float* e = T + ((z + 1024) & (C4RING - 1)) * C4PS + (ty + 2) * C4W + 4 + 128;  // cell xb+128 of u_x
-        float other;
-        if (lane == 0) other = e[-1];
-        else if (lane == 1) other = e[-C4W];
-        else {  // plane z-1 is not in the ring any more: one scalar from global memory
-          const float* src;
-          i64 cs;
-          plane_src(z - 1, src, cs);
-          int xx = xb + 128;
-          if (xx > g.N[0] - 2) xx -= g.N[0] - 2;
-          other = src[g.xo + min(xx, g.N[0] - 2) + (i64)g.px * min(y, g.N[1] - 2)];
-        }
+        // (plane z-1 has left the ring: its value was kept in a register when it was plane z)
+        const float other = lane == 0 ? e[-1] : (lane == 1 ? e[-C4W] : e0prev);
         const float* ei = e + lane * C4CS;
         fex = flux_p<LAM, EXACT>((e[0] + other) / 2.f, ei[-2], ei[-1], ei[0], ei[1], nu);
       }
@@ -292,6 +285,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 3; c++) own[c] = ld4(p0 + c * C4CS);
     }
+    e0prev = T[((z + 1024) & (C4RING - 1)) * C4PS + (ty + 2) * C4W + 4 + 128];
     // ---- y fluxes: lower flux of the own row from the previous step, upper flux = next row's lower flux ----
     float4 Fy2lo = f4zero();
     if (live) {
@@ -352,17 +346,22 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       }
     }
     // ---- lower y fluxes of plane z+1 for the next step (the block's last row also computes its upper flux) ----
+    // The upper flux of the block's last row (row C4TY of Fy) is one more row of work: its three components go to the last three
+    // warps, one each, so that no warp carries a whole extra row into the plane barrier.
     if (z + 1 < z1) {
-      const int nrow = lastrow ? 2 : 1;
+      const int cex = ty - (C4TY - 3);  // component of the edge row this warp computes (< 0: none)
+      const int nrow = cex >= 0 ? 2 : 1;
       for (int k = 0; k < nrow; k++) {
-        const float* q1 = p1 + k * C4W;
-        const float* q0 = p0 + k * C4W;
+        const int dr = k * (C4TY - ty);  // rows above the own row
+        const float* q1 = p1 + dr * C4W;
+        const float* q0 = p0 + dr * C4W;
         const float4 v1 = ld4(q1 + C4CS);             // u_y on plane z+1, row y+k
         const float vl = q1[C4CS - 1];                //   … one cell to the left
         const float4 vd = ld4(q1 + C4CS - C4W);       //   … one row down
         const float4 vz = ld4(q0 + C4CS);             //   … one plane down (plane z)
 #pragma unroll
         for (int c = 0; c < 3; c++) {
+          if (k == 1 && c != cex) continue;
           const float4 s2 = ld4(q1 + c * C4CS - 2 * C4W);
           const float4 s1 = c == 1 ? vd : ld4(q1 + c * C4CS - C4W);
           const float4 s0 = c == 1 ? v1 : ld4(q1 + c * C4CS);
@@ -371,7 +370,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
           if (c == 0) uf = avg4_shift(v1, vl);
           else if (c == 1) uf = avg4(v1, vd);
           else uf = avg4(v1, vz);
-          *fy4((z + 1) & 1, c, ty + k) = flux_p4<LAM, EXACT>(uf, s2, s1, s0, sp, nu2);
+          *fy4((z + 1) & 1, c, ty + dr) = flux_p4<LAM, EXACT>(uf, s2, s1, s0, sp, nu2);
         }
       }
     }

@@ -1498,3 +1498,185 @@ __global__ void __launch_bounds__(32 * FTY, 4) k_small_levels(const SmallOp* __r
     grid.sync();
   }
 }
+
+// ================================================================================================
+// k_tiny_uni — the innermost levels of the V-cycle (≤ 8192 cells: 18³ and coarser) of uniform mode in ONE block, in shared memory.
+// A grid-wide barrier of k_small_levels costs ≈2.5 µs — more than an operation on such a level — and the coarse end of a V-cycle
+// is nine operations per level.  Here the levels live in shared memory as dense interior-only arrays (every direction is periodic
+// in uniform mode: neighbours wrap, ghosts do not exist), one block of 1024 threads runs
+//     Vcycle!(ml; l=T) ; smooth!(levels[T])            (src/MultiLevelPoisson.jl:88-101,106)
+// between block barriers, reading r of level T from global memory and leaving x (and r) of level T there.  The arithmetic is that
+// of the general bodies in wl_kernels.cuh (b_k_jacobi, b_k_restrict, b_k_gs_init, b_k_gs_sweep, b_k_increment, b_k_prolong_inc)
+// with the level's uniform coefficients — same operations, same order, same bits.
+// ================================================================================================
+#define TINY_MAXLEV 6
+struct TinyArgs {
+  int nlev;
+  int n[TINY_MAXLEV][3];  // interior sizes, all even
+  float L[TINY_MAXLEV][3], D[TINY_MAXLEV], iD[TINY_MAXLEV];
+  Grid g0;         // layout of level T in global memory
+  const float* r0; // its residual (input)
+  float* x0;       // its solution (output)
+  float* r0out;    // its residual after the smoother (output, for observers)
+  const float* wp; // ω
+};
+struct TinyLvl {
+  float *X, *R, *E;
+  int n0, n1, n2, cells;
+  unsigned m0, m1, mh;  // ⌈2³²/n0⌉, ⌈2³²/n1⌉, ⌈2³²/(n0/2)⌉: c / n = umulhi(c, m) exactly for c·n < 2³² (cells ≤ 8192)
+  float L0, L1, L2, D, iD;
+  // cell index → (i, j, k) with two multiply-high divisions
+  __device__ __forceinline__ void ijk(int c, int& i, int& j, int& k) const {
+    const int row = (int)__umulhi((unsigned)c, m0);
+    i = c - row * n0;
+    k = (int)__umulhi((unsigned)row, m1);
+    j = row - k * n1;
+  }
+};
+__host__ __device__ inline unsigned tiny_magic(int n) { return n <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n); }
+__device__ __forceinline__ int tiny_wrap(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
+
+// GaussSeidelRB!(p; it=4, ω) + increment! (src/Poisson.jl:141-148, 100-104)
+__device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero, int tid) {
+  const int s1 = l.n0, s2 = l.n0 * l.n1;
+  for (int c = tid; c < l.cells; c += 1024) l.E[c] = l.R[c] * l.iD;
+  __syncthreads();
+  const int h0 = l.n0 >> 1;
+  for (int k0 = 1; k0 <= 4; k0++) {
+    for (int q = tid; q < (l.cells >> 1); q += 1024) {
+      const int row = h0 == 1 ? q : (int)__umulhi((unsigned)q, l.mh), ih = q - row * h0;
+      const int k = l.n1 == 1 ? row : (int)__umulhi((unsigned)row, l.m1), j = row - k * l.n1;
+      const int i = 2 * ih + ((1 + k0 + j + k) & 1);  // Σ(1-based indices) ≡ 1+k₀ (mod 2)  ⇔  i+j+k ≡ 1+k₀
+      const int c = i + s1 * j + s2 * k;
+      float s = l.R[c];
+      // across a periodic face the sweep sees the stale ϵ⁰ = r·iD of the wrapped cell (perBC! runs once, before the sweeps)
+      const float xlo = i == 0 ? l.R[c + (l.n0 - 1)] * l.iD : l.E[c - 1], xhi = i == l.n0 - 1 ? l.R[c - (l.n0 - 1)] * l.iD : l.E[c + 1];
+      s -= xlo * l.L0 + xhi * l.L0;
+      const float ylo = j == 0 ? l.R[c + s1 * (l.n1 - 1)] * l.iD : l.E[c - s1], yhi = j == l.n1 - 1 ? l.R[c - s1 * (l.n1 - 1)] * l.iD : l.E[c + s1];
+      s -= ylo * l.L1 + yhi * l.L1;
+      const float zlo = k == 0 ? l.R[c + s2 * (l.n2 - 1)] * l.iD : l.E[c - s2], zhi = k == l.n2 - 1 ? l.R[c - s2 * (l.n2 - 1)] * l.iD : l.E[c + s2];
+      s -= zlo * l.L2 + zhi * l.L2;
+      l.E[c] = s * l.iD;
+    }
+    __syncthreads();
+  }
+  for (int c = tid; c < l.cells; c += 1024) {
+    int i, j, k;
+    l.ijk(c, i, j, k);
+    const float e = l.E[c];
+    float Ae = e * l.D;
+    Ae += l.E[c - i + tiny_wrap(i - 1, l.n0)] * l.L0 + l.E[c - i + tiny_wrap(i + 1, l.n0)] * l.L0;
+    Ae += l.E[c + s1 * (tiny_wrap(j - 1, l.n1) - j)] * l.L1 + l.E[c + s1 * (tiny_wrap(j + 1, l.n1) - j)] * l.L1;
+    Ae += l.E[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.L2 + l.E[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.L2;
+    l.R[c] = l.R[c] - w * Ae;
+    l.X[c] = x_is_zero ? w * e : l.X[c] + w * e;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ TinyArgs a) {
+  extern __shared__ float tiny_sm[];
+  const int tid = threadIdx.x;
+  TinyLvl lv[TINY_MAXLEV];
+  {
+    float* p = tiny_sm;
+#pragma unroll
+    for (int q = 0; q < TINY_MAXLEV; q++) {
+      if (q < a.nlev) {
+        TinyLvl& l = lv[q];
+        l.n0 = a.n[q][0], l.n1 = a.n[q][1], l.n2 = a.n[q][2];
+        l.cells = l.n0 * l.n1 * l.n2;
+        l.m0 = tiny_magic(l.n0), l.m1 = tiny_magic(l.n1), l.mh = tiny_magic(l.n0 >> 1);
+        l.L0 = a.L[q][0], l.L1 = a.L[q][1], l.L2 = a.L[q][2], l.D = a.D[q], l.iD = a.iD[q];
+        l.X = p, l.R = p + l.cells, l.E = p + 2 * l.cells;
+        p += 3 * l.cells;
+      }
+    }
+  }
+  const float w = *a.wp;
+  {  // r of level T from global memory
+    const TinyLvl& l = lv[0];
+    for (int c = tid; c < l.cells; c += 1024) {
+      int i, j, k;
+      l.ijk(c, i, j, k);
+      l.R[c] = a.r0[(i64)(a.g0.xo + i + 1) + a.g0.s[1] * (j + 1) + a.g0.s[2] * (k + 1)];
+    }
+  }
+  __syncthreads();
+  // ---- down-stroke: Jacobi! (x = ϵ: the level starts from x = 0) and restrict! ----
+#pragma unroll
+  for (int q = 0; q < TINY_MAXLEV - 1; q++) {
+    if (q < a.nlev - 1) {
+      TinyLvl& l = lv[q];
+      const int s1 = l.n0, s2 = l.n0 * l.n1;
+      for (int c = tid; c < l.cells; c += 1024) {
+        int i, j, k;
+        l.ijk(c, i, j, k);
+        const float e = l.R[c] * l.iD;
+        float s = e * l.D;
+        s += (l.R[c - i + tiny_wrap(i - 1, l.n0)] * l.iD) * l.L0 + (l.R[c - i + tiny_wrap(i + 1, l.n0)] * l.iD) * l.L0;
+        s += (l.R[c + s1 * (tiny_wrap(j - 1, l.n1) - j)] * l.iD) * l.L1 + (l.R[c + s1 * (tiny_wrap(j + 1, l.n1) - j)] * l.iD) * l.L1;
+        s += (l.R[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.iD) * l.L2 + (l.R[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.iD) * l.L2;
+        l.E[c] = l.R[c] - 1.f * s;
+        l.X[c] = e;
+      }
+      __syncthreads();
+      {  // the new residual is in E: swap the roles (Jacobi! writes r out of place)
+        float* t = l.R;
+        l.R = l.E;
+        l.E = t;
+      }
+      const TinyLvl& cl = lv[q + 1];
+      for (int c = tid; c < cl.cells; c += 1024) {
+        int i, j, k;
+        cl.ijk(c, i, j, k);
+        float s = 0.f;
+        for (int kk = 2 * k; kk <= 2 * k + 1; kk++)
+          for (int jj = 2 * j; jj <= 2 * j + 1; jj++)
+            for (int ii = 2 * i; ii <= 2 * i + 1; ii++) s += l.R[ii + s1 * jj + s2 * kk];
+        cl.R[c] = s;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- coarsest level: smooth! from x = 0 ----
+#pragma unroll
+  for (int q = 0; q < TINY_MAXLEV; q++)
+    if (q == a.nlev - 1) tiny_gs(lv[q], w, 1, tid);
+  // ---- up-stroke: prolongate! + increment!, smooth! ----
+#pragma unroll
+  for (int q = TINY_MAXLEV - 2; q >= 0; q--) {
+    if (q < a.nlev - 1) {
+      const TinyLvl& l = lv[q];
+      const TinyLvl& cl = lv[q + 1];
+      const int s2 = l.n0 * l.n1, c1 = cl.n0, c2 = cl.n0 * cl.n1;
+      for (int c = tid; c < l.cells; c += 1024) {
+        int i, j, k;
+        l.ijk(c, i, j, k);
+        // ϵ[J] = x_c[down(J)] on the periodic image of J
+        auto ec = [&](int ii, int jj, int kk) -> float {
+          return cl.X[(tiny_wrap(ii, l.n0) >> 1) + c1 * (tiny_wrap(jj, l.n1) >> 1) + c2 * (tiny_wrap(kk, l.n2) >> 1)];
+        };
+        const float e = ec(i, j, k);
+        float s = e * l.D;
+        s += ec(i - 1, j, k) * l.L0 + ec(i + 1, j, k) * l.L0;
+        s += ec(i, j - 1, k) * l.L1 + ec(i, j + 1, k) * l.L1;
+        s += ec(i, j, k - 1) * l.L2 + ec(i, j, k + 1) * l.L2;
+        l.R[c] = l.R[c] - w * s;
+        l.X[c] = l.X[c] + w * e;
+      }
+      __syncthreads();
+      tiny_gs(l, w, 0, tid);
+    }
+  }
+  {  // x (and r) of level T back to global memory
+    const TinyLvl& l = lv[0];
+    for (int c = tid; c < l.cells; c += 1024) {
+      int i, j, k;
+      l.ijk(c, i, j, k);
+      const i64 o = (i64)(a.g0.xo + i + 1) + a.g0.s[1] * (j + 1) + a.g0.s[2] * (k + 1);
+      a.x0[o] = l.X[c];
+      a.r0out[o] = l.R[c];
+    }
+  }
+}
