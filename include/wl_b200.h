@@ -110,6 +110,31 @@ int wl_apply_bc(wl_handle* h);
  * BC!(μ₀,0,false,perdir); BC!(V,0,exitBC,perdir). */
 int wl_measure_bc(wl_handle* h);
 
+/* measure!(flow, body; t, ϵ) ON THE DEVICE for bodies the library can evaluate itself (src/Body.jl:28-51,
+ * src/AutoBody.jl:29-37, set operations src/Body.jl:88-107): primitive k is AutoBody(sdf_k, (x,t) -> x .- vel_k.*t) with sdf_k a
+ * sphere (circle in 2-D) or a torus with its axis along x; the body is ((p₀ op₁ p₁) op₂ p₂) … with op ∈ {∪, ∩, −}.  Everything a
+ * host closure would do for these shapes — signed distance at the cell centres (flow.σ), distance, normal and velocity at the
+ * faces of the band |d| < 2+ϵ, μ₀, μ₁, V, then BC!(μ₀,0), BC!(V,0,exitBC) — runs in one kernel; the Poisson hierarchy is marked
+ * stale (rebuilt by wl_update or by the next step).  This is what makes sim_step!(sim; remeasure=true) possible without a
+ * per-step upload.  wl_set_body registers the body (nprims ≤ 8; nprims = 0 removes it); wl_measure measures it at time t;
+ * wl_set_remeasure(h,1) makes every step of wl_mom_step / wl_sim_step_n / wl_sim_step_until start with
+ * measure!(sim, t=sum(Δt)) + update!(pois) like sim_step!(sim; remeasure=true) (src/WaterLily.jl:136-149). */
+enum { WL_BODY_SPHERE = 0, WL_BODY_TORUS = 1 };
+enum { WL_OP_UNION = 0, WL_OP_INTERSECT = 1, WL_OP_MINUS = 2 };
+typedef struct wl_body_prim {
+  int32_t kind;    /* WL_BODY_* */
+  int32_t op;      /* WL_OP_* combining this primitive with everything before it (ignored for the first) */
+  float center[3]; /* at t = 0, in cell units like the reference's coordinates (src/core.jl:177) */
+  float R;         /* sphere radius / torus major radius */
+  float r;         /* torus minor radius */
+  float vel[3];    /* translation velocity of the rigid map */
+} wl_body_prim;
+int wl_set_body(wl_handle* h, const wl_body_prim* prims, int nprims, float eps);
+int wl_measure(wl_handle* h, float t);
+int wl_set_remeasure(wl_handle* h, int enabled);
+/* sum(flow.Δt): the time at the END of the next step, the default `t` of measure!(sim) (src/WaterLily.jl:146). */
+int wl_time_next(wl_handle* h, double* t);
+
 /* update!(pois) (src/WaterLily.jl:148, src/MultiLevelPoisson.jl:79-86, src/Poisson.jl:47): call after uploading μ₀
  * (measure!): set_diag! on level 1 and restrictL! + set_diag! on every coarse level. */
 int wl_update(wl_handle* h);

@@ -54,6 +54,8 @@ def lib():
         L.wlo_cfl.restype = C.c_float
         L.wlo_measure_sphere.argtypes = [C.c_void_p, fp, C.c_float, C.c_float]
         L.wlo_measure_torus.argtypes = [C.c_void_p, fp, C.c_float, C.c_float, C.c_float]
+        L.wlo_measure_prims.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.wlo_measure_prims.restype = None
         for name in ("wlo_dt_len", "wlo_iters_len", "wlo_log_len", "wlo_num_levels", "wlo_pois_solve"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_int
@@ -174,6 +176,23 @@ class OracleSim:
     def measure_torus(self, center, R, r, eps=1.0):
         c = np.asarray(center, np.float32)
         self.L.wlo_measure_torus(self.h, _fp(c), R, r, eps)
+
+    def measure_prims(self, prims, eps=1.0, t=0.0):
+        """measure!(flow, body; t, ϵ) for primitives with a translation map and set operations (src/Body.jl:28-51,88-107).
+        `prims`: list of dicts kind/op/center/R/r/vel (kind 0 sphere, 1 torus; op 0 ∪, 1 ∩, 2 −)."""
+        class P(C.Structure):
+            _fields_ = [("kind", C.c_int), ("op", C.c_int), ("c", C.c_float * 3), ("R", C.c_float), ("r", C.c_float), ("vel", C.c_float * 3)]
+        arr = (P * len(prims))()
+        for q, p in enumerate(prims):
+            arr[q].kind, arr[q].op, arr[q].R, arr[q].r = p["kind"], p["op"], p["R"], p["r"]
+            for d in range(3):
+                arr[q].c[d] = p["center"][d] if d < len(p["center"]) else 0.0
+                arr[q].vel[d] = p["vel"][d] if d < len(p["vel"]) else 0.0
+        self.L.wlo_measure_prims(self.h, arr, len(prims), eps, t)
+
+    def time_next(self):
+        """sum(Δt): the default t of measure!(sim) (src/WaterLily.jl:146)"""
+        return float(np.float32(np.sum(self.dt.astype(np.float64))))
 
     def init_pois(self):
         """pois_ctor(flow) (src/WaterLily.jl:97,105)"""

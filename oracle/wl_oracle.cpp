@@ -698,8 +698,16 @@ static inline T ulp(T d) {  // Julia eps(d::Float32)
   T a = std::fabs(d);
   return std::nextafter(a, INFINITY) - a;
 }
-static inline T sinpiT(T x) { return (T)std::sin(M_PI * (double)x); }
-static inline T cospiT(T x) { return (T)std::cos(M_PI * (double)x); }
+// sinpi / cospi (src/Body.jl:55-56 call Julia's sinpi/cospi, which are exact at multiples of ½: sinpi(1) = 0, cospi(½) = 0 — the
+// kernel moments vanish EXACTLY at |d| = ϵ).  Evaluated in double with the argument reduced to [−½, ½] first (exact for Float32
+// inputs), then rounded; valid for |x| ≤ 1.5, the kernels call them on [−1, 1].
+static inline double sinpi_d(double x) {
+  const double a = std::fabs(x);
+  const double r = a <= 0.5 ? std::sin(M_PI * a) : std::sin(M_PI * (1.0 - a));
+  return x < 0 ? -r : r;
+}
+static inline T sinpiT(T x) { return (T)sinpi_d((double)x); }
+static inline T cospiT(T x) { return (T)sinpi_d(0.5 - std::fabs((double)x)); }
 static inline T kern0(T d) { return (1 + d + sinpiT(d) / (T)M_PI) / 2; }                                               // :55
 static inline T kern1(T d) { return (1 - d * d) / 4 - (d * sinpiT(d) + (1 + cospiT(d)) / (T)M_PI) / (2 * (T)M_PI); }  // :56
 static inline T mu0f(T d, T e) { return d / e < -1 + std::sqrt(ulp(d)) ? (T)0 : kern0(std::min(d / e, (T)1)); }       // :59
@@ -750,6 +758,115 @@ static void body_measure(const Body& b, int D, const T* x, T fastd2, T* d, T* n)
   m = std::sqrt(m);
   *d /= m;
   for (int k = 0; k < D; k++) n[k] = gk[k] / m;
+}
+// ---- parametrised bodies with a rigid translation map and lazy set operations (src/AutoBody.jl:10-37, src/Body.jl:88-107) ----
+// Primitive k is AutoBody(sdf_k, (x,t) -> x .- vel_k.*t); the body is ((p₀ op₁ p₁) op₂ p₂) … with op ∈ {∪ = min, ∩ = max, − = a ∩ (−b)}
+// on the measure tuples (d, n, V) (tuple isless: lexicographic).
+struct Prim {
+  int kind, op;  // kind: 0 sphere/circle, 1 torus (axis ∥ x); op: 0 ∪, 1 ∩, 2 − (ignored for the first primitive)
+  T c[3];
+  T R, r;
+  T vel[3];
+};
+struct Meas {
+  T d, n[3], V[3];
+};
+static Meas prim_measure(const Prim& p, int D, const T* x, T t, T fastd2) {  // measure(body::AutoBody,x,t;fastd²)  src/AutoBody.jl:29-37
+  Body b{p.kind, {p.c[0], p.c[1], p.c[2]}, p.R, p.r};
+  T xi[3] = {0, 0, 0};
+  for (int k = 0; k < D; k++) xi[k] = x[k] - p.vel[k] * t;  // map(x,t)
+  Meas m;
+  m.d = body_sdf(b, D, xi);
+  for (int k = 0; k < 3; k++) m.n[k] = m.V[k] = 0;
+  if (m.d * m.d > fastd2) return m;
+  T gk[3] = {0, 0, 0};
+  body_grad(b, D, xi, gk);
+  for (int k = 0; k < D; k++)
+    if (std::isnan(gk[k])) return m;
+  T mm = 0;  // J = I: n = J'n
+  for (int k = 0; k < D; k++) mm += gk[k] * gk[k];
+  mm = std::sqrt(mm);
+  m.d /= mm;
+  for (int k = 0; k < D; k++) {
+    m.n[k] = gk[k] / mm;
+    m.V[k] = p.vel[k];  // −J\∂ₜmap = vel
+  }
+  return m;
+}
+static bool fless(T a, T b) {  // isless(::Float32, ::Float32): NaN is the largest, −0.0 < 0.0
+  if (std::isnan(a)) return false;
+  if (std::isnan(b)) return true;
+  if (a == b) return std::signbit(a) && !std::signbit(b);
+  return a < b;
+}
+static bool meas_less(const Meas& a, const Meas& b, int D) {  // isless on the tuples (d, n, V)
+  if (fless(a.d, b.d)) return true;
+  if (fless(b.d, a.d)) return false;
+  for (int k = 0; k < D; k++) {
+    if (fless(a.n[k], b.n[k])) return true;
+    if (fless(b.n[k], a.n[k])) return false;
+  }
+  for (int k = 0; k < D; k++) {
+    if (fless(a.V[k], b.V[k])) return true;
+    if (fless(b.V[k], a.V[k])) return false;
+  }
+  return false;
+}
+static Meas csg_measure(const Prim* ps, int np, int D, const T* x, T t, T fastd2) {  // measure(body::SetBody, …)  src/Body.jl:104-107
+  Meas acc = prim_measure(ps[0], D, x, t, fastd2);
+  for (int q = 1; q < np; q++) {
+    Meas m = prim_measure(ps[q], D, x, t, fastd2);
+    if (ps[q].op == 2) {  // a − b = a ∩ (−b): (−d, −n, V)
+      m.d = -m.d;
+      for (int k = 0; k < D; k++) m.n[k] = -m.n[k];
+    }
+    if (ps[q].op == 0) {  // min(x,y) = ifelse(isless(y,x), y, x)
+      if (meas_less(m, acc, D)) acc = m;
+    } else {  // max(x,y) = ifelse(isless(y,x), x, y)
+      if (!meas_less(m, acc, D)) acc = m;
+    }
+  }
+  return acc;
+}
+static void measure_prims(Flow& a, const Prim* ps, int np, T eps, T t) {  // measure!(flow, body; t, ϵ)  src/Body.jl:28-51
+  const Grid& g = a.g;
+  const size_t n = g.n();
+  const int D = g.D;
+  std::fill(a.V.begin(), a.V.end(), (T)0);
+  std::fill(a.mu0.begin(), a.mu0.end(), (T)1);
+  std::fill(a.mu1.begin(), a.mu1.end(), (T)0);
+  const T d2 = (2 + eps) * (2 + eps);
+  loop(inside(g), [&](I3 I) {  // measure_sdf!(σ, body, t; fastd²=d²): AutoBody → its sdf (src/AutoBody.jl:19); SetBody → measure(…)[1] (src/Body.jl:67)
+    T x[3];
+    for (int d = 0; d < 3; d++) x[d] = (T)I.v[d] - 1.5f;
+    if (np == 1) {
+      Body b{ps[0].kind, {ps[0].c[0], ps[0].c[1], ps[0].c[2]}, ps[0].R, ps[0].r};
+      T xi[3] = {0, 0, 0};
+      for (int k = 0; k < D; k++) xi[k] = x[k] - ps[0].vel[k] * t;
+      a.sigma[g.at(I)] = body_sdf(b, D, xi);
+    } else
+      a.sigma[g.at(I)] = csg_measure(ps, np, D, x, t, d2).d;
+  });
+  loop(inside(g), [&](I3 I) {
+    size_t o = g.at(I);
+    T dI = a.sigma[o];
+    if (dI * dI < d2) {
+      for (int i = 0; i < D; i++) {
+        T x[3];
+        for (int d = 0; d < 3; d++) x[d] = (T)I.v[d] - 1.5f - (d == i ? 0.5f : 0.f);  // loc(i,I)  src/core.jl:177
+        Meas m = csg_measure(ps, np, D, x, t, d2);
+        T di = std::fabs(m.d) <= 0.5f ? m.d : std::copysign(m.d, dI);
+        a.V[o + n * i] = m.V[i];
+        a.mu0[o + n * i] = mu0f(di, eps);
+        for (int j = 0; j < D; j++) a.mu1[o + n * ((size_t)i + (size_t)D * j)] = mu1f(di, eps) * m.n[j];
+      }
+    } else if (dI < 0) {
+      for (int i = 0; i < D; i++) a.mu0[o + n * i] = 0;
+    }
+  });
+  T zero[3] = {0, 0, 0};
+  BC(g, a.mu0.data(), zero, false, a.per);
+  BC(g, a.V.data(), zero, a.exit, a.per);
 }
 static void measure(Flow& a, const Body& b, T eps) {  // measure!  src/Body.jl:28-51
   const Grid& g = a.g;
@@ -869,6 +986,8 @@ void wlo_measure_torus(void* h, const float* c, float R, float r, float eps) {
   Body b{1, {c[0], c[1], c[2]}, R, r};
   measure(*(Flow*)h, b, eps);
 }
+// measure!(flow, body; t, ϵ) for a body made of `np` primitives (struct layout = wl_body_prim of include/wl_b200.h)
+void wlo_measure_prims(void* h, const void* prims, int np, float eps, float t) { measure_prims(*(Flow*)h, (const Prim*)prims, np, eps, t); }
 // pois_ctor(flow): MultiLevelPoisson(flow.p,flow.μ₀,flow.σ;perdir) (kind 0) or Poisson(...) (kind 1)
 int wlo_init_pois(void* h, int kind) {
   Flow* a = (Flow*)h;

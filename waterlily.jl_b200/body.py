@@ -37,13 +37,50 @@ class AutoBody:
         return out
 
 
-class Sphere(AutoBody):
-    """AutoBody((x,t)->√sum(abs2, x .- center) - radius)  (README.md:118-119; circle in 2-D)"""
+class _Parametrised:
+    """Bodies the library measures ON THE DEVICE (wl_set_body / wl_measure): primitives with a rigid translation
+    map (x,t) -> x .- velocity.*t, combined with the reference's lazy set operations (src/Body.jl:88-103):
+    a | b or a + b (∪), a & b (∩), a - b (a ∩ −b)."""
 
-    def __init__(self, center, radius):
+    def prims(self):
+        raise NotImplementedError
+
+    def __or__(self, other):
+        return BodySetOp(self, other, 0)
+
+    __add__ = __or__
+
+    def __and__(self, other):
+        return BodySetOp(self, other, 1)
+
+    def __sub__(self, other):
+        return BodySetOp(self, other, 2)
+
+
+class BodySetOp(_Parametrised):
+    """SetBody(op, a, b) restricted to left-leaning trees: b must be a primitive."""
+
+    def __init__(self, a, b, op):
+        pb = b.prims()
+        if len(pb) != 1:
+            raise ValueError("set operations take a primitive on the right-hand side: write ((a ∪ b) ∪ c), not a ∪ (b ∪ c)")
+        self._p = a.prims() + [dict(pb[0], op=op)]
+
+    def prims(self):
+        return [dict(p) for p in self._p]
+
+
+class Sphere(AutoBody, _Parametrised):
+    """AutoBody((x,t)->√sum(abs2, x .- center) - radius, (x,t)->x .- velocity.*t)  (README.md:118-119; circle in 2-D)"""
+
+    def __init__(self, center, radius, velocity=None):
         self.c = [F(v) for v in center]
         self.R = F(radius)
+        self.vel = [F(v) for v in (velocity if velocity is not None else (0,) * len(center))]
         super().__init__(self._sdf, self._g)
+
+    def prims(self):
+        return [dict(kind=0, op=0, center=[float(v) for v in self.c], R=float(self.R), r=0.0, vel=[float(v) for v in self.vel])]
 
     def _sdf(self, x):
         s = F(0)
@@ -60,14 +97,18 @@ class Sphere(AutoBody):
             return [(xd - self.c[d]) / m for d, xd in enumerate(x)]
 
 
-class Torus(AutoBody):
+class Torus(AutoBody, _Parametrised):
     """Torus with its axis along x (WaterLily-Examples ThreeD_Donut recipe): major radius R, minor radius r."""
 
-    def __init__(self, center, R, r):
+    def __init__(self, center, R, r, velocity=None):
         self.c = [F(v) for v in center]
         self.R = F(R)
         self.r = F(r)
+        self.vel = [F(v) for v in (velocity if velocity is not None else (0, 0, 0))]
         super().__init__(self._sdf, self._g)
+
+    def prims(self):
+        return [dict(kind=1, op=0, center=[float(v) for v in self.c], R=float(self.R), r=float(self.r), vel=[float(v) for v in self.vel])]
 
     def _parts(self, x):
         xx, y, z = x[0] - self.c[0], x[1] - self.c[1], x[2] - self.c[2]
@@ -85,12 +126,32 @@ class Torus(AutoBody):
             return [xx / m, (q / m) * (y / rho), (q / m) * (z / rho)]
 
 
+def prim_array(body):
+    """ctypes array of wl_body_prim for a parametrised body"""
+    from .lib import BodyPrim
+    ps = body.prims()
+    arr = (BodyPrim * len(ps))()
+    for q, p in enumerate(ps):
+        arr[q].kind, arr[q].op, arr[q].R, arr[q].r = p["kind"], p["op"], p["R"], p["r"]
+        for d in range(3):
+            arr[q].center[d] = p["center"][d] if d < len(p["center"]) else 0.0
+            arr[q].vel[d] = p["vel"][d] if d < len(p["vel"]) else 0.0
+    return arr
+
+
+def _sinpi64(x):
+    """sinpi in double with the argument reduced to [-1/2, 1/2] first (exact at multiples of 1/2 like Julia's sinpi); |x| ≤ 1.5"""
+    a = np.abs(x)
+    r = np.where(a <= 0.5, np.sin(np.pi * a), np.sin(np.pi * (1.0 - a)))
+    return np.where(x < 0, -r, r)
+
+
 def _sinpi(x):
-    return np.sin(np.pi * x.astype(np.float64)).astype(F)
+    return _sinpi64(np.asarray(x, F).astype(np.float64)).astype(F)
 
 
 def _cospi(x):
-    return np.cos(np.pi * x.astype(np.float64)).astype(F)
+    return _sinpi64(0.5 - np.abs(np.asarray(x, F).astype(np.float64))).astype(F)
 
 
 def _kern0(d):  # src/Body.jl:55

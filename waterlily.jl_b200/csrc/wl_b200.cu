@@ -175,6 +175,9 @@ struct wl_handle {
   int* d_flags = nullptr;  // [0]: a velocity field holds a non-finite value (or |u| > 1e37); [2]: range word of the current u, [3]: its ticket (range_note)
   float* stage = nullptr;  // dense staging buffer of one component for host transfers
   size_t stage_cap = 0;
+  BodySet body;            // parametrised body registered with wl_set_body (np = 0: none)
+  float body_eps = 1.f;
+  bool remeasure = false;  // every step starts with measure!(sim, t=sum(Δt)) + update!(pois)
   bool range_checked = false;  // the current u was range-checked by the kernel that wrote it (range_note, wl_common.cuh)
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
@@ -1929,10 +1932,79 @@ int wl_update(wl_handle* h) {
   return update_levels(h);
 }
 
+// time(a) = sum(@view a.Δt[1:end-1]) (src/Flow.jl:174; all = false) and sum(a.Δt) (measure!(sim)'s default t; all = true).
+// Julia's Float32 `sum` is pairwise in blocks of 1024 with a @simd inner loop: its rounding depends on the vector width (unpinned),
+// but it stays within a few ulp of the exact sum for any length.  Here the sum is accumulated incrementally in double (O(1) per
+// step; the running Float32 loop this replaces was O(n) per call and drifted by O(n·eps) from the reference after thousands of
+// steps) and rounded to Float32 once, i.e. the Float32 nearest to the exact sum.
+static int time_sum(wl_handle* h, bool all, double* t) {
+  TRY(sync_dt(h));
+  const size_t n = h->dt.empty() ? 0 : h->dt.size() - 1;
+  if (h->tsum_n > n) h->tsum_n = 0, h->tsum = 0.0;
+  for (; h->tsum_n < n; h->tsum_n++) h->tsum += (double)h->dt[h->tsum_n];
+  *t = (double)(float)(all && !h->dt.empty() ? h->tsum + (double)h->dt.back() : h->tsum);
+  return 0;
+}
+// measure!(flow, body; t, ϵ) for the registered body (src/Body.jl:28-51)
+static int measure_body(wl_handle* h, float t) {
+  if (h->body.np <= 0) return fail("wl_measure: no body registered (wl_set_body)");
+  flush_ghosts(h);
+  dim3 b = h->D == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
+  Box in = h->levels[0].inside();
+  LAUNCH_D(h, k_measure, grd(in, b), b, h->g, in, h->body, h->body_eps, t, h->sigma, h->V, h->mu0, h->mu1);
+  h->nobody_valid = false;
+  h->pois_dirty = true;
+  return wl_measure_bc(h);  // BC!(μ₀,0,false,perdir); BC!(V,0,exitBC,perdir) (+ z-slab halo planes)
+}
+// sim_step!(sim; remeasure) (src/WaterLily.jl:136-139)
+static int sim_step(wl_handle* h) {
+  if (h->remeasure && h->body.np > 0) {
+    double t;
+    TRY(time_sum(h, true, &t));  // measure!(sim, t = sum(sim.flow.Δt)) (src/WaterLily.jl:146-149)
+    TRY(measure_body(h, (float)t));
+    TRY(update_levels(h));
+  }
+  return mom_step(h);
+}
+
+int wl_set_body(wl_handle* h, const wl_body_prim* prims, int nprims, float eps) {
+  if (!h) return fail("null handle");
+  if (nprims < 0 || nprims > 8) return fail("wl_set_body: %d primitives (0 … 8 supported)", nprims);
+  if (nprims > 0 && !prims) return fail("null argument");
+  static_assert(sizeof(wl_body_prim) == sizeof(BodyPrim), "wl_body_prim and BodyPrim must have the same layout");
+  memset(&h->body, 0, sizeof h->body);
+  for (int q = 0; q < nprims; q++) {
+    if (prims[q].kind != WL_BODY_SPHERE && prims[q].kind != WL_BODY_TORUS) return fail("wl_set_body: unknown primitive kind %d", prims[q].kind);
+    if (prims[q].kind == WL_BODY_TORUS && h->D != 3) return fail("wl_set_body: the torus is a 3-D body");
+    if (prims[q].op < 0 || prims[q].op > 2) return fail("wl_set_body: unknown set operation %d", prims[q].op);
+    memcpy(&h->body.p[q], &prims[q], sizeof(BodyPrim));
+  }
+  h->body.np = nprims;
+  h->body_eps = eps;
+  return 0;
+}
+
+int wl_measure(wl_handle* h, float t) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  return measure_body(h, t);
+}
+
+int wl_set_remeasure(wl_handle* h, int enabled) {
+  if (!h) return fail("null handle");
+  h->remeasure = enabled != 0;
+  return 0;
+}
+
+int wl_time_next(wl_handle* h, double* t) {
+  if (!h || !t) return fail("null argument");
+  return time_sum(h, true, t);
+}
+
 int wl_mom_step(wl_handle* h) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
-  TRY(mom_step(h));
+  TRY(sim_step(h));
   return check_flags(h);
 }
 
@@ -1940,24 +2012,15 @@ int wl_sim_step_n(wl_handle* h, int nsteps) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   for (int i = 0; i < nsteps; i++) {
-    TRY(mom_step(h));
+    TRY(sim_step(h));
     if ((i & 63) == 63) TRY(check_flags(h));  // a diverged field or a dead peer stops the loop within 64 steps
   }
   return check_flags(h);
 }
 
-// time(a) = sum(@view a.Δt[1:end-1]) (src/Flow.jl:174).  Julia's Float32 `sum` is pairwise in blocks of 1024 with a @simd inner loop:
-// its rounding depends on the vector width (unpinned), but it stays within a few ulp of the exact sum for any length.  Here the
-// sum is accumulated incrementally in double (O(1) per step; the running Float32 loop this replaces was O(n) per call and drifted
-// by O(n·eps) from the reference after thousands of steps) and rounded to Float32 once, i.e. the Float32 nearest to the exact sum.
 int wl_time(wl_handle* h, double* t) {
   if (!h || !t) return fail("null argument");
-  TRY(sync_dt(h));
-  const size_t n = h->dt.empty() ? 0 : h->dt.size() - 1;
-  if (h->tsum_n > n) h->tsum_n = 0, h->tsum = 0.0;
-  for (; h->tsum_n < n; h->tsum_n++) h->tsum += (double)h->dt[h->tsum_n];
-  *t = (double)(float)h->tsum;
-  return 0;
+  return time_sum(h, false, t);
 }
 
 int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t max_steps, int64_t* steps_taken) {
@@ -1968,7 +2031,7 @@ int wl_sim_step_until(wl_handle* h, double t_end, double U, double L, int64_t ma
     double t;
     TRY(wl_time(h, &t));
     if (!(t * U / L < t_end) || k >= max_steps) break;
-    TRY(mom_step(h));
+    TRY(sim_step(h));
     TRY(check_flags(h));
     k++;
   }

@@ -855,3 +855,159 @@ __global__ void __launch_bounds__(256) k_range_check(const float4* __restrict__ 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) ra.add4(a[i]);
   ra.publish(flags);
 }
+
+// ================================================================================================
+// measure!(flow, body; t, ϵ) on the device (src/Body.jl:28-60, src/AutoBody.jl:29-37, src/Body.jl:88-107) for parametrised bodies:
+// primitives (sphere / torus) with a rigid translation map, combined by lazy set operations.  One thread per interior cell.
+// The arithmetic follows the reference expression by expression (the gradients are the closed forms ForwardDiff produces for
+// these sdfs; sinpi / cospi are evaluated in double and rounded, like the oracle's restatement).
+// ================================================================================================
+struct BodyPrim {  // = wl_body_prim (include/wl_b200.h)
+  int kind, op;
+  float c[3];
+  float R, r;
+  float vel[3];
+};
+struct BodySet {
+  int np;
+  BodyPrim p[8];
+};
+struct Meas {
+  float d, n[3], V[3];
+};
+__device__ __forceinline__ float prim_sdf(const BodyPrim& b, int D, const float* x) {
+  if (b.kind == 0) {
+    float s = 0.f;
+    for (int d = 0; d < D; d++) s += (x[d] - b.c[d]) * (x[d] - b.c[d]);
+    return sqrtf(s) - b.R;
+  }
+  const float y = x[1] - b.c[1], z = x[2] - b.c[2], xx = x[0] - b.c[0];
+  const float q = sqrtf(y * y + z * z) - b.R;
+  return sqrtf(q * q + xx * xx) - b.r;
+}
+__device__ __forceinline__ void prim_grad(const BodyPrim& b, int D, const float* x, float* n) {
+  if (b.kind == 0) {
+    float s = 0.f;
+    for (int d = 0; d < D; d++) s += (x[d] - b.c[d]) * (x[d] - b.c[d]);
+    const float m = sqrtf(s);
+    for (int d = 0; d < D; d++) n[d] = (x[d] - b.c[d]) / m;
+    return;
+  }
+  const float y = x[1] - b.c[1], z = x[2] - b.c[2], xx = x[0] - b.c[0];
+  const float rho = sqrtf(y * y + z * z);
+  const float q = rho - b.R;
+  const float m = sqrtf(q * q + xx * xx);
+  n[0] = xx / m;
+  n[1] = (q / m) * (y / rho);
+  n[2] = (q / m) * (z / rho);
+}
+// measure(body::AutoBody, x, t; fastd²) with map(x,t) = x − vel·t: J = I, V = −J\∂ₜmap = vel
+__device__ __forceinline__ Meas prim_measure(const BodyPrim& p, int D, const float* x, float t, float fastd2) {
+  float xi[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < D; k++) xi[k] = x[k] - p.vel[k] * t;
+  Meas m;
+  m.d = prim_sdf(p, D, xi);
+  for (int k = 0; k < 3; k++) m.n[k] = m.V[k] = 0.f;
+  if (m.d * m.d > fastd2) return m;
+  float gk[3] = {0.f, 0.f, 0.f};
+  prim_grad(p, D, xi, gk);
+  for (int k = 0; k < D; k++)
+    if (isnan(gk[k])) return m;
+  float mm = 0.f;
+  for (int k = 0; k < D; k++) mm += gk[k] * gk[k];
+  mm = sqrtf(mm);
+  m.d /= mm;
+  for (int k = 0; k < D; k++) {
+    m.n[k] = gk[k] / mm;
+    m.V[k] = p.vel[k];
+  }
+  return m;
+}
+__device__ __forceinline__ bool fless(float a, float b) {  // isless(::Float32, ::Float32)
+  if (isnan(a)) return false;
+  if (isnan(b)) return true;
+  if (a == b) return signbit(a) && !signbit(b);
+  return a < b;
+}
+__device__ __forceinline__ bool meas_less(const Meas& a, const Meas& b, int D) {  // isless on the tuples (d, n, V)
+  if (fless(a.d, b.d)) return true;
+  if (fless(b.d, a.d)) return false;
+  for (int k = 0; k < D; k++) {
+    if (fless(a.n[k], b.n[k])) return true;
+    if (fless(b.n[k], a.n[k])) return false;
+  }
+  for (int k = 0; k < D; k++) {
+    if (fless(a.V[k], b.V[k])) return true;
+    if (fless(b.V[k], a.V[k])) return false;
+  }
+  return false;
+}
+__device__ __forceinline__ Meas csg_measure(const BodySet& B, int D, const float* x, float t, float fastd2) {
+  Meas acc = prim_measure(B.p[0], D, x, t, fastd2);
+  for (int q = 1; q < B.np; q++) {
+    Meas m = prim_measure(B.p[q], D, x, t, fastd2);
+    if (B.p[q].op == 2) {
+      m.d = -m.d;
+      for (int k = 0; k < D; k++) m.n[k] = -m.n[k];
+    }
+    if (B.p[q].op == 0) {
+      if (meas_less(m, acc, D)) acc = m;
+    } else {
+      if (!meas_less(m, acc, D)) acc = m;
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ float ulp_f(float d) {  // eps(d::Float32)
+  const float a = fabsf(d);
+  return __uint_as_float(__float_as_uint(a) + 1u) - a;
+}
+__device__ __forceinline__ float sinpi_f(float x) { return (float)sinpi((double)x); }
+__device__ __forceinline__ float cospi_f(float x) { return (float)cospi((double)x); }
+__device__ __forceinline__ float kern0_f(float d) { return (1.f + d + sinpi_f(d) / 3.14159274101257324f) / 2.f; }
+__device__ __forceinline__ float kern1_f(float d) {
+  return (1.f - d * d) / 4.f - (d * sinpi_f(d) + (1.f + cospi_f(d)) / 3.14159274101257324f) / (2.f * 3.14159274101257324f);
+}
+__device__ __forceinline__ float mu0_f(float d, float e) { return d / e < -1.f + sqrtf(ulp_f(d)) ? 0.f : kern0_f(fminf(d / e, 1.f)); }
+__device__ __forceinline__ float mu1_f(float d, float e) { return e * kern1_f(fmaxf(-1.f, fminf(d / e, 1.f))); }
+
+template <int D>
+__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ Grid g, Box box, const __grid_constant__ BodySet B, float eps, float t,
+                                                 float* __restrict__ sigma, float* __restrict__ V, float* __restrict__ mu0, float* __restrict__ mu1) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  const float d2 = (2.f + eps) * (2.f + eps);
+  // loc(0,I): cell centre, in GLOBAL coordinates (1-based index − 1.5; g.zoff = global z index of local plane 0)
+  float xc[3] = {0.f, 0.f, 0.f};
+  for (int d = 0; d < D; d++) xc[d] = (float)(I[d] + 1 + (d == 2 ? g.zoff : 0)) - 1.5f;
+  float dI;
+  if (B.np == 1) {  // sdf(body::AutoBody,x,t) = body.sdf(body.map(x,t),t)
+    float xi[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < D; k++) xi[k] = xc[k] - B.p[0].vel[k] * t;
+    dI = prim_sdf(B.p[0], D, xi);
+  } else  // sdf(body::SetBody,…) = measure(body,x,t;fastd²)[1]
+    dI = csg_measure(B, D, xc, t, d2).d;
+  sigma[o] = dI;
+  // V = 0, μ₀ = 1, μ₁ = 0 outside the band (the reference resets the arrays first)
+  float v[3] = {0.f, 0.f, 0.f}, m0[3] = {1.f, 1.f, 1.f}, m1[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (dI * dI < d2) {
+    for (int i = 0; i < D; i++) {
+      float x[3] = {xc[0], xc[1], xc[2]};
+      x[i] = xc[i] - 0.5f;  // loc(i,I)
+      const Meas m = csg_measure(B, D, x, t, d2);
+      const float di = fabsf(m.d) <= 0.5f ? m.d : copysignf(m.d, dI);
+      v[i] = m.V[i];
+      m0[i] = mu0_f(di, eps);
+      const float k1 = mu1_f(di, eps);
+      for (int j = 0; j < D; j++) m1[i + D * j] = k1 * m.n[j];
+    }
+  } else if (dI < 0.f) {
+    for (int i = 0; i < D; i++) m0[i] = 0.f;
+  }
+  for (int i = 0; i < D; i++) {
+    V[o + g.sc * i] = v[i];
+    mu0[o + g.sc * i] = m0[i];
+    for (int j = 0; j < D; j++) mu1[o + g.sc * (i + D * j)] = m1[i + D * j];
+  }
+}

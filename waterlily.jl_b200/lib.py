@@ -20,6 +20,12 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("flags", C.c_int32)]
 
 
+class BodyPrim(C.Structure):
+    """struct wl_body_prim (include/wl_b200.h)"""
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("center", C.c_float * 3), ("R", C.c_float), ("r", C.c_float),
+                ("vel", C.c_float * 3)]
+
+
 # -fmad=false: the production library executes plain IEEE Float32 operations in the reference's order, which
 # makes it bit-identical to the CPU oracle (compiled with -ffp-contract=off) over whole simulations — see
 # DESIGN.md §numerics.  The HBM-bound kernels do not pay for it; the flux kernel (FP32-issue-bound) pays ≈20 % more
@@ -101,6 +107,10 @@ def load_library(fmad=False):
         "wl_launch_count": [H, C.POINTER(C.c_int64)],
         "wl_is_const_coeff": [H, C.POINTER(C.c_int)],
         "wl_set_tuning": [H, C.c_char_p, C.c_int],
+        "wl_set_body": [H, C.c_void_p, C.c_int, C.c_float],
+        "wl_measure": [H, C.c_float],
+        "wl_set_remeasure": [H, C.c_int],
+        "wl_time_next": [H, C.POINTER(C.c_double)],
         "wl_stream": [H, C.POINTER(C.c_void_p)],
     }
     sig["wl_selftest_div6"] = [C.POINTER(C.c_uint64)]

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .body import NoBody, measure_body
+from .body import NoBody, _Parametrised, measure_body, prim_array
 from .flow import Flow, MultiLevelPoisson, Poisson, quick
 
 F = np.float32
@@ -17,7 +17,7 @@ class Simulation:
     factories and default to the B200 `Flow` and `MultiLevelPoisson`."""
 
     def __init__(self, dims, uBC, L, U=None, Δt=0.25, ν=0.0, g=None, ϵ=1, perdir=(), u0=None, exitBC=False, λ=quick,
-                 body=None, T=np.float32, flow_ctor=None, pois_ctor=None, **kw):
+                 body=None, T=np.float32, flow_ctor=None, pois_ctor=None, host_measure=False, **kw):
         if callable(uBC) and U is None:
             raise AssertionError("`U` (velocity scale) must be specified if boundary conditions `uBC` is a `Function`")
         if U is None:
@@ -33,17 +33,32 @@ class Simulation:
             def pois_ctor(flow):
                 return MultiLevelPoisson(flow) if pois == "multilevel" else Poisson(flow)
         self.pois = pois_ctor(self.flow)
-        measure(self)
+        # parametrised bodies (Sphere, Torus, set operations of them) are measured on the device; `host_measure=True` keeps the
+        # NumPy path (what a host binding does for an arbitrary AutoBody closure)
+        self.device_body = isinstance(self.body, _Parametrised) and not host_measure
+        if self.device_body:
+            arr = prim_array(self.body)
+            _lib.check(self.flow.L, self.flow.L.wl_set_body(self.flow.h, arr, len(arr), float(ϵ)))
+        measure(self, t=0.0)
 
     def close(self):
         self.flow.close()
 
 
 def measure(sim, t=None):
-    """measure!(sim) (src/WaterLily.jl:146-149): measure!(flow,body;ϵ) + update!(pois).  Static bodies only."""
+    """measure!(sim, t=sum(Δt)) (src/WaterLily.jl:146-149): measure!(flow,body;t,ϵ) + update!(pois).  Parametrised bodies are
+    measured by the library on the device at time t; any other AutoBody is measured here in NumPy (static: t is ignored)."""
     if isinstance(sim.body, NoBody):
         return
     fl = sim.flow
+    if getattr(sim, "device_body", False):
+        if t is None:
+            tt = C.c_double()
+            _lib.check(fl.L, fl.L.wl_time_next(fl.h, C.byref(tt)))
+            t = tt.value
+        _lib.check(fl.L, fl.L.wl_measure(fl.h, float(t)))
+        sim.pois.update()
+        return
     mu0, mu1, V, sigma = measure_body(fl.N, sim.body, sim.ϵ, fl.zoff)
     fl.upload("mu0", mu0)
     fl.upload("mu1", mu1)
@@ -60,12 +75,16 @@ def sim_time(sim):
 
 def sim_step(sim, t_end=None, remeasure=False, max_steps=2**62, verbose=False, udf=None):
     """sim_step!(sim,t_end;remeasure,max_steps,verbose) and sim_step!(sim;remeasure) (src/WaterLily.jl:128-139).
-    `remeasure=True` needs a body-motion closure on the host and is not supported on this path."""
+    `remeasure=True` re-measures a parametrised (device-measured) body at t = sum(Δt) before every step, inside the library;
+    a body given as a host closure cannot be re-measured per step through the C ABI."""
     if udf is not None:
         raise _lib.WLError("udf is a host closure: not supported by the B200 C ABI")
-    if remeasure and not isinstance(sim.body, NoBody):
-        raise _lib.WLError("remeasure=true (moving bodies) is outside the static-body hot path; pass remeasure=False")
     fl = sim.flow
+    if remeasure and not isinstance(sim.body, NoBody):
+        if not getattr(sim, "device_body", False):
+            raise _lib.WLError("remeasure=true needs a parametrised body (Sphere, Torus, set operations): an AutoBody closure "
+                               "lives on the host; pass remeasure=False or measure and upload it yourself")
+    _lib.check(fl.L, fl.L.wl_set_remeasure(fl.h, int(bool(remeasure) and getattr(sim, "device_body", False))))
     if t_end is None:
         _lib.check(fl.L, fl.L.wl_mom_step(fl.h))
         return 1
