@@ -135,6 +135,38 @@ int wl_set_remeasure(wl_handle* h, int enabled);
 /* sum(flow.Δt): the time at the END of the next step, the default `t` of measure!(sim) (src/WaterLily.jl:146). */
 int wl_time_next(wl_handle* h, double* t);
 
+/* pressure_force, viscous_force, pressure_moment(x₀), viscous_moment(x₀) of the registered body (src/Metrics.jl:111-190) at
+ * t = time(flow), as one fused device reduction over p and u (Float32 per-cell vectors, Float64 sums like sum(Float64, df)).
+ * out[0:3] pressure force, out[3:6] viscous force, out[6:9] pressure moment, out[9:12] viscous moment about x0 (3 floats; may be
+ * NULL = origin).  In 2-D the third components are 0 and both moment components hold the scalar a₁b₂−a₂b₁ like the reference's
+ * broadcast.  total_force = out[0:3] + out[3:6]. */
+int wl_body_forces(wl_handle* h, const float* x0, double* out12);
+
+/* MeanFlow (src/Metrics.jl:205-257): running time averages P, U and (uu_stats) UU = u⊗u kept ON THE DEVICE in the library's
+ * layout.  wl_meanflow_init = MeanFlow(flow; t_init=time(flow), uu_stats); wl_meanflow_update = update!(meanflow, flow) with the
+ * reference's weights (ε = dt/(dt + time(meanflow) + eps(T)), ε = 1 on the first update), over all cells, ghosts included;
+ * wl_meanflow_reset = reset!(meanflow; t_init); wl_meanflow_copy_to_flow = copy!(flow, meanflow) (u .= U; p .= P).
+ * wl_meanflow_download / _upload move P (which = 0, ΠN floats), U (1, D·ΠN) or UU (2, D·D·ΠN; component i + D·j) in the reference
+ * layout — upload is what load!(meanflow) of a checkpoint does (ext/WaterLilyJLD2Ext.jl:24-38); wl_meanflow_times reads / writes
+ * meanflow.t (buf = NULL queries the length). */
+int wl_meanflow_init(wl_handle* h, int uu_stats);
+int wl_meanflow_update(wl_handle* h);
+int wl_meanflow_reset(wl_handle* h, float t_init);
+int wl_meanflow_copy_to_flow(wl_handle* h);
+int wl_meanflow_download(wl_handle* h, int which, float* dst, int dst_is_device);
+int wl_meanflow_upload(wl_handle* h, int which, const float* src, int src_is_device);
+int wl_meanflow_get_times(wl_handle* h, float* buf, int* len);
+int wl_meanflow_set_times(wl_handle* h, const float* buf, int len);
+
+/* Enumerated forcings in place of the host closures g(i,x,t) and uBC(i,x,t) (accelerate!, src/Flow.jl:64-73, and
+ * BC! with a function uBC, src/core.jl:201-219), uniform in space:
+ *     g_i(t) = g0_i + g1_i·t                       (body force / reference-frame acceleration)
+ *     U_i(t) = cfg.uBC_i + U1_i·t + ½·U2_i·t²      (boundary velocity; its dU/dt = U1 + U2·t is added to the momentum equation)
+ * Every step adds g(t₀)+dU/dt(t₀) to the predictor's and g(t₁)+dU/dt(t₁) to the corrector's right-hand side (on every cell of r,
+ * ghosts included, like the reference's loop over CartesianIndices(r)) and applies BC! with U(t₁), t₁ = sum(Δt), t₀ = t₁ − Δt[end].
+ * Any pointer may be NULL (= zeros); all zeros switches the forcing off. */
+int wl_set_forcing(wl_handle* h, const float* g0, const float* g1, const float* U1, const float* U2);
+
 /* update!(pois) (src/WaterLily.jl:148, src/MultiLevelPoisson.jl:79-86, src/Poisson.jl:47): call after uploading μ₀
  * (measure!): set_diag! on level 1 and restrictL! + set_diag! on every coarse level. */
 int wl_update(wl_handle* h);

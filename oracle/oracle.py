@@ -56,6 +56,10 @@ def lib():
         L.wlo_measure_torus.argtypes = [C.c_void_p, fp, C.c_float, C.c_float, C.c_float]
         L.wlo_measure_prims.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.wlo_measure_prims.restype = None
+        L.wlo_body_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, fp, C.POINTER(C.c_double)]
+        L.wlo_body_forces.restype = None
+        L.wlo_set_forcing.argtypes = [C.c_void_p, fp, fp, fp, fp]
+        L.wlo_set_forcing.restype = None
         for name in ("wlo_dt_len", "wlo_iters_len", "wlo_log_len", "wlo_num_levels", "wlo_pois_solve"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_int
@@ -189,6 +193,36 @@ class OracleSim:
                 arr[q].c[d] = p["center"][d] if d < len(p["center"]) else 0.0
                 arr[q].vel[d] = p["vel"][d] if d < len(p["vel"]) else 0.0
         self.L.wlo_measure_prims(self.h, arr, len(prims), eps, t)
+
+    def _prim_array(self, prims):
+        class P(C.Structure):
+            _fields_ = [("kind", C.c_int), ("op", C.c_int), ("c", C.c_float * 3), ("R", C.c_float), ("r", C.c_float), ("vel", C.c_float * 3)]
+        arr = (P * len(prims))()
+        for q, p in enumerate(prims):
+            arr[q].kind, arr[q].op, arr[q].R, arr[q].r = p["kind"], p["op"], p["R"], p["r"]
+            for d in range(3):
+                arr[q].c[d] = p["center"][d] if d < len(p["center"]) else 0.0
+                arr[q].vel[d] = p["vel"][d] if d < len(p["vel"]) else 0.0
+        return arr
+
+    def body_forces(self, prims, x0=None, t=None):
+        """rows: pressure_force, viscous_force, pressure_moment(x₀), viscous_moment(x₀) (src/Metrics.jl:121-190) at t = time(flow)"""
+        arr = self._prim_array(prims)
+        x0a = np.zeros(3, np.float32)
+        if x0 is not None:
+            x0a[: len(x0)] = x0
+        out = (C.c_double * 12)()
+        self.L.wlo_body_forces(self.h, arr, len(prims), self.time() if t is None else t, _fp(x0a), out)
+        return np.array(out[:], np.float64).reshape(4, 3)[:, : self.D]
+
+    def set_forcing(self, g0=(0, 0, 0), g1=(0, 0, 0), U1=(0, 0, 0), U2=(0, 0, 0)):
+        """g_i(t) = g0_i + g1_i·t and U_i(t) = uBC_i + U1_i·t + ½·U2_i·t² in place of the closures g(i,x,t), uBC(i,x,t)"""
+        def v(a):
+            out = np.zeros(3, np.float32)
+            out[: len(a)] = a
+            return out
+        self._forcing = [v(g0), v(g1), v(U1), v(U2)]
+        self.L.wlo_set_forcing(self.h, *[_fp(a) for a in self._forcing])
 
     def time_next(self):
         """sum(Δt): the default t of measure!(sim) (src/WaterLily.jl:146)"""

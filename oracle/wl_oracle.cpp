@@ -602,6 +602,11 @@ struct Flow {
   SolverLog log;
   double tol = 1e-4;
   int itmx = 32;
+  // enumerated forcings standing in for the closures g(i,x,t) and uBC(i,x,t) (src/Flow.jl:64-73, src/core.jl:201-219):
+  // g_i(t) = g0_i + g1_i·t;  U_i(t) = uBC_i + U1_i·t + ½·U2_i·t²  (uniform in space)
+  bool forcing = false;
+  T g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, U1[3] = {0, 0, 0}, U2[3] = {0, 0, 0};
+  T ubc_t[3];  // uBC evaluated at the time the current BC! call is made at
   ~Flow() {
     delete ml;
     delete single;
@@ -659,7 +664,7 @@ static void project(Flow& a, T w) {  // mom_project! :223-232
   }
 #pragma omp parallel for schedule(static)
   for (size_t o = 0; o < n; o++) b.x[o] /= dt;
-  BC(g, a.u.data(), a.uBC, a.exit, a.per);
+  BC(g, a.u.data(), a.forcing ? a.ubc_t : a.uBC, a.exit, a.per);
 }
 static T CFL(Flow& a) {  // :234-244
   const Grid& g = a.g;
@@ -674,21 +679,42 @@ static T CFL(Flow& a) {  // :234-244
   for (size_t o = 0; o < n; o++) m = std::max(m, a.sigma[o]);
   return std::min((T)10, 1 / (m + 5 * a.nu));
 }
+// accelerate!(r,t,g,U): r[Ii] += g(i,x,t) + dU(i,x,t)/dt over ALL cells of r  (src/Flow.jl:64-73)
+static void accelerate(Flow& a, T t) {
+  if (!a.forcing) return;
+  const size_t n = a.g.n();
+  for (int i = 0; i < a.g.D; i++) {
+    const T acc = (a.g0[i] + a.g1[i] * t) + (a.U1[i] + a.U2[i] * t);
+    T* fi = a.f.data() + (size_t)i * n;
+#pragma omp parallel for schedule(static)
+    for (size_t o = 0; o < n; o++) fi[o] += acc;
+  }
+}
 static void mom_step(Flow& a) {  // mom_step! :156-167
   const Grid& g = a.g;
   a.u0 = a.u;
   scale_u(a, 0);
+  T t1 = 0, t0 = 0;
+  if (a.forcing) {  // t₁ = sum(a.Δt); t₀ = t₁ − a.Δt[end]  (the Float32 nearest to the exact sum, see oracle.py time())
+    double s = 0;
+    for (T v : a.dt) s += (double)v;
+    t1 = (T)s;
+    t0 = t1 - a.dt.back();
+    for (int i = 0; i < 3; i++) a.ubc_t[i] = a.uBC[i] + a.U1[i] * t1 + (a.U2[i] * t1) * t1 / 2;  // BC MUST be at t₁ (src/Flow.jl:194)
+  }
   // predictor  :190-196
   conv_diff(g, a.f.data(), a.u0.data(), a.sigma.data(), a.lam, a.nu, a.per);
+  accelerate(a, t0);
   BDIM(a);
-  BC(g, a.u.data(), a.uBC, a.exit, a.per);
+  BC(g, a.u.data(), a.forcing ? a.ubc_t : a.uBC, a.exit, a.per);
   if (a.exit) exitBC(g, a.u.data(), a.u0.data(), a.dt.back());
   project(a, 1);
   // corrector  :205-210
   conv_diff(g, a.f.data(), a.u.data(), a.sigma.data(), a.lam, a.nu, a.per);
+  accelerate(a, t1);
   BDIM(a);
   scale_u(a, 0.5f);
-  BC(g, a.u.data(), a.uBC, a.exit, a.per);
+  BC(g, a.u.data(), a.forcing ? a.ubc_t : a.uBC, a.exit, a.per);
   project(a, 0.5f);
   a.dt.push_back(CFL(a));
 }
@@ -827,6 +853,70 @@ static Meas csg_measure(const Prim* ps, int np, int D, const T* x, T t, T fastd2
     }
   }
   return acc;
+}
+// ---- forces and moments on the body (src/Metrics.jl:111-190) ----
+// nds(body,x,t) = n·kern(clamp(d,−1,1)) with (d,n) = measure(body,x,t,fastd²=1), kern(d) = (1+cospi(d))/2.
+// out[0:3] pressure_force, out[3:6] viscous_force, out[6:9] pressure_moment(x₀), out[9:12] viscous_moment(x₀); Float64 sums of the
+// Float32 per-cell vectors df[I,:] like sum(Float64, df, dims=…).  2-D moments: cross of 2-vectors is the scalar a₁b₂−a₂b₁,
+// broadcast into both components of df.
+static void body_forces(Flow& a, const Prim* ps, int np, T t, const T* x0, double* out) {
+  const Grid& g = a.g;
+  const size_t n = g.n();
+  const int D = g.D;
+  for (int q = 0; q < 12; q++) out[q] = 0;
+  const T* u = a.u.data();
+  const T nu2 = -2 * a.nu;
+  auto U = [&](I3 I, int i) { return u[g.at(I) + n * i]; };
+  auto dd = [&](int i, int j, I3 I) -> T {  // ∂(i,j,I,u)  src/Metrics.jl:42-44
+    if (i == j) return U(shift(I, i), i) - U(I, i);
+    I3 P = shift(I, j), M = shift(I, j, -1);
+    return (U(P, i) + U(shift(P, i), i) - U(M, i) - U(shift(M, i), i)) / 4;
+  };
+  double acc[12] = {0};
+  Range R = inside(g);
+  for (int k = R.lo[2]; k <= R.hi[2]; k++)
+    for (int j = R.lo[1]; j <= R.hi[1]; j++)
+      for (int i = R.lo[0]; i <= R.hi[0]; i++) {
+        I3 I{{i, j, k}};
+        T x[3] = {0, 0, 0};
+        for (int d = 0; d < D; d++) x[d] = (T)I.v[d] - 1.5f;
+        Meas m = csg_measure(ps, np, D, x, t, (T)1);
+        T kd = (1 + cospiT(std::max((T)-1, std::min(m.d, (T)1)))) / 2;
+        T nds[3] = {0, 0, 0};
+        for (int d = 0; d < D; d++) nds[d] = m.n[d] * kd;
+        T S[3][3] = {{0}}, Sn[3] = {0, 0, 0}, fv[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+        for (int p = 0; p < D; p++)
+          for (int q = 0; q < D; q++) S[p][q] = (dd(p, q, I) + dd(q, p, I)) / 2;
+        for (int p = 0; p < D; p++) {
+          T s1 = 0, s2 = 0;
+          for (int q = 0; q < D; q++) {
+            s1 = q == 0 ? S[p][q] * nds[q] : s1 + S[p][q] * nds[q];
+            s2 = q == 0 ? (nu2 * S[p][q]) * nds[q] : s2 + (nu2 * S[p][q]) * nds[q];
+          }
+          Sn[p] = s1;
+          fv[p] = s2;
+        }
+        for (int d = 0; d < D; d++) r[d] = x[d] - x0[d];
+        T pr = a.p[g.at(I)];
+        T pm[3], vm[3];
+        if (D == 3) {
+          T c1[3] = {r[1] * nds[2] - r[2] * nds[1], r[2] * nds[0] - r[0] * nds[2], r[0] * nds[1] - r[1] * nds[0]};
+          T c2[3] = {r[1] * Sn[2] - r[2] * Sn[1], r[2] * Sn[0] - r[0] * Sn[2], r[0] * Sn[1] - r[1] * Sn[0]};
+          for (int d = 0; d < 3; d++) pm[d] = pr * c1[d], vm[d] = nu2 * c2[d];
+        } else {
+          T c1 = r[0] * nds[1] - r[1] * nds[0], c2 = r[0] * Sn[1] - r[1] * Sn[0];
+          pm[0] = pm[1] = pr * c1;
+          vm[0] = vm[1] = nu2 * c2;
+          pm[2] = vm[2] = 0;
+        }
+        for (int d = 0; d < D; d++) {
+          acc[d] += (double)(T)(pr * nds[d]);
+          acc[3 + d] += (double)fv[d];
+          acc[6 + d] += (double)pm[d];
+          acc[9 + d] += (double)vm[d];
+        }
+      }
+  for (int q = 0; q < 12; q++) out[q] = acc[q];
 }
 static void measure_prims(Flow& a, const Prim* ps, int np, T eps, T t) {  // measure!(flow, body; t, ϵ)  src/Body.jl:28-51
   const Grid& g = a.g;
@@ -988,6 +1078,14 @@ void wlo_measure_torus(void* h, const float* c, float R, float r, float eps) {
 }
 // measure!(flow, body; t, ϵ) for a body made of `np` primitives (struct layout = wl_body_prim of include/wl_b200.h)
 void wlo_measure_prims(void* h, const void* prims, int np, float eps, float t) { measure_prims(*(Flow*)h, (const Prim*)prims, np, eps, t); }
+// enumerated forcings (see struct Flow): g_i(t) = g0_i + g1_i·t, U_i(t) = uBC_i + U1_i·t + ½·U2_i·t²
+void wlo_set_forcing(void* h, const float* g0, const float* g1, const float* U1, const float* U2) {
+  Flow* a = (Flow*)h;
+  a->forcing = true;
+  for (int i = 0; i < 3; i++) a->g0[i] = g0[i], a->g1[i] = g1[i], a->U1[i] = U1[i], a->U2[i] = U2[i];
+}
+// pressure_force / viscous_force / pressure_moment / viscous_moment at time t about x0 (out: 12 doubles, see body_forces)
+void wlo_body_forces(void* h, const void* prims, int np, float t, const float* x0, double* out) { body_forces(*(Flow*)h, (const Prim*)prims, np, t, x0, out); }
 // pois_ctor(flow): MultiLevelPoisson(flow.p,flow.μ₀,flow.σ;perdir) (kind 0) or Poisson(...) (kind 1)
 int wlo_init_pois(void* h, int kind) {
   Flow* a = (Flow*)h;

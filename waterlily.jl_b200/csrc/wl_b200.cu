@@ -175,9 +175,20 @@ struct wl_handle {
   int* d_flags = nullptr;  // [0]: a velocity field holds a non-finite value (or |u| > 1e37); [2]: range word of the current u, [3]: its ticket (range_note)
   float* stage = nullptr;  // dense staging buffer of one component for host transfers
   size_t stage_cap = 0;
+  // MeanFlow (src/Metrics.jl:205-257): device-resident running averages
+  float *mfP = nullptr, *mfU = nullptr, *mfUU = nullptr;
+  std::vector<float> mft;
+  bool mf_uu = false;
+  RedBuf force_red{nullptr, nullptr, nullptr};  // wl_body_forces: 12 sums per block
+  size_t force_cap = 0;
   BodySet body;            // parametrised body registered with wl_set_body (np = 0: none)
   float body_eps = 1.f;
   bool remeasure = false;  // every step starts with measure!(sim, t=sum(Δt)) + update!(pois)
+  // enumerated forcings in place of the closures g(i,x,t), uBC(i,x,t): g_i(t) = g0_i + g1_i·t, U_i(t) = uBC_i + U1_i·t + ½·U2_i·t²
+  bool forcing = false;
+  float fg0[3] = {0, 0, 0}, fg1[3] = {0, 0, 0}, fU1[3] = {0, 0, 0}, fU2[3] = {0, 0, 0};
+  Force fc{0, {0.f, 0.f, 0.f}};  // what the flux kernels of the current stage add to r
+  float ubc_now[3] = {0, 0, 0};  // uBC at the time the step's BC! calls are made at (t₁)
   bool range_checked = false;  // the current u was range-checked by the kernel that wrote it (range_note, wl_common.cuh)
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
@@ -530,7 +541,7 @@ static void step_bc(wl_handle* h, const float* keep) {
     h->ghosts_dirty = true;
     return;
   }
-  launch_bc_vec(h, h->g, h->u, h->cfg.uBC, h->cfg.exitBC, keep);
+  launch_bc_vec(h, h->g, h->u, h->forcing ? h->ubc_now : h->cfg.uBC, h->cfg.exitBC, keep);
 }
 static void flush_ghosts(wl_handle* h) {
   if (!h->ghosts_dirty) return;
@@ -1287,9 +1298,9 @@ static void conv_launch(wl_handle* h, const float* ua, int mode) {
   Box all = h->levels[0].all();
   prof_begin(h, "k_conv_bdim1");
   if (h->D == 3)
-    k_conv_bdim1<3, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode);
+    k_conv_bdim1<3, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
   else
-    k_conv_bdim1<2, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode);
+    k_conv_bdim1<2, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
   prof_end(h);
   h->launches++;
 }
@@ -1329,10 +1340,10 @@ static int fconv_launch(wl_handle* h, const float* ua, float* out, int corrector
     // the fast-division instance, then the IEEE-division instance on the same grid: the device-side range word picks the one that
     // runs (the other returns at once), so no host decision and no second pass over marked blocks
     prof_begin(h, "fm_conv4");
-    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2);
+    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2, h->fc);
     prof_end(h);
     prof_begin(h, "fm_conv4_exact");
-    fm_conv4<LAM, true><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2);
+    fm_conv4<LAM, true><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2, h->fc);
     prof_end(h);
     h->launches += 2;
     return 0;
@@ -1340,10 +1351,10 @@ static int fconv_launch(wl_handle* h, const float* ua, float* out, int corrector
   prof_begin(h, "fm_conv");
   if (nowall)
     fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                            h->red, SLOT_PHIMAX, h->uext, h->d_flags);
+                                                                            h->red, SLOT_PHIMAX, h->uext, h->d_flags, h->fc);
   else
     fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                             h->red, SLOT_PHIMAX, h->uext, h->d_flags);
+                                                                             h->red, SLOT_PHIMAX, h->uext, h->d_flags, h->fc);
   prof_end(h);
   h->launches++;
   return 0;
@@ -1376,7 +1387,7 @@ static int momentum(wl_handle* h, int corrector) {
     TRY(fconv<false>(h, corrector ? h->u : h->u0, h->f, corrector));
     dim3 pb(32, 8, 1);
     int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
-    LAUNCH(h, k_f_lowghost, dim3(cdiv(m0, 32), cdiv(m1, 8), 3), pb, g, (const float*)h->u0, (const float*)h->V, h->f, dtp(h));
+    LAUNCH(h, k_f_lowghost, dim3(cdiv(m0, 32), cdiv(m1, 8), 3), pb, g, (const float*)h->u0, (const float*)h->V, h->f, dtp(h), h->fc);
     TRY(exch(h, l, h->f, 3));  // BDIM-2 reads f one plane beyond the slab
   } else
     conv_bdim1(h, corrector ? h->u : h->u0, 1);
@@ -1488,21 +1499,48 @@ static int sync_dt(wl_handle* h) {  // mirror device Δt history to the host vec
 }
 
 // mom_step!(a,b)  src/Flow.jl:156-167
+// time(a) = sum(@view a.Δt[1:end-1]) (src/Flow.jl:174; all = false) and sum(a.Δt) (measure!(sim)'s default t; all = true).
+// Julia's Float32 `sum` is pairwise in blocks of 1024 with a @simd inner loop: its rounding depends on the vector width (unpinned),
+// but it stays within a few ulp of the exact sum for any length.  Here the sum is accumulated incrementally in double (O(1) per
+// step; the running Float32 loop this replaces was O(n) per call and drifted by O(n·eps) from the reference after thousands of
+// steps) and rounded to Float32 once, i.e. the Float32 nearest to the exact sum.
+static int time_sum(wl_handle* h, bool all, double* t) {
+  TRY(sync_dt(h));
+  const size_t n = h->dt.empty() ? 0 : h->dt.size() - 1;
+  if (h->tsum_n > n) h->tsum_n = 0, h->tsum = 0.0;
+  for (; h->tsum_n < n; h->tsum_n++) h->tsum += (double)h->dt[h->tsum_n];
+  *t = (double)(float)(all && !h->dt.empty() ? h->tsum + (double)h->dt.back() : h->tsum);
+  return 0;
+}
 static int mom_step(wl_handle* h) {
   TRY(ensure_hierarchy(h));
   TRY(ensure_dt_capacity(h, h->dt_dev_len + 1));
+  float t0 = 0.f, t1 = 0.f;
+  if (h->forcing) {  // t₁ = sum(a.Δt); t₀ = t₁ − a.Δt[end]  (src/Flow.jl:157); BC! at t₁ (src/Flow.jl:194,209,230)
+    double s;
+    TRY(time_sum(h, true, &s));
+    t1 = (float)s;
+    t0 = t1 - h->dt.back();
+    for (int i = 0; i < 3; i++) h->ubc_now[i] = h->cfg.uBC[i] + h->fU1[i] * t1 + (h->fU2[i] * t1) * t1 / 2.f;
+  }
+  auto stage_force = [&](float t) {  // accelerate!(a.f, t, a.g, a.uBC): g(i,x,t) + dU(i,x,t)/dt
+    h->fc.on = h->forcing ? 1 : 0;
+    for (int i = 0; i < 3; i++) h->fc.a[i] = (h->fg0[i] + h->fg1[i] * t) + (h->fU1[i] + h->fU2[i] * t);
+  };
   const Grid& g = h->g;
   dim3 b = blk(h->D);
   Level& l = h->levels[0];
   Box in = l.inside(), all = l.all();
   std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
   // predictor  src/Flow.jl:190-196
+  stage_force(t0);
   TRY(momentum(h, 0));
   step_bc(h, h->u0);
   if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
   TRY(exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
+  stage_force(t1);
   TRY(momentum(h, 1));
   step_bc(h, h->u);
   TRY(exch_u(h, h->u));
@@ -1853,6 +1891,8 @@ int wl_destroy(wl_handle* h) {
   // (the communicator belongs to the process-wide cache and outlives the handle)
   for (void* q : h->allocs) cudaFree(q);
   if (h->stage) cudaFree(h->stage);
+  if (h->force_red.partials) cudaFree(h->force_red.partials);
+  if (h->force_red.out) cudaFree(h->force_red.out);
   if (h->d_dthist) cudaFree(h->d_dthist);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_ops) cudaFreeHost(h->h_ops);
@@ -1932,19 +1972,6 @@ int wl_update(wl_handle* h) {
   return update_levels(h);
 }
 
-// time(a) = sum(@view a.Δt[1:end-1]) (src/Flow.jl:174; all = false) and sum(a.Δt) (measure!(sim)'s default t; all = true).
-// Julia's Float32 `sum` is pairwise in blocks of 1024 with a @simd inner loop: its rounding depends on the vector width (unpinned),
-// but it stays within a few ulp of the exact sum for any length.  Here the sum is accumulated incrementally in double (O(1) per
-// step; the running Float32 loop this replaces was O(n) per call and drifted by O(n·eps) from the reference after thousands of
-// steps) and rounded to Float32 once, i.e. the Float32 nearest to the exact sum.
-static int time_sum(wl_handle* h, bool all, double* t) {
-  TRY(sync_dt(h));
-  const size_t n = h->dt.empty() ? 0 : h->dt.size() - 1;
-  if (h->tsum_n > n) h->tsum_n = 0, h->tsum = 0.0;
-  for (; h->tsum_n < n; h->tsum_n++) h->tsum += (double)h->dt[h->tsum_n];
-  *t = (double)(float)(all && !h->dt.empty() ? h->tsum + (double)h->dt.back() : h->tsum);
-  return 0;
-}
 // measure!(flow, body; t, ϵ) for the registered body (src/Body.jl:28-51)
 static int measure_body(wl_handle* h, float t) {
   if (h->body.np <= 0) return fail("wl_measure: no body registered (wl_set_body)");
@@ -1988,6 +2015,148 @@ int wl_measure(wl_handle* h, float t) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   return measure_body(h, t);
+}
+
+int wl_body_forces(wl_handle* h, const float* x0, double* out12) {
+  if (!h || !out12) return fail("null argument");
+  if (h->body.np <= 0) return fail("wl_body_forces: no body registered (wl_set_body)");
+  CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
+  dim3 b = h->D == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
+  Box in = h->levels[0].inside();
+  const dim3 gr = grd(in, b);
+  const size_t need = (size_t)12 * ((size_t)gr.x * gr.y * gr.z + gr.z + 1);
+  if (!h->force_red.partials || h->force_cap < need) {  // own partial sums: 12 values per block
+    if (h->force_red.partials) CK(cudaFree(h->force_red.partials));
+    if (!h->force_red.out) CK(cudaMalloc((void**)&h->force_red.out, 16 * sizeof(double)));
+    CK(cudaMalloc((void**)&h->force_red.partials, need * sizeof(double)));
+    h->force_cap = need;
+    h->force_red.ticket = h->red.ticket;
+  }
+  double t;
+  TRY(time_sum(h, false, &t));  // time(flow)
+  const float z[3] = {0.f, 0.f, 0.f};
+  const float* c = x0 ? x0 : z;
+  LAUNCH_D(h, k_forces, gr, b, h->g, in, h->body, (float)t, h->cfg.nu, c[0], h->D > 1 ? c[1] : 0.f, h->D > 2 ? c[2] : 0.f, (const float*)h->u,
+           (const float*)h->p, h->force_red, 0);
+  if (h->dist.on()) {
+    prof_begin(h, "allreduce");
+    NCK(g_nccl.AllReduce(h->force_red.out, h->force_red.out, 12, WL_NCCL_DOUBLE, WL_NCCL_SUM, h->dist.comm, h->st));
+    prof_end(h);
+  }
+  CK(cudaMemcpyAsync(out12, h->force_red.out, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int wl_meanflow_init(wl_handle* h, int uu_stats) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->mfP && (uu_stats != 0) != h->mf_uu && uu_stats) {
+    if (!h->mfUU) TRY(dalloc(h, &h->mfUU, (size_t)h->g.sc * h->D * h->D));
+  }
+  if (!h->mfP) {
+    TRY(dalloc(h, &h->mfP, (size_t)h->g.sc));
+    TRY(dalloc(h, &h->mfU, (size_t)h->g.sc * h->D));
+    if (uu_stats) TRY(dalloc(h, &h->mfUU, (size_t)h->g.sc * h->D * h->D));
+  }
+  h->mf_uu = uu_stats != 0;
+  double t;
+  TRY(time_sum(h, false, &t));
+  return wl_meanflow_reset(h, (float)t);
+}
+
+int wl_meanflow_reset(wl_handle* h, float t_init) {
+  if (!h) return fail("null handle");
+  if (!h->mfP) return fail("no MeanFlow (wl_meanflow_init)");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->mfP, 0, (size_t)h->g.sc * sizeof(float), h->st));
+  CK(cudaMemsetAsync(h->mfU, 0, (size_t)h->g.sc * h->D * sizeof(float), h->st));
+  if (h->mfUU) CK(cudaMemsetAsync(h->mfUU, 0, (size_t)h->g.sc * h->D * h->D * sizeof(float), h->st));
+  h->mft.assign(1, t_init);
+  return 0;
+}
+
+int wl_meanflow_update(wl_handle* h) {
+  if (!h) return fail("null handle");
+  if (!h->mfP) return fail("no MeanFlow (wl_meanflow_init)");
+  CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
+  launch_perbc(h, h->g, h->p);  // the reference's solver leaves p with its periodic ghosts filled
+  double tf;
+  TRY(time_sum(h, false, &tf));
+  const float dt = (float)tf - h->mft.back();
+  const float tm = h->mft.back() - h->mft.front();  // time(meanflow)
+  float eps = dt / (dt + tm + 1.1920929e-7f);
+  if (h->mft.size() == 1) eps = 1.f;
+  LAUNCH(h, k_meanflow, 1184, 256, (long long)h->g.sc, h->D, h->mf_uu ? 1 : 0, eps, (const float*)h->p, (const float*)h->u, h->mfP, h->mfU, h->mfUU);
+  h->mft.push_back(h->mft.back() + dt);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wl_meanflow_copy_to_flow(wl_handle* h) {
+  if (!h) return fail("null handle");
+  if (!h->mfP) return fail("no MeanFlow (wl_meanflow_init)");
+  CK(cudaSetDevice(h->cfg.device));
+  flush_ghosts(h);
+  h->range_checked = false;
+  CK(cudaMemcpyAsync(h->u, h->mfU, (size_t)h->g.sc * h->D * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaMemcpyAsync(h->p, h->mfP, (size_t)h->g.sc * sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+  return 0;
+}
+
+static int meanflow_ptr(wl_handle* h, int which, float** p, int* nc) {
+  if (!h->mfP) return fail("no MeanFlow (wl_meanflow_init)");
+  if (which == 0) { *p = h->mfP; *nc = 1; return 0; }
+  if (which == 1) { *p = h->mfU; *nc = h->D; return 0; }
+  if (which == 2) {
+    if (!h->mfUU) return fail("this MeanFlow was created without uu_stats");
+    *p = h->mfUU; *nc = h->D * h->D; return 0;
+  }
+  return fail("unknown MeanFlow array %d", which);
+}
+int wl_meanflow_download(wl_handle* h, int which, float* dst, int dst_is_device) {
+  if (!h || !dst) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(meanflow_ptr(h, which, &p, &nc));
+  return copy_out(h, h->g, dst, p, nc, dst_is_device);
+}
+int wl_meanflow_upload(wl_handle* h, int which, const float* src, int src_is_device) {
+  if (!h || !src) return fail("null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  float* p;
+  int nc;
+  TRY(meanflow_ptr(h, which, &p, &nc));
+  return copy_in(h, h->g, p, src, nc, src_is_device);
+}
+int wl_meanflow_get_times(wl_handle* h, float* buf, int* len) {
+  if (!h || !len) return fail("null argument");
+  if (buf) std::copy(h->mft.begin(), h->mft.begin() + std::min<int>(*len, (int)h->mft.size()), buf);
+  *len = (int)h->mft.size();
+  return 0;
+}
+int wl_meanflow_set_times(wl_handle* h, const float* buf, int len) {
+  if (!h || !buf || len < 1) return fail("bad argument");
+  h->mft.assign(buf, buf + len);
+  return 0;
+}
+
+int wl_set_forcing(wl_handle* h, const float* g0, const float* g1, const float* U1, const float* U2) {
+  if (!h) return fail("null handle");
+  const float* src[4] = {g0, g1, U1, U2};
+  float* dst[4] = {h->fg0, h->fg1, h->fU1, h->fU2};
+  bool any = false;
+  for (int q = 0; q < 4; q++)
+    for (int i = 0; i < 3; i++) {
+      dst[q][i] = (src[q] && i < h->D) ? src[q][i] : 0.f;
+      any = any || dst[q][i] != 0.f;
+    }
+  h->forcing = any;
+  for (int i = 0; i < 3; i++) h->ubc_now[i] = h->cfg.uBC[i];
+  return 0;
 }
 
 int wl_set_remeasure(wl_handle* h, int enabled) {

@@ -30,6 +30,13 @@ struct Grid {
   int zoff;
 };
 
+// accelerate!(r,t,g,U) (src/Flow.jl:64-73) for forcings that are uniform in space: r[I,i] += a[i] on every cell of r, with
+// a[i] = g_i(t) + dU_i/dt(t) evaluated by the host for the stage's time.  on = 0: no forcing (r is left untouched, bit for bit).
+struct Force {
+  int on;
+  float a[3];
+};
+
 struct Box {
   int lo[3];
   int n[3];

@@ -140,7 +140,7 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 template <int LAM, bool EXACT>
 __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__ Grid g, const float* __restrict__ ua, const float* __restrict__ u0,
                                                          float* __restrict__ out, const float* __restrict__ dtp, float nu, int zchunk, int corrector, RedBuf R,
-                                                         int slot, const float* __restrict__ uext, int* __restrict__ rflag) {
+                                                         int slot, const float* __restrict__ uext, int* __restrict__ rflag, const Force fc) {
   if ((*reinterpret_cast<volatile int*>(rflag) != 0) != EXACT) return;
   const int vbx = blockIdx.x, vby = blockIdx.y, vbz = blockIdx.z;
   extern __shared__ float4 smem4[];
@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__
       const i64 o = (i64)g.xo + x0 + g.s[1] * y + g.s[2] * z;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
+        if (fc.on) acc_add(r[c], splat4(fc.a[c]));      // accelerate! (src/Flow.jl:64-73)
         const float4 b = corrector ? ub[c] : own[c];  // predictor: ua is u⁰ itself, already in the tile
         float2 f01 = add2x(lo2(b), mul2(dt2, lo2(r[c]))), f23 = add2x(hi2(b), mul2(dt2, hi2(r[c])));
         if (corrector) {

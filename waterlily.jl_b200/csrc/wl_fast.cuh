@@ -938,7 +938,7 @@ __device__ __forceinline__ float flux_from(float uf, float um2, float um1, float
 template <int LAM, bool FUSE, bool PER3>
 __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restrict__ ua, const float* __restrict__ u0, const float* __restrict__ V,
                                                     float* __restrict__ out, float* __restrict__ sigma, const float* __restrict__ dtp, float nu, int zchunk,
-                                                    int corrector, RedBuf R, int slot, const float* __restrict__ uext, int* __restrict__ flag) {
+                                                    int corrector, RedBuf R, int slot, const float* __restrict__ uext, int* __restrict__ flag, const Force fc) {
   extern __shared__ float smem_raw[];
   float* const T = smem_raw;  // [CRING][3][CH][CW]
   constexpr int PL = CH * CW;  // one component plane
@@ -1122,6 +1122,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
           r += Fz[i];
           r -= Fzhi[i];
         }
+        if (fc.on) r += fc.a[i];  // accelerate! (src/Flow.jl:64-73)
         const i64 oc = o + (i64)i * g.sc;
         if (FUSE) {
           const float f = u0[oc] + dt * r;  // − V with V ≡ 0; then X = 0/2 + 0 + 1·f
@@ -1160,7 +1161,8 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
 }
 
 // f on the lower ghost planes (any index 0): r = 0 there, so f = u⁰ + Δt·0 − V  (src/Flow.jl:178 over CartesianIndices(f))
-__global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f, const float* __restrict__ dtp) {
+__global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f, const float* __restrict__ dtp,
+                             const Force fc) {
   const int j = blockIdx.z;  // plane I_j = 0
   if (j == 2 && g.zopen[0]) return;  // slab-internal face: that plane of f arrives by halo exchange
   const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
@@ -1172,7 +1174,7 @@ __global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* 
   I[db] = t1;
   const i64 o = cell_off(g, I);
   const float dt = *dtp;
-  for (int i = 0; i < 3; i++) f[o + g.sc * i] = u0[o + g.sc * i] + dt * 0.f - V[o + g.sc * i];
+  for (int i = 0; i < 3; i++) f[o + g.sc * i] = u0[o + g.sc * i] + dt * (fc.on ? 0.f + fc.a[i] : 0.f) - V[o + g.sc * i];
 }
 
 // max of σ over the ghost cells (where the reference's stale Φ lives) → out[slot]; planes selected by blockIdx.z

@@ -94,7 +94,7 @@ __device__ __forceinline__ float face_flux(const Grid& g, const float* __restric
 template <int D, int LAM>
 __global__ void __launch_bounds__(512) k_conv_bdim1(Grid g, Box box, const float* __restrict__ ua, const float* __restrict__ u0,
                                                     const float* __restrict__ V, float* __restrict__ f, float* __restrict__ sigma,
-                                                    const float* __restrict__ dtp, float nu, int mode) {
+                                                    const float* __restrict__ dtp, float nu, int mode, const Force fc) {
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(512) k_conv_bdim1(Grid g, Box box, const float
       }
     }
     const i64 oc = o + (i64)i * g.sc;
+    if (mode && fc.on) r += fc.a[i];  // accelerate!
     f[oc] = mode ? (u0[oc] + dt * r - V[oc]) : r;
   }
   bool ghost = false;
@@ -1009,5 +1010,90 @@ __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ Grid g,
     V[o + g.sc * i] = v[i];
     mu0[o + g.sc * i] = m0[i];
     for (int j = 0; j < D; j++) mu1[o + g.sc * (i + D * j)] = m1[i + D * j];
+  }
+}
+
+// ================================================================================================
+// Forces and moments on the body (src/Metrics.jl:111-190) as ONE fused device reduction:
+//   pressure_force  Σ p[I]·nds            viscous_force  Σ −2ν·S(I,u)·nds
+//   pressure_moment Σ p[I]·(x−x₀)×nds     viscous_moment Σ −2ν·(x−x₀)×(S(I,u)·nds)
+// with nds(body,x,t) = n·kern(clamp(d,−1,1)), (d,n) = measure(body,x,t,fastd²=1), kern(d) = (1+cospi(d))/2, over inside(p).
+// The per-cell vectors are Float32 like the reference's df; the sums are Float64 (sum(Float64, df)), deterministic.
+// out[slot0 + 0:3 | 3:6 | 6:9 | 9:12].
+// ================================================================================================
+template <int D>
+__global__ void __launch_bounds__(256) k_forces(const __grid_constant__ Grid g, Box box, const __grid_constant__ BodySet B, float t, float nu, float x00,
+                                                float x01, float x02, const float* __restrict__ u, const float* __restrict__ p, RedBuf R, int slot0) {
+  int I[3];
+  const bool ok = thread_cell<D>(box, I);
+  double v[12], fin[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) v[q] = 0.0;
+  if (ok) {
+    const i64 o = cell_off(g, I);
+    float x[3] = {0.f, 0.f, 0.f};
+    for (int d = 0; d < D; d++) x[d] = (float)(I[d] + 1 + (d == 2 ? g.zoff : 0)) - 1.5f;
+    const Meas m = csg_measure(B, D, x, t, 1.f);
+    const float kd = (1.f + cospi_f(fmaxf(-1.f, fminf(m.d, 1.f)))) / 2.f;
+    float nds[3] = {0.f, 0.f, 0.f};
+    for (int d = 0; d < D; d++) nds[d] = m.n[d] * kd;
+    if (nds[0] != 0.f || nds[1] != 0.f || nds[2] != 0.f) {  // (every term below is a multiple of nds: exact zeros elsewhere)
+      const float nu2 = -2.f * nu;
+      auto U = [&](i64 off, int i) { return u[o + off + g.sc * i]; };
+      auto dd = [&](int i, int j) -> float {  // ∂(i,j,I,u)
+        if (i == j) return U(g.s[i], i) - U(0, i);
+        return (U(g.s[j], i) + U(g.s[j] + g.s[i], i) - U(-g.s[j], i) - U(-g.s[j] + g.s[i], i)) / 4.f;
+      };
+      float S[3][3], Sn[3] = {0.f, 0.f, 0.f}, fv[3] = {0.f, 0.f, 0.f}, r[3] = {0.f, 0.f, 0.f};
+      for (int a = 0; a < D; a++)
+        for (int b = 0; b < D; b++) S[a][b] = (dd(a, b) + dd(b, a)) / 2.f;
+      for (int a = 0; a < D; a++) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int b = 0; b < D; b++) {
+          s1 = b == 0 ? S[a][b] * nds[b] : s1 + S[a][b] * nds[b];
+          s2 = b == 0 ? (nu2 * S[a][b]) * nds[b] : s2 + (nu2 * S[a][b]) * nds[b];
+        }
+        Sn[a] = s1;
+        fv[a] = s2;
+      }
+      const float x0[3] = {x00, x01, x02};
+      for (int d = 0; d < D; d++) r[d] = x[d] - x0[d];
+      const float pr = p[o];
+      float pm[3] = {0.f, 0.f, 0.f}, vm[3] = {0.f, 0.f, 0.f};
+      if (D == 3) {
+        const float c1[3] = {r[1] * nds[2] - r[2] * nds[1], r[2] * nds[0] - r[0] * nds[2], r[0] * nds[1] - r[1] * nds[0]};
+        const float c2[3] = {r[1] * Sn[2] - r[2] * Sn[1], r[2] * Sn[0] - r[0] * Sn[2], r[0] * Sn[1] - r[1] * Sn[0]};
+        for (int d = 0; d < 3; d++) pm[d] = pr * c1[d], vm[d] = nu2 * c2[d];
+      } else {
+        const float c1 = r[0] * nds[1] - r[1] * nds[0], c2 = r[0] * Sn[1] - r[1] * Sn[0];
+        pm[0] = pm[1] = pr * c1;
+        vm[0] = vm[1] = nu2 * c2;
+      }
+      for (int d = 0; d < D; d++) {
+        v[d] = (double)(pr * nds[d]);
+        v[3 + d] = (double)fv[d];
+        v[6 + d] = (double)pm[d];
+        v[9 + d] = (double)vm[d];
+      }
+    }
+  }
+  grid_reduce<RED_SUM, 12>(v, R, slot0, fin);
+}
+
+// update!(meanflow, flow) (src/Metrics.jl:236-247): P = ε·p + (1−ε)·P, U = ε·u + (1−ε)·U, UU[i,j] = ε·(u_i·u_j) + (1−ε)·UU[i,j]
+// over every cell of the arrays (ghosts included; the pitched layout's padding rides along).  n = floats of one scalar field.
+__global__ void __launch_bounds__(256) k_meanflow(long long n, int D, int uu, float eps, const float* __restrict__ p, const float* __restrict__ u,
+                                                  float* __restrict__ P, float* __restrict__ U, float* __restrict__ UU) {
+  const float om = 1.f - eps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    P[i] = eps * p[i] + om * P[i];
+    float v[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < D; c++) {
+      v[c] = u[i + n * c];
+      U[i + n * c] = eps * v[c] + om * U[i + n * c];
+    }
+    if (uu)
+      for (int a = 0; a < D; a++)
+        for (int b = 0; b < D; b++) UU[i + n * (a + D * b)] = eps * (v[a] * v[b]) + om * UU[i + n * (a + D * b)];
   }
 }

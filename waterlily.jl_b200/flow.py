@@ -19,6 +19,28 @@ _FIELDS = {"u": 0, "u0": 1, "f": 2, "p": 3, "sigma": 4, "V": 5, "mu0": 6, "mu1":
 _LVL = {"L": 0, "D": 1, "iD": 2, "x": 3, "eps": 4, "r": 5, "z": 6}
 
 
+class Forcing:
+    """g(i,x,t) = g0[i] + g1[i]·t: the enumerated, spatially uniform stand-in for the reference's body-force closure `g`
+    (accelerate!, src/Flow.jl:64-73).  Evaluated on the device inside the flux kernels."""
+
+    def __init__(self, g0=None, g1=None):
+        self.g0, self.g1 = g0, g1
+
+
+class TimeBC:
+    """uBC(i,x,t) = U0[i] + U1[i]·t + ½·U2[i]·t²: the enumerated stand-in for a function-valued boundary velocity (BC! with a
+    function uBC, src/core.jl:201-219; its time derivative enters accelerate!, src/Flow.jl:72)."""
+
+    def __init__(self, U0, U1=None, U2=None):
+        self.U0, self.U1, self.U2 = tuple(float(v) for v in U0), U1, U2
+
+    def __iter__(self):
+        return iter(self.U0)
+
+    def __len__(self):
+        return len(self.U0)
+
+
 def loc_grid(N, i, zoff=0):
     """loc(i,I) for all cells of a ghost-padded grid (src/core.jl:177): list of D broadcastable coordinate arrays."""
     from .body import _loc
@@ -41,9 +63,14 @@ class Flow:
     def __init__(self, N, uBC, Δt=0.25, ν=0.0, g=None, u0=None, perdir=(), exitBC=False, λ=quick, T=np.float32,
                  pois="multilevel", smoother="gs", tol=1e-4, itmx=0, device=0, fmad=False, flags=0, dist=None):
         if callable(uBC):
-            raise _lib.WLError("function-valued uBC is a host closure: not supported by the B200 C ABI (SURVEY.md §8b)")
-        if g is not None:
-            raise _lib.WLError("acceleration g(i,x,t) is a host closure: not supported by the B200 C ABI")
+            raise _lib.WLError("function-valued uBC is a host closure: not supported by the B200 C ABI (SURVEY.md §8b); "
+                               "use TimeBC(U0, U1, U2) for U(t) = U0 + U1·t + ½·U2·t²")
+        if g is not None and not isinstance(g, Forcing):
+            raise _lib.WLError("acceleration g(i,x,t) is a host closure: not supported by the B200 C ABI; "
+                               "use Forcing(g0, g1) for g(t) = g0 + g1·t")
+        tbc = uBC if isinstance(uBC, TimeBC) else None
+        if tbc is not None:
+            uBC = tbc.U0
         if np.dtype(T) != np.float32:
             raise _lib.WLError("only T=Float32 is supported")
         self.L = _lib.load_library(fmad)
@@ -85,6 +112,14 @@ class Flow:
             _lib.check(self.L, self.L.wl_create_dist(C.byref(cfg), self.rank, self.world, idb, C.byref(self.h)))
         else:
             _lib.check(self.L, self.L.wl_create(C.byref(cfg), C.byref(self.h)))
+        if g is not None or tbc is not None:
+            def v3(a):
+                out = (C.c_float * 3)()
+                for d, x in enumerate(a or ()):
+                    out[d] = float(x)
+                return out
+            _lib.check(self.L, self.L.wl_set_forcing(self.h, v3(g.g0 if g else None), v3(g.g1 if g else None),
+                                                     v3(tbc.U1 if tbc else None), v3(tbc.U2 if tbc else None)))
         if u0 is not None:
             # apply!(u0, a.u) (src/Flow.jl:140): component by component, so that an array the caller already holds goes to the
             # device without being assembled into one more host copy

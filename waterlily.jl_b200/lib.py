@@ -111,6 +111,16 @@ def load_library(fmad=False):
         "wl_measure": [H, C.c_float],
         "wl_set_remeasure": [H, C.c_int],
         "wl_time_next": [H, C.POINTER(C.c_double)],
+        "wl_body_forces": [H, C.POINTER(C.c_float), C.POINTER(C.c_double)],
+        "wl_set_forcing": [H, fp, fp, fp, fp],
+        "wl_meanflow_init": [H, C.c_int],
+        "wl_meanflow_update": [H],
+        "wl_meanflow_reset": [H, C.c_float],
+        "wl_meanflow_copy_to_flow": [H],
+        "wl_meanflow_download": [H, C.c_int, C.c_void_p, C.c_int],
+        "wl_meanflow_upload": [H, C.c_int, C.c_void_p, C.c_int],
+        "wl_meanflow_get_times": [H, fp, C.POINTER(C.c_int)],
+        "wl_meanflow_set_times": [H, fp, C.c_int],
         "wl_stream": [H, C.POINTER(C.c_void_p)],
     }
     sig["wl_selftest_div6"] = [C.POINTER(C.c_uint64)]

@@ -18,7 +18,8 @@ class Simulation:
 
     def __init__(self, dims, uBC, L, U=None, Δt=0.25, ν=0.0, g=None, ϵ=1, perdir=(), u0=None, exitBC=False, λ=quick,
                  body=None, T=np.float32, flow_ctor=None, pois_ctor=None, host_measure=False, **kw):
-        if callable(uBC) and U is None:
+        from .flow import TimeBC
+        if (callable(uBC) or isinstance(uBC, TimeBC)) and U is None:
             raise AssertionError("`U` (velocity scale) must be specified if boundary conditions `uBC` is a `Function`")
         if U is None:
             U = float(np.sqrt(sum(float(v) ** 2 for v in uBC)))
