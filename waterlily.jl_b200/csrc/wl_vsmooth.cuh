@@ -103,24 +103,27 @@ __device__ __forceinline__ float vs_pair(float a, float b, float L) {
   return a * L + b * L;
 }
 
+// oS: offset of the x neighbour beyond the group inside the other array (−1: last cell of the group to the left, for TE; +4: first
+// cell of the group to the right); oYm / oYp: offsets of the rows below / above (∓ one row of groups).  The tile's edge threads
+// (first / last group of a row, first / last row) have no such neighbour inside the tile: they pass 0 and re-read an element of their
+// own — what they compute is halo garbage by design, but it must not come from an element another thread writes in the same
+// phase (compute-sanitizer racecheck is clean with this; out-of-tile reads raced with the neighbouring rows' stores before).
 template <bool TE, int LM>
 __device__ __forceinline__ void vs_sweep(float* sb, int eq, int eqm, int eqp, int rq, int rqm, int rqp, bool stS, float mS, bool anyYZ, bool stYm,
-                                         bool stYp, bool stZm, bool stZp, const VsArgs& a) {
+                                         bool stYp, bool stZm, bool stZp, const VsArgs& a, int oS, int oYm, int oYp) {
   constexpr int tg = TE ? 0 : VS_AF, ot = TE ? VS_AF : 0;
-  constexpr int oS = TE ? -1 : 4;  // last cell of the group to the left / first cell of the group to the right
-  constexpr int oY = VS_NGX * 4;
   const float iD = a.iD;
   const float4 V = ld4(sb + eq + ot);
   const float S = sb[(stS ? rq : eq) + ot + oS] * mS;
   float4 ym, yp, zm, zp;
   if (!anyYZ) {
-    ym = ld4(sb + eq + tg - oY);
-    yp = ld4(sb + eq + tg + oY);
+    ym = ld4(sb + eq + tg + oYm);
+    yp = ld4(sb + eq + tg + oYp);
     zm = ld4(sb + eqm + tg);
     zp = ld4(sb + eqp + tg);
   } else {
-    ym = stYm ? mul4s(ld4(sb + rq + tg - oY), iD) : ld4(sb + eq + tg - oY);
-    yp = stYp ? mul4s(ld4(sb + rq + tg + oY), iD) : ld4(sb + eq + tg + oY);
+    ym = stYm ? mul4s(ld4(sb + rq + tg + oYm), iD) : ld4(sb + eq + tg + oYm);
+    yp = stYp ? mul4s(ld4(sb + rq + tg + oYp), iD) : ld4(sb + eq + tg + oYp);
     zm = stZm ? mul4s(ld4(sb + rqm + tg), iD) : ld4(sb + eqm + tg);
     zp = stZp ? mul4s(ld4(sb + rqp + tg), iD) : ld4(sb + eqp + tg);
   }
@@ -206,6 +209,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
   const bool stY = stYm || stYp;
   const float mL = stL ? a.iD : 1.f, mR = stR ? a.iD : 1.f;
   constexpr int oY = VS_NGX * 4;
+  // neighbour offsets of the sweeps; 0 where the neighbour would lie outside the tile (see vs_sweep)
+  const int oSl = gx == 0 ? 0 : -1, oSr = gx == VS_NGX - 1 ? 0 : 4;
+  const int oYm = ry == 0 ? 0 : -oY, oYp = ry == VS_TH - 1 ? 0 : oY;
   const bool core = act && gx >= 1 && gx <= VS_NGX - 2 && ry >= VS_HALO && ry < VS_TH - VS_HALO && xu <= n0 && yu <= n1;
   // global offsets (in-plane)
   const int gin = g.xo + xs + g.px * yr;
@@ -313,9 +319,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         const bool te = ((1 + ypar + q) & 1) == 0;  // colour of the even-position array on this row and plane
         const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a, oSl, oYm, oYp);
         else
-          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a, oSr, oYm, oYp);
       }
     }
     __syncthreads();
@@ -331,9 +337,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
         const bool te = ((1 + ypar + q) & 1) == 1;
         const bool anyYZ = stY || zsm || zsp;
         if (te)
-          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<true, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stL, mL, anyYZ, stYm, stYp, zsm, zsp, a, oSl, oYm, oYp);
         else
-          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a);
+          vs_sweep<false, LM>(sb, le[k], le[k + 1], le[k - 1], lr[k], lr[k + 1], lr[k - 1], stR, mR, anyYZ, stYm, stYp, zsm, zsp, a, oSr, oYm, oYp);
       }
     }
     // ---- increment!: r² = r¹ − ω·A ϵ⁴ ; x² = (x + ω·ϵc) + ω·ϵ⁴ on plane t−7, core cells only ----
