@@ -816,33 +816,20 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
   if (fused_out) *fused_out = fused;
   return 0;
 }
-// pcg!(p;it=6)  src/Poisson.jl:166-186 — host-driven (three dots per iteration decide early exits)
+// pcg!(p;it=6)  src/Poisson.jl:166-186 — device-driven: all stages of the six iterations are enqueued, the early exits are taken
+// on the device (PcgCtl), the host never waits
 static int pcg(wl_handle* h, Level& l, int it = 6) {
   dim3 b = blk(h->D);
   Box in = l.inside();
   Lvl d = l.dev();
-  const float eps32 = 1.1920929e-7f;
-  double v;
-  LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 0, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
-  TRY(read_slot(h, SLOT_RHO, &v));
-  float rho = (float)v;
-  if (std::fabs(rho) < 10 * eps32) return 0;
+  PcgCtl* ctl = reinterpret_cast<PcgCtl*>(h->d_scal + 8);
+  LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 0, ctl, h->red, SLOT_RHO);
   for (int i = 1; i <= it; i++) {
-    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 1, (const float*)h->d_scal + 2, h->red, SLOT_SIG);
-    TRY(read_slot(h, SLOT_SIG, &v));
-    const float alpha = rho / (float)v;
-    if (std::fabs(alpha) < 1e-2 || std::fabs(alpha) > 1e2) return 0;
-    set_scalar(h, 2, alpha);
-    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 2, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
-    if (i == it) return 0;
-    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 3, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
-    TRY(read_slot(h, SLOT_RHO, &v));
-    const float rho2 = (float)v;
-    if (std::fabs(rho2) < 10 * eps32) return 0;
-    const float beta = rho2 / rho;
-    set_scalar(h, 3, beta);
-    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 4, (const float*)h->d_scal + 2, h->red, SLOT_RHO);
-    rho = rho2;
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 1, ctl, h->red, SLOT_SIG);
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 2, ctl, h->red, SLOT_RHO);
+    if (i == it) break;
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 3, ctl, h->red, SLOT_RHO);
+    LAUNCH_D(h, k_pcg, grd(in, b), b, d, in, 4, ctl, h->red, SLOT_RHO);
   }
   return 0;
 }

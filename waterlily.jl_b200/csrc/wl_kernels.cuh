@@ -689,10 +689,18 @@ __global__ void k_mult(Lvl l, Box box, const float* __restrict__ x, float* __res
 // stage 2: x += αϵ ; r −= αz                            (:176-177)   α = sc[0]
 // stage 3: z = r·iD ; ρ₂ = r⋅z                          (:179-180)
 // stage 4: ϵ = βϵ + z                                    (:183)       β = sc[1]
+// The iteration is driven ON THE DEVICE: the block that folds a dot product also forms ρ, α, β (Float32 divisions like the
+// reference's) and evaluates pcg!'s early exits — abs(ρ) < 10eps, abs(α) ∉ [1e-2, 1e2] — into `ctl->active`; every later stage
+// of the same pcg! call returns at once when it is 0.  The host enqueues all stages of the six iterations and never waits.
+struct PcgCtl {
+  float rho, alpha, beta;
+  int active;
+};
 template <int D>
-__global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, const float* __restrict__ sc, RedBuf R, int slot) {
+__global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, PcgCtl* __restrict__ ctl, RedBuf R, int slot) {
   const Grid& g = l.g;
   int I[3];
+  if (stage > 0 && ctl->active == 0) return;  // (written by an earlier launch only: the last block of a stage writes it after every block has started)
   const bool ok = thread_cell<D>(box, I);
   double v[1] = {0.0}, fin[1];
   if (ok) {
@@ -709,7 +717,7 @@ __global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, const fl
       l.z[o] = z;
       v[0] = (double)z * (double)l.eps[o];
     } else if (stage == 2) {
-      const float a = sc[0];
+      const float a = ctl->alpha;
       l.x[o] += a * l.eps[o];
       l.r[o] -= a * l.z[o];
     } else if (stage == 3) {
@@ -717,10 +725,31 @@ __global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, const fl
       l.z[o] = z;
       v[0] = (double)l.r[o] * (double)z;
     } else {
-      l.eps[o] = sc[1] * l.eps[o] + l.z[o];
+      l.eps[o] = ctl->beta * l.eps[o] + l.z[o];
     }
   }
-  if (stage == 0 || stage == 1 || stage == 3) grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+  if (stage == 0 || stage == 1 || stage == 3) {
+    const bool last = grid_reduce<RED_SUM, 1>(v, R, slot, fin);
+    if (last && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+      const float eps10 = 10.f * 1.1920929e-7f;
+      const float d = (float)fin[0];
+      if (stage == 0) {
+        ctl->rho = d;
+        ctl->active = fabsf(d) < eps10 ? 0 : 1;
+      } else if (stage == 1) {
+        const float alpha = ctl->rho / d;
+        ctl->alpha = alpha;
+        if ((double)fabsf(alpha) < 1e-2 || (double)fabsf(alpha) > 1e2) ctl->active = 0;  // alpha should be O(1) (Float64 literals in the reference)
+      } else {
+        if (fabsf(d) < eps10)
+          ctl->active = 0;
+        else {
+          ctl->beta = d / ctl->rho;
+          ctl->rho = d;
+        }
+      }
+    }
+  }
 }
 
 // L₂(p) = r⋅r and L∞(p) = maximum(abs,r) (src/Poisson.jl:189-190) as a standalone reduction.
