@@ -71,6 +71,7 @@ enum {
   WL_FLAG_NO_FUSED_UNI = 64, /* constant-coefficient mode: f_div_residual / f_jacobi / f_correct + f_cfl instead of their fused forms */
   WL_FLAG_NO_TINY = 256,     /* run the coarsest levels (≤ 8192 cells) inside the cooperative coarse-level kernel instead of the one-block kernel */
   WL_FLAG_NO_SEMI = 128,     /* general mode: always read the face coefficients L (no semi-uniform march blocks, no body-free BDIM blocks) */
+  WL_FLAG_NO_FAST_READ = 512, /* read the solver's residual norms with a copy + stream synchronisation instead of polling the mapped mirror the reduction writes */
 };
 
 const char* wl_last_error(void);
@@ -166,6 +167,13 @@ int wl_meanflow_set_times(wl_handle* h, const float* buf, int len);
  * ghosts included, like the reference's loop over CartesianIndices(r)) and applies BC! with U(t₁), t₁ = sum(Δt), t₀ = t₁ − Δt[end].
  * Any pointer may be NULL (= zeros); all zeros switches the forcing off. */
 int wl_set_forcing(wl_handle* h, const float* g0, const float* g1, const float* U1, const float* U2);
+
+/* The reference's LES udf as a built-in: sim_step!(sim; udf=sgs!, νₜ=smagorinsky, S, Cs, Δ) (src/util.jl:46-76) with
+ * the Smagorinsky–Lilly eddy viscosity of its docstring, νₜ(I) = (Cs·Δ)²·sqrt(S[I,:,:]⋅S[I,:,:]), S(I,u) the rate-of-strain tensor at the
+ * cell centre (src/Metrics.jl:42-44,140).  In both phases of every step, between conv_diff! and accelerate! (src/Flow.jl:192,207), the
+ * sub-grid fluxes −νₜ(I)·∂ⱼuᵢ are added to the right-hand side over inside_u(N,j), evaluated on the advecting field of the phase (u⁰ /
+ * u).  Cs·Δ = 0 switches it off.  Runs on the general kernels (the udf reads ghost cells of u); not available on z slabs. */
+int wl_set_sgs(wl_handle* h, float Cs, float Delta);
 
 /* update!(pois) (src/WaterLily.jl:148, src/MultiLevelPoisson.jl:79-86, src/Poisson.jl:47): call after uploading μ₀
  * (measure!): set_diag! on level 1 and restrictL! + set_diag! on every coarse level. */

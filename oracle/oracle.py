@@ -60,6 +60,10 @@ def lib():
         L.wlo_body_forces.restype = None
         L.wlo_set_forcing.argtypes = [C.c_void_p, fp, fp, fp, fp]
         L.wlo_set_forcing.restype = None
+        L.wlo_set_sgs.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.wlo_set_sgs.restype = None
+        L.wlo_sgs.argtypes = [C.c_void_p, C.c_int]
+        L.wlo_sgs.restype = None
         for name in ("wlo_dt_len", "wlo_iters_len", "wlo_log_len", "wlo_num_levels", "wlo_pois_solve"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_int
@@ -223,6 +227,14 @@ class OracleSim:
             return out
         self._forcing = [v(g0), v(g1), v(U1), v(U2)]
         self.L.wlo_set_forcing(self.h, *[_fp(a) for a in self._forcing])
+
+    def set_sgs(self, Cs, Delta):
+        """udf = sgs! with νₜ = smagorinsky (src/util.jl:46-76); Cs·Δ = 0 switches it off"""
+        self.L.wlo_set_sgs(self.h, float(Cs), float(Delta))
+
+    def sgs(self, from_u0=False):
+        """sgs!(flow,u,t) alone: flow.f += sub-grid fluxes of flow.u (or flow.u⁰)"""
+        self.L.wlo_sgs(self.h, int(from_u0))
 
     def time_next(self):
         """sum(Δt): the default t of measure!(sim) (src/WaterLily.jl:146)"""

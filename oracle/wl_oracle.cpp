@@ -607,6 +607,10 @@ struct Flow {
   bool forcing = false;
   T g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, U1[3] = {0, 0, 0}, U2[3] = {0, 0, 0};
   T ubc_t[3];  // uBC evaluated at the time the current BC! call is made at
+  // built-in udf: sgs! with the Smagorinsky–Lilly νₜ of its docstring (src/util.jl:57-76); S is the user's buffer (N…,D,D), zeros outside inside(σ)
+  bool sgs = false;
+  T sgs_c2 = 0;  // (Cs·Δ)²
+  std::vector<T> S;
   ~Flow() {
     delete ml;
     delete single;
@@ -690,6 +694,42 @@ static void accelerate(Flow& a, T t) {
     for (size_t o = 0; o < n; o++) fi[o] += acc;
   }
 }
+// ∂(i,j,I,u): ∂uᵢ/∂xⱼ at the centre of cell I  (src/Metrics.jl:42-44)
+static inline T dudx_c(const Grid& g, const T* u, int i, int j, const I3& I) {
+  const size_t n = g.n();
+  const T* ui = u + n * i;
+  if (i == j) return ui[g.at(shift(I, i, 1))] - ui[g.at(I)];
+  const I3 P = shift(I, j, 1), M = shift(I, j, -1);
+  return (ui[g.at(P)] + ui[g.at(shift(P, i, 1))] - ui[g.at(M)] - ui[g.at(shift(M, i, 1))]) / 4;
+}
+// sgs!(flow,u,t; νₜ,S,Cs,Δ)  src/util.jl:66-76, with νₜ = smagorinsky(I;S,Cs,Δ) = (Cs·Δ)²·sqrt(dot(S[I,:,:],S[I,:,:]))  (src/util.jl:62)
+// and S(I,u) = (∂(i,j,I,u)+∂(j,i,I,u))/2  (src/Metrics.jl:140).  `u` is the advecting field of the phase (u⁰ / u, src/Flow.jl:192,207).
+static void sgs(Flow& a, const T* u) {
+  const Grid& g = a.g;
+  const size_t n = g.n();
+  const int D = g.D;
+  loop(inside(g), [&](I3 I) {
+    const size_t o = g.at(I);
+    for (int j = 0; j < D; j++)
+      for (int i = 0; i < D; i++) a.S[o + n * ((size_t)i + (size_t)D * j)] = (dudx_c(g, u, i, j, I) + dudx_c(g, u, j, i, I)) / 2;
+  });
+  auto nut = [&](size_t o) -> T {  // generic `dot` of the two views: sequential, column-major
+    T s = 0;
+    for (int q = 0; q < D * D; q++) s += a.S[o + n * q] * a.S[o + n * q];
+    return a.sgs_c2 * std::sqrt(s);
+  };
+  for (int i = 0; i < D; i++)
+    for (int j = 0; j < D; j++) {
+      const T* ui = u + n * i;
+      T* fi = a.f.data() + n * i;
+      loop(inside_u(g, j), [&](I3 I) {
+        const size_t o = g.at(I);
+        a.sigma[o] = -nut(o) * (ui[o] - ui[g.at(shift(I, j, -1))]);
+        fi[o] += a.sigma[o];
+      });
+      loop(inside_u(g, j), [&](I3 I) { fi[g.at(shift(I, j, -1))] -= a.sigma[g.at(I)]; });
+    }
+}
 static void mom_step(Flow& a) {  // mom_step! :156-167
   const Grid& g = a.g;
   a.u0 = a.u;
@@ -704,6 +744,7 @@ static void mom_step(Flow& a) {  // mom_step! :156-167
   }
   // predictor  :190-196
   conv_diff(g, a.f.data(), a.u0.data(), a.sigma.data(), a.lam, a.nu, a.per);
+  if (a.sgs) sgs(a, a.u0.data());  // udf!(a,udf,a.u⁰,t₀)  src/Flow.jl:192
   accelerate(a, t0);
   BDIM(a);
   BC(g, a.u.data(), a.forcing ? a.ubc_t : a.uBC, a.exit, a.per);
@@ -711,6 +752,7 @@ static void mom_step(Flow& a) {  // mom_step! :156-167
   project(a, 1);
   // corrector  :205-210
   conv_diff(g, a.f.data(), a.u.data(), a.sigma.data(), a.lam, a.nu, a.per);
+  if (a.sgs) sgs(a, a.u.data());  // udf!(a,udf,a.u,t)  src/Flow.jl:207
   accelerate(a, t1);
   BDIM(a);
   scale_u(a, 0.5f);
@@ -1085,6 +1127,18 @@ void wlo_set_forcing(void* h, const float* g0, const float* g1, const float* U1,
   for (int i = 0; i < 3; i++) a->g0[i] = g0[i], a->g1[i] = g1[i], a->U1[i] = U1[i], a->U2[i] = U2[i];
 }
 // pressure_force / viscous_force / pressure_moment / viscous_moment at time t about x0 (out: 12 doubles, see body_forces)
+// udf = sgs! with νₜ = smagorinsky, Cs, Δ (src/util.jl:46-76); Cs·Δ = 0 switches it off
+void wlo_set_sgs(void* h, float Cs, float Delta) {
+  Flow* a = (Flow*)h;
+  const T c = Cs * Delta;
+  a->sgs = c != 0;
+  a->sgs_c2 = c * c;
+  a->S.assign(a->g.n() * a->g.D * a->g.D, 0);
+}
+void wlo_sgs(void* h, int from_u0) {  // sgs!(flow, u, t) alone: adds the sub-grid fluxes of u (or u⁰) to flow.f
+  Flow* a = (Flow*)h;
+  sgs(*a, from_u0 ? a->u0.data() : a->u.data());
+}
 void wlo_body_forces(void* h, const void* prims, int np, float t, const float* x0, double* out) { body_forces(*(Flow*)h, (const Prim*)prims, np, t, x0, out); }
 // pois_ctor(flow): MultiLevelPoisson(flow.p,flow.μ₀,flow.σ;perdir) (kind 0) or Poisson(...) (kind 1)
 int wlo_init_pois(void* h, int kind) {

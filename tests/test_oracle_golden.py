@@ -211,3 +211,70 @@ def test_kernel_moments(oracle_lib):  # :2-5
     assert L.wlo_mu0(0.0, 1.0) == 0.5
     assert L.wlo_mu0(float(np.float32(np.finfo(np.float32).eps) - np.float32(1)), 1.0) == 0.0
     assert abs(L.wlo_mu1(0.0, 2.0) - 2 * (1 / 4 - 1 / np.pi**2)) < 1e-7
+
+
+# ---------------------------------------------------------------- src/util.jl:46-76 (sgs! with the docstring's smagorinsky νₜ)
+def _sgs_numpy(f, u, sigma, Cs, Delta):
+    """An array-level transliteration of sgs! (src/util.jl:66-76), S(I,u) and ∂(i,j,I,u) (src/Metrics.jl:42-44,140), independent of
+    the C++ restatement.  f, u: reference index order (x,y,(z),c); ranges below are the reference's 1-based ranges."""
+    F = np.float32
+    D = u.shape[-1]
+    N = u.shape[:-1]
+
+    def sl(rng):
+        return tuple(slice(lo - 1, hi) for lo, hi in rng)
+
+    def shift(rng, d, k):
+        r = list(rng)
+        r[d] = (r[d][0] + k, r[d][1] + k)
+        return r
+
+    inside = [(2, n - 1) for n in N]
+
+    def dudx(i, j, rng):
+        ui = u[..., i]
+        if i == j:
+            return ui[sl(shift(rng, i, 1))] - ui[sl(rng)]
+        P, M = shift(rng, j, 1), shift(rng, j, -1)
+        return (ui[sl(P)] + ui[sl(shift(P, i, 1))] - ui[sl(M)] - ui[sl(shift(M, i, 1))]) / F(4)
+
+    S = np.zeros(N + (D, D), F)
+    for j in range(D):
+        for i in range(D):
+            S[sl(inside) + (i, j)] = (dudx(i, j, inside) + dudx(j, i, inside)) / F(2)
+    s = np.zeros(N, F)
+    for j in range(D):
+        for i in range(D):
+            s = s + S[..., i, j] * S[..., i, j]
+    c = F(Cs) * F(Delta)
+    nut = (c * c) * np.sqrt(s)
+    for i in range(D):
+        for j in range(D):
+            R = [(3, N[d] - 1) if d == j else (2, N[d]) for d in range(D)]
+            Rm = shift(R, j, -1)
+            sigma[sl(R)] = -nut[sl(R)] * (u[..., i][sl(R)] - u[..., i][sl(Rm)])
+            f[..., i][sl(R)] += sigma[sl(R)]
+            f[..., i][sl(Rm)] -= sigma[sl(R)]
+
+
+@pytest.mark.parametrize("dims", [(12, 10), (10, 8, 6)])
+def test_sgs_restatement_equals_array_transliteration(dims):
+    D = len(dims)
+    rng = np.random.default_rng(5)
+    s = OracleSim(dims, (1.0,) + (0.0,) * (D - 1), nu=0.01)
+    u, f, sg = s.field("u"), s.field("f"), s.field("sigma")
+    u[...] = rng.standard_normal(u.shape).astype(np.float32)
+    f[...] = rng.standard_normal(f.shape).astype(np.float32)
+    sg[...] = rng.standard_normal(sg.shape).astype(np.float32)
+    ax = tuple(range(D, 0, -1)) + (0,)  # C order (c,(z),y,x) → reference order (x,y,(z),c)
+    fr, ur, sr = np.transpose(f.copy(), ax), np.transpose(u.copy(), ax), np.transpose(sg.copy(), tuple(range(D - 1, -1, -1)))
+    _sgs_numpy(fr, ur, sr, 0.2, 1.5)
+    s.set_sgs(0.2, 1.5)
+    s.sgs()
+    assert np.array_equal(np.transpose(f, ax), fr)
+    assert np.array_equal(np.transpose(sg, tuple(range(D - 1, -1, -1))), sr)
+    # a uniform stream has no strain: the model adds exactly nothing
+    u[...] = 0.75
+    before = f.copy()
+    s.sgs()
+    assert np.array_equal(f, before)

@@ -7,7 +7,7 @@ package never touches oracle/.
 """
 from .lib import load_library, build_library, WLError, library_path  # noqa: F401
 from .body import AutoBody, NoBody, Sphere, Torus, measure_body, mu0_kernel, mu1_kernel  # noqa: F401
-from .flow import Flow, MultiLevelPoisson, Poisson, mom_step, quick, cds, vanLeer, loc_grid, dist_unique_id, Forcing, TimeBC  # noqa: F401
+from .flow import Flow, MultiLevelPoisson, Poisson, mom_step, quick, cds, vanLeer, loc_grid, dist_unique_id, Forcing, TimeBC, sgs, smagorinsky  # noqa: F401
 from .simulation import Simulation, sim_step, sim_time, measure, sim_info  # noqa: F401
 from .metrics import (pressure_force, viscous_force, total_force, pressure_moment, viscous_moment, total_moment, MeanFlow,  # noqa: F401
                       save, load)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -145,8 +146,13 @@ struct wl_handle {
   Grid g;
   float *u = nullptr, *u0 = nullptr, *f = nullptr, *p = nullptr, *sigma = nullptr, *V = nullptr, *mu0 = nullptr, *mu1 = nullptr;
   std::vector<Level> levels;
-  RedBuf red{nullptr, nullptr, nullptr};
+  RedBuf red{nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
   double* h_out = nullptr;  // pinned mirror of red.out
+  // mapped pinned mirror the folding thread of a reduction writes itself (RedBuf::hout/hseq): slot_tag[s] = tag of the last launch
+  // that reduces into slot s (0 = none pending), see red_for / read_slot
+  unsigned int tag_ctr = 0;
+  unsigned int slot_tag[NSLOTS] = {0};
+  bool fast_read = true;
   float* d_dthist = nullptr;
   size_t dt_cap = 0;
   float* d_scal = nullptr;  // [0]=omega, [1]=one, [2]=alpha, [3]=beta, [4]=scratch dt
@@ -189,6 +195,10 @@ struct wl_handle {
   float fg0[3] = {0, 0, 0}, fg1[3] = {0, 0, 0}, fU1[3] = {0, 0, 0}, fU2[3] = {0, 0, 0};
   Force fc{0, {0.f, 0.f, 0.f}};  // what the flux kernels of the current stage add to r
   float ubc_now[3] = {0, 0, 0};  // uBC at the time the step's BC! calls are made at (t₁)
+  // built-in udf: sgs! with νₜ = smagorinsky (src/util.jl:46-76): (Cs·Δ)², the νₜ scratch field (ghost cells stay 0)
+  bool sgs_on = false;
+  float sgs_c2 = 0.f;
+  float* nut = nullptr;
   bool range_checked = false;  // the current u was range-checked by the kernel that wrote it (range_note, wl_common.cuh)
   SmallOp* d_ops = nullptr;
   SmallOp* h_ops = nullptr;  // pinned
@@ -477,6 +487,17 @@ static int exch_u(wl_handle* h, float* u, float* p = nullptr) {
   prof_end(h);
   return 0;
 }
+// Uniform mode, between the flux kernel and the projection's velocity correction: the only ghost values of the intermediate velocity
+// anyone reads are u_z one plane above the slab (div in f_divres_uni, flux_out in f_correct_cfl) — the corrected field is exchanged in
+// full (two planes per side, three components, and p) after the correction.  One plane, one direction, instead of twelve.
+static int exch_uz_up(wl_handle* h, float* u) {
+  if (!h->dist.on()) return 0;
+  if (!h->p2p) return exch_u(h, u);
+  const Grid& g = h->g;
+  float* b = u + (size_t)2 * g.sc;
+  PlaneMove mv[1] = {{b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)}};  // my bottom interior plane → the lower neighbour's upper ghost plane
+  return p2p_push(h, g, mv, 1);
+}
 // In-place all-reduce of one reduction slot (double) across the ranks, on the compute stream.
 static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `count` adjacent slots in one call
   if (!h->dist.on()) return 0;
@@ -705,7 +726,8 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
   // uniform-coefficient specialisation: legal iff no body (μ₀≡1, μ₁≡0, V≡0) and every direction periodic
   h->uni = false;
   const Grid& g = h->g;
-  if (h->D == 3 && g.per[0] && g.per[1] && (g.per[2] || h->perz_global) && !(h->cfg.flags & WL_FLAG_GENERAL_COEFF)) {
+  // (the sub-grid udf reads the ghost cells of u and adds to the raw flux sum: general kernels)
+  if (h->D == 3 && g.per[0] && g.per[1] && (g.per[2] || h->perz_global) && !(h->cfg.flags & WL_FLAG_GENERAL_COEFF) && !h->sgs_on) {
     LAUNCH(h, k_check_uniform, dim3(592, 1, 1), dim3(256, 1, 1), (const float*)h->mu0, (const float*)h->mu1, (const float*)h->V, g, h->red, SLOT_UNI);
     TRY(allreduce_slot(h, SLOT_UNI, WL_NCCL_MAX));
     CK(cudaMemcpyAsync(h->h_out + SLOT_UNI, h->red.out + SLOT_UNI, sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -721,10 +743,41 @@ static inline int ensure_hierarchy(wl_handle* h) { return h->pois_dirty ? update
 static void set_scalar(wl_handle* h, int idx, float v) {
   LAUNCH(h, k_set_scalar, 1, 1, h->d_scal + idx, v);
 }
-static int read_slot(wl_handle* h, int slot, double* out) {
-  CK(cudaMemcpyAsync(h->h_out + slot, h->red.out + slot, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+// The reduction buffer for a launch that reduces into `slot` and whose result the host will read: tagged, so that the folding
+// thread publishes the result to the mapped mirror (`active` = the launch really reduces).
+static RedBuf red_for(wl_handle* h, int slot, bool active = true) {
+  RedBuf r = h->red;
+  if (active && r.hseq) {
+    if (++h->tag_ctr == 0) h->tag_ctr = 1;
+    r.tag = h->tag_ctr;
+    h->slot_tag[slot] = r.tag;
+  }
+  return r;
+}
+// Result slot(s) → host.  One GPU: the host polls the word the folding thread writes after the values (≈ 1 µs after the kernel's last
+// block instead of a copy + stream synchronisation); the stream query covers a launch that did not reduce after all.
+// z slabs: the slot was all-reduced on the stream after the kernel — copy and synchronise.
+static int read_slot(wl_handle* h, int slot, double* out, int n = 1) {
+  const unsigned int want = h->slot_tag[slot];
+  h->slot_tag[slot] = 0;
+  if (h->fast_read && want && !h->dist.on()) {
+    volatile unsigned int* sq = h->red.hseq + slot;
+    bool ok = true;
+    for (unsigned int spins = 1; *sq != want; spins++) {
+      if ((spins & 1023u) == 0 && cudaStreamQuery(h->st) != cudaErrorNotReady) {
+        ok = (*sq == want);
+        break;
+      }
+    }
+    if (ok) {
+      std::atomic_thread_fence(std::memory_order_acquire);
+      for (int i = 0; i < n; i++) out[i] = reinterpret_cast<volatile double*>(h->red.hout)[slot + i];
+      return 0;
+    }
+  }
+  CK(cudaMemcpyAsync(h->h_out + slot, h->red.out + slot, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  *out = h->h_out[slot];
+  for (int i = 0; i < n; i++) out[i] = h->h_out[slot + i];
   return 0;
 }
 
@@ -746,8 +799,8 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
         LAUNCH(h, f_gs_half<true>, l.fgrid(), fb, l.g, l.coef(true), (const float*)l.r, l.eps, k0, l.zchunk());
         if (exch(h, l, l.eps, 1)) return 1;
       }
-      LAUNCH(h, (f_increment<true, false>), l.fgrid(), fb, l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2, h->red,
-             SLOT_R2);
+      LAUNCH(h, (f_increment<true, false>), l.fgrid(), fb, l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
+             red_for(h, SLOT_R2, with_l2), SLOT_R2);
     } else {
       LAUNCH(h, f_gs_a<false>, l.fgrid(), fb, l.g, l.coef(false), (const float*)l.r, l.eps, l.zchunk());
       if (exch(h, l, l.eps, 1)) return 1;
@@ -756,7 +809,7 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
         if (exch(h, l, l.eps, 1)) return 1;
       }
       LAUNCH(h, (f_increment<false, false>), l.fgrid(), fb, l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
-             h->red, SLOT_R2);
+             red_for(h, SLOT_R2, with_l2), SLOT_R2);
     }
     if (exch2(h, l, l.r, l.x)) return 1;
     if (with_l2 && allreduce_slot(h, SLOT_R2, WL_NCCL_SUM)) return 1;
@@ -772,12 +825,12 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
     ProlongSrc ps{nullptr, l.g, 0, 0, 0};
     if (h->uni)
       LAUNCH(h, (f_increment<true, false>), l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(), with_l2,
-             h->red, SLOT_R2);
+             red_for(h, SLOT_R2, with_l2), SLOT_R2);
     else
       LAUNCH(h, (f_increment<false, false>), l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)l.eps, ps, l.r, l.x, wp, x_is_zero, l.zchunk(),
-             with_l2, h->red, SLOT_R2);
+             with_l2, red_for(h, SLOT_R2, with_l2), SLOT_R2);
   } else
-    LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, h->red, SLOT_R2);
+    LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, red_for(h, SLOT_R2, with_l2), SLOT_R2);
   return 0;
 }
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
@@ -836,7 +889,7 @@ static int pcg(wl_handle* h, Level& l, int it = 6) {
 static int l2_norm(wl_handle* h, Level& l, float* out, int want_max = 0) {
   dim3 b = blk(h->D);
   Box in = l.inside();
-  LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, h->red, want_max ? SLOT_LINF : SLOT_R2, want_max);
+  LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, red_for(h, want_max ? SLOT_LINF : SLOT_R2), want_max ? SLOT_LINF : SLOT_R2, want_max);
   TRY(allreduce_slot(h, want_max ? SLOT_LINF : SLOT_R2, want_max ? WL_NCCL_MAX : WL_NCCL_SUM));
   double v;
   TRY(read_slot(h, want_max ? SLOT_LINF : SLOT_R2, &v));
@@ -852,7 +905,7 @@ static int smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int wi
   if (with_l2) {
     dim3 b = blk(h->D);
     Box in = l.inside();
-    LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, h->red, SLOT_R2, 0);
+    LAUNCH_D(h, k_norms, grd(in, b), b, l.dev(), in, red_for(h, SLOT_R2), SLOT_R2, 0);
   }
   return 0;
 }
@@ -891,13 +944,16 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
     h->attr_vs = true;
   }
   const int n0 = f.g.N[0] - 2, n1 = f.g.N[1] - 2, n2 = f.g.N[2] - 2;
-  const int tiles = cdiv(n0, VS_CX) * cdiv(n1, VS_CY);
+  // tile height: the level's rows split evenly over the smallest number of tiles (128 rows: 4 × 32 instead of 3 × 42 + 2 — the rows
+  // beyond n1 would be marched for nothing)
+  const int cy = cdiv(n1, cdiv(n1, VS_CY));
+  const int tiles = cdiv(n0, VS_CX) * cdiv(n1, cy);
   // z chunks: every chunk pays 12 planes of pipeline fill; pick the count that minimises waves × (planes per chunk + 12)
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
   int best = 1;
   long bestcost = -1;
-  for (int nz = 1; nz <= std::max(1, n2 / 16); nz++) {
+  for (int nz = 1; nz <= std::max(1, n2 / 8); nz++) {
     const long cost = (long)cdiv(tiles * nz, nsm * VS_BPS) * (cdiv(n2, nz) + 12);
     if (bestcost < 0 || cost < bestcost) {
       bestcost = cost;
@@ -921,6 +977,8 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   a.D = k.Dc;
   a.iD = k.iDc;
   a.zchunk = zc;
+  a.cy = cy;
+  a.th = cy + 2 * VS_HALO;
   a.slab = f.slab ? 1 : 0;
   a.cslab = c.slab ? 1 : 0;
   a.zoff = f.slab ? f.g.zoff : 0;
@@ -951,9 +1009,9 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
       TRY(p2p_push(h, c.g, mv, m));
     }
   }
-  dim3 gr(cdiv(n0, VS_CX), cdiv(n1, VS_CY), cdiv(n2, zc));
+  dim3 gr(cdiv(n0, VS_CX), cdiv(n1, cy), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
-  vs_tab[with_l2 ? 1 : 0][f.slab ? 1 : 0][lm]<<<gr, VS_NT, VS_SMEM, h->st>>>(a, h->red, SLOT_R2);
+  vs_tab[with_l2 ? 1 : 0][f.slab ? 1 : 0][lm]<<<gr, VS_NT, VS_SMEM, h->st>>>(a, red_for(h, SLOT_R2, with_l2), SLOT_R2);
   prof_end(h);
   h->launches++;
   std::swap(f.r, f.r2);
@@ -1197,32 +1255,32 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
   if (h->dist.on() && !(l.fast && with_div)) return fail("standalone residual! is not available with z-slab decomposition");
   if (l.fast && with_div) {
     if (h->uni && h->divres_uni)
-      LAUNCH(h, f_divres_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, dtp(h), w, l.zchunk(), h->red,
-             SLOT_RSUM);
+      LAUNCH(h, f_divres_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, dtp(h), w, l.zchunk(),
+             red_for(h, SLOT_RSUM), SLOT_RSUM);
     else if (h->uni)
       LAUNCH(h, f_div_residual<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
-             l.zchunk(), h->red, SLOT_RSUM);
+             l.zchunk(), red_for(h, SLOT_RSUM), SLOT_RSUM);
     else
       LAUNCH(h, f_div_residual<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(false), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
-             l.zchunk(), h->red, SLOT_RSUM);
+             l.zchunk(), red_for(h, SLOT_RSUM), SLOT_RSUM);
     TRY(allreduce_slot(h, SLOT_RSUM, WL_NCCL_SUM, 2));  // Σr and Σr² (adjacent slots)
     // residual! subtracts the mean only when |s| > 2eps (src/Poisson.jl:96); otherwise r is final and the Σr² of the same pass is L₂
     static_assert(SLOT_R2 == SLOT_RSUM + 1, "f_div_residual reduces Σr and Σr² into adjacent slots");
-    CK(cudaMemcpyAsync(h->h_out + SLOT_RSUM, h->red.out + SLOT_RSUM, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    const float s = (float)h->h_out[SLOT_RSUM] / count;
+    double sums[2];
+    TRY(read_slot(h, SLOT_RSUM, sums, 2));
+    const float s = (float)sums[0] / count;
     if (std::fabs(s) > 2.f * 1.1920929e-7f) {
-      LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), h->red, SLOT_RSUM, SLOT_R2);
+      LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), red_for(h, SLOT_R2), SLOT_RSUM, SLOT_R2);
       TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
       TRY(exch(h, l, l.r, 1));
     } else {
       TRY(exch(h, l, l.r, 1));
-      *r2 = (float)h->h_out[SLOT_R2];
+      *r2 = (float)sums[1];
       return 0;
     }
   } else {
     LAUNCH_D(h, k_div_residual, grd(in, b), b, l.dev(), in, (const float*)h->u, (const float*)h->p, dtp(h), w, with_div, h->red, SLOT_RSUM);
-    LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, h->red, SLOT_RSUM, SLOT_R2);
+    LAUNCH_D(h, k_resid_fix, grd(in, b), b, l.dev(), in, count, red_for(h, SLOT_R2), SLOT_RSUM, SLOT_R2);
   }
   double v;
   TRY(read_slot(h, SLOT_R2, &v));
@@ -1370,7 +1428,14 @@ static int momentum(wl_handle* h, int corrector) {
     }
     return 0;
   }
-  if (h->D == 3) {
+  if (h->sgs_on) {
+    // conv_diff! → udf! = sgs! → accelerate! → BDIM-1 (src/Flow.jl:191-193,206-208): the raw flux sum, νₜ, then the gather kernel
+    const float* ua = corrector ? h->u : h->u0;
+    Box all = l.all();
+    conv_bdim1(h, ua, 0);
+    LAUNCH_D(h, k_sgs_nut, grd(in, b), b, g, in, ua, h->nut, h->sgs_c2);
+    LAUNCH_D(h, k_sgs_apply, grd(all, b), b, g, all, ua, (const float*)h->nut, (const float*)h->u0, (const float*)h->V, h->f, h->sigma, dtp(h), h->fc);
+  } else if (h->D == 3) {
     TRY(fconv<false>(h, corrector ? h->u : h->u0, h->f, corrector));
     dim3 pb(32, 8, 1);
     int m0 = std::max(g.N[0], g.N[1]), m1 = std::max(g.N[1], g.N[2]);
@@ -1524,13 +1589,13 @@ static int mom_step(wl_handle* h) {
   TRY(momentum(h, 0));
   step_bc(h, h->u0);
   if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
-  TRY(exch_u(h, h->u));
+  TRY(lazy_bc(h) ? exch_uz_up(h, h->u) : exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
   stage_force(t1);
   TRY(momentum(h, 1));
   step_bc(h, h->u);
-  TRY(exch_u(h, h->u));
+  TRY(lazy_bc(h) ? exch_uz_up(h, h->u) : exch_u(h, h->u));
   bool cfl_done = false;
   TRY(project(h, 0.5f, h->d_dthist + h->dt_dev_len, &cfl_done));
   // push!(a.Δt, CFL(a))
@@ -1831,6 +1896,15 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
     h->red.out = (double*)q;
     h->allocs.push_back(q);
     if (cudaMallocHost((void**)&h->h_out, NSLOTS * sizeof(double)) != cudaSuccess) { rc = fail("cudaMallocHost"); break; }
+    {  // mapped mirror: NSLOTS doubles, then NSLOTS sequence words (unified addressing: the host pointer is valid on the device)
+      void* m = nullptr;
+      if (cudaHostAlloc(&m, NSLOTS * (sizeof(double) + sizeof(unsigned int)), cudaHostAllocMapped) != cudaSuccess) { rc = fail("cudaHostAlloc (mapped)"); break; }
+      memset(m, 0, NSLOTS * (sizeof(double) + sizeof(unsigned int)));
+      h->red.hout = (double*)m;
+      h->red.hseq = (unsigned int*)((char*)m + NSLOTS * sizeof(double));
+      h->red.tag = 0;
+      h->fast_read = !(cfg->flags & WL_FLAG_NO_FAST_READ);
+    }
     if ((rc = dalloc(h, &h->d_scal, 16))) break;
     if ((rc = ensure_dt_capacity(h, 1024))) break;
     if (h->dist.on() && !(cfg->flags & WL_FLAG_NCCL_HALO)) {
@@ -1882,6 +1956,7 @@ int wl_destroy(wl_handle* h) {
   if (h->force_red.out) cudaFree(h->force_red.out);
   if (h->d_dthist) cudaFree(h->d_dthist);
   if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->red.hout) cudaFreeHost(h->red.hout);
   if (h->h_ops) cudaFreeHost(h->h_ops);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
@@ -2143,6 +2218,21 @@ int wl_set_forcing(wl_handle* h, const float* g0, const float* g1, const float* 
     }
   h->forcing = any;
   for (int i = 0; i < 3; i++) h->ubc_now[i] = h->cfg.uBC[i];
+  return 0;
+}
+
+int wl_set_sgs(wl_handle* h, float Cs, float Delta) {
+  if (!h) return fail("null handle");
+  const float c = Cs * Delta;
+  const bool on = c != 0.f;
+  if (on && h->dist.on()) return fail("the built-in sgs! udf is not available with z-slab decomposition");
+  if (on && !h->nut) TRY(dalloc(h, &h->nut, (size_t)h->g.sc));
+  if (on != h->sgs_on) {
+    flush_ghosts(h);       // (uniform mode defers BC!(u); the general kernels read the ghost cells)
+    h->pois_dirty = true;  // the uniform-coefficient kernels are re-decided at the next step (update_levels)
+  }
+  h->sgs_on = on;
+  h->sgs_c2 = c * c;
   return 0;
 }
 

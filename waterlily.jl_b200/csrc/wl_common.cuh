@@ -159,6 +159,12 @@ struct RedBuf {
   double* partials;      // capacity >= NV * (number of blocks + gridDim.z)
   unsigned int* ticket;  // [0] = top ticket, [1+z] = per-layer tickets; all zero between launches
   double* out;           // result slots
+  // host-visible mirror (mapped pinned memory; null = none): when `tag` is non-zero the folding thread also stores the results to
+  // hout[slot…] and then, after a system-wide fence, `tag` to hseq[slot0] — the host polls that word instead of paying a copy and a
+  // stream synchronisation for eight bytes (read_slot, wl_b200.cu)
+  double* hout;
+  unsigned int* hseq;
+  unsigned int tag;
 };
 
 enum { RED_SUM = 0, RED_MAX = 1 };
@@ -262,9 +268,16 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], const RedBuf& R, in
       if (lane == 0) {
         R.out[slot0 + q] = w;
         fin[q] = w;
+        if (R.tag) R.hout[slot0 + q] = w;
       }
     }
-    if (lane == 0) *R.ticket = 0u;
+    if (lane == 0) {
+      *R.ticket = 0u;
+      if (R.tag) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(R.hseq + slot0) = R.tag;
+      }
+    }
   }
   return true;
 }

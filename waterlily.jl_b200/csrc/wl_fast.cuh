@@ -1576,28 +1576,28 @@ __device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero
   __syncthreads();
 }
 
+// One copy of each stage's code, looped over the levels (the fully unrolled version was 11 000 instructions = 180 KB that ran once,
+// straight through: the kernel spent its time fetching instructions — `no_instruction` was its top stall, 44 µs per launch).
 __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ TinyArgs a) {
   extern __shared__ float tiny_sm[];
+  __shared__ TinyLvl lv[TINY_MAXLEV];
   const int tid = threadIdx.x;
-  TinyLvl lv[TINY_MAXLEV];
-  {
+  if (tid == 0) {
     float* p = tiny_sm;
-#pragma unroll
-    for (int q = 0; q < TINY_MAXLEV; q++) {
-      if (q < a.nlev) {
-        TinyLvl& l = lv[q];
-        l.n0 = a.n[q][0], l.n1 = a.n[q][1], l.n2 = a.n[q][2];
-        l.cells = l.n0 * l.n1 * l.n2;
-        l.m0 = tiny_magic(l.n0), l.m1 = tiny_magic(l.n1), l.mh = tiny_magic(l.n0 >> 1);
-        l.L0 = a.L[q][0], l.L1 = a.L[q][1], l.L2 = a.L[q][2], l.D = a.D[q], l.iD = a.iD[q];
-        l.X = p, l.R = p + l.cells, l.E = p + 2 * l.cells;
-        p += 3 * l.cells;
-      }
+    for (int q = 0; q < a.nlev; q++) {
+      TinyLvl& l = lv[q];
+      l.n0 = a.n[q][0], l.n1 = a.n[q][1], l.n2 = a.n[q][2];
+      l.cells = l.n0 * l.n1 * l.n2;
+      l.m0 = tiny_magic(l.n0), l.m1 = tiny_magic(l.n1), l.mh = tiny_magic(l.n0 >> 1);
+      l.L0 = a.L[q][0], l.L1 = a.L[q][1], l.L2 = a.L[q][2], l.D = a.D[q], l.iD = a.iD[q];
+      l.X = p, l.R = p + l.cells, l.E = p + 2 * l.cells;
+      p += 3 * l.cells;
     }
   }
+  __syncthreads();
   const float w = *a.wp;
   {  // r of level T from global memory
-    const TinyLvl& l = lv[0];
+    const TinyLvl l = lv[0];
     for (int c = tid; c < l.cells; c += 1024) {
       int i, j, k;
       l.ijk(c, i, j, k);
@@ -1606,51 +1606,50 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
   }
   __syncthreads();
   // ---- down-stroke: Jacobi! (x = ϵ: the level starts from x = 0) and restrict! ----
-#pragma unroll
-  for (int q = 0; q < TINY_MAXLEV - 1; q++) {
-    if (q < a.nlev - 1) {
-      TinyLvl& l = lv[q];
-      const int s1 = l.n0, s2 = l.n0 * l.n1;
-      for (int c = tid; c < l.cells; c += 1024) {
-        int i, j, k;
-        l.ijk(c, i, j, k);
-        const float e = l.R[c] * l.iD;
-        float s = e * l.D;
-        s += (l.R[c - i + tiny_wrap(i - 1, l.n0)] * l.iD) * l.L0 + (l.R[c - i + tiny_wrap(i + 1, l.n0)] * l.iD) * l.L0;
-        s += (l.R[c + s1 * (tiny_wrap(j - 1, l.n1) - j)] * l.iD) * l.L1 + (l.R[c + s1 * (tiny_wrap(j + 1, l.n1) - j)] * l.iD) * l.L1;
-        s += (l.R[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.iD) * l.L2 + (l.R[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.iD) * l.L2;
-        l.E[c] = l.R[c] - 1.f * s;
-        l.X[c] = e;
-      }
-      __syncthreads();
-      {  // the new residual is in E: swap the roles (Jacobi! writes r out of place)
-        float* t = l.R;
-        l.R = l.E;
-        l.E = t;
-      }
-      const TinyLvl& cl = lv[q + 1];
-      for (int c = tid; c < cl.cells; c += 1024) {
-        int i, j, k;
-        cl.ijk(c, i, j, k);
-        float s = 0.f;
-        for (int kk = 2 * k; kk <= 2 * k + 1; kk++)
-          for (int jj = 2 * j; jj <= 2 * j + 1; jj++)
-            for (int ii = 2 * i; ii <= 2 * i + 1; ii++) s += l.R[ii + s1 * jj + s2 * kk];
-        cl.R[c] = s;
-      }
-      __syncthreads();
+#pragma unroll 1
+  for (int q = 0; q < a.nlev - 1; q++) {
+    TinyLvl l = lv[q];
+    const int s1 = l.n0, s2 = l.n0 * l.n1;
+    for (int c = tid; c < l.cells; c += 1024) {
+      int i, j, k;
+      l.ijk(c, i, j, k);
+      const float e = l.R[c] * l.iD;
+      float s = e * l.D;
+      s += (l.R[c - i + tiny_wrap(i - 1, l.n0)] * l.iD) * l.L0 + (l.R[c - i + tiny_wrap(i + 1, l.n0)] * l.iD) * l.L0;
+      s += (l.R[c + s1 * (tiny_wrap(j - 1, l.n1) - j)] * l.iD) * l.L1 + (l.R[c + s1 * (tiny_wrap(j + 1, l.n1) - j)] * l.iD) * l.L1;
+      s += (l.R[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.iD) * l.L2 + (l.R[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.iD) * l.L2;
+      l.E[c] = l.R[c] - 1.f * s;
+      l.X[c] = e;
     }
+    __syncthreads();
+    {  // the new residual is in E: swap the roles (Jacobi! writes r out of place), also in the table the up-stroke reads
+      float* t = l.R;
+      l.R = l.E;
+      l.E = t;
+      if (tid == 0) {
+        lv[q].R = l.R;
+        lv[q].E = l.E;
+      }
+    }
+    const TinyLvl cl = lv[q + 1];
+    for (int c = tid; c < cl.cells; c += 1024) {
+      int i, j, k;
+      cl.ijk(c, i, j, k);
+      float s = 0.f;
+      for (int kk = 2 * k; kk <= 2 * k + 1; kk++)
+        for (int jj = 2 * j; jj <= 2 * j + 1; jj++)
+          for (int ii = 2 * i; ii <= 2 * i + 1; ii++) s += l.R[ii + s1 * jj + s2 * kk];
+      cl.R[c] = s;
+    }
+    __syncthreads();
   }
-  // ---- coarsest level: smooth! from x = 0 ----
-#pragma unroll
-  for (int q = 0; q < TINY_MAXLEV; q++)
-    if (q == a.nlev - 1) tiny_gs(lv[q], w, 1, tid);
-  // ---- up-stroke: prolongate! + increment!, smooth! ----
-#pragma unroll
-  for (int q = TINY_MAXLEV - 2; q >= 0; q--) {
-    if (q < a.nlev - 1) {
-      const TinyLvl& l = lv[q];
-      const TinyLvl& cl = lv[q + 1];
+  // ---- coarsest level: smooth! from x = 0; then the up-stroke: prolongate! + increment!, smooth! ----
+#pragma unroll 1
+  for (int q = a.nlev - 1; q >= 0; q--) {
+    const TinyLvl l = lv[q];
+    const bool coarsest = q == a.nlev - 1;
+    if (!coarsest) {
+      const TinyLvl cl = lv[q + 1];
       const int s2 = l.n0 * l.n1, c1 = cl.n0, c2 = cl.n0 * cl.n1;
       for (int c = tid; c < l.cells; c += 1024) {
         int i, j, k;
@@ -1668,11 +1667,11 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
         l.X[c] = l.X[c] + w * e;
       }
       __syncthreads();
-      tiny_gs(l, w, 0, tid);
     }
+    tiny_gs(l, w, coarsest ? 1 : 0, tid);
   }
   {  // x (and r) of level T back to global memory
-    const TinyLvl& l = lv[0];
+    const TinyLvl l = lv[0];
     for (int c = tid; c < l.cells; c += 1024) {
       int i, j, k;
       l.ijk(c, i, j, k);

@@ -170,6 +170,83 @@ __global__ void __launch_bounds__(512) k_bdim2(Grid g, Box box, float* __restric
   }
 }
 
+// ---- built-in udf: sgs! with the Smagorinsky–Lilly eddy viscosity (src/util.jl:46-76) --------------------------------------
+// ∂uᵢ/∂xⱼ at the centre of cell I (src/Metrics.jl:42-44); o = offset of I.
+__device__ __forceinline__ float sgs_dudx(const Grid& g, const float* __restrict__ u, i64 o, int i, int j) {
+  const float* ui = u + (i64)i * g.sc;
+  if (i == j) return ui[o + g.s[i]] - ui[o];
+  const i64 p = o + g.s[j], m = o - g.s[j];
+  return (ui[p] + ui[p + g.s[i]] - ui[m] - ui[m + g.s[i]]) / 4.f;
+}
+// νₜ[I] = (Cs·Δ)²·sqrt(dot(S[I,:,:],S[I,:,:])) with S(I,u) = (∂ᵢuⱼ+∂ⱼuᵢ)/2 (src/util.jl:62,68; src/Metrics.jl:140) over inside(σ).
+// The reference keeps the tensor in the user's buffer S and evaluates νₜ from it at every use; the value is the same, so only νₜ is
+// stored.  Ghost cells of νₜ stay 0: the reference's S is written on inside(σ) only and the flux loops below read it on upper ghosts.
+template <int D>
+__global__ void __launch_bounds__(512) k_sgs_nut(Grid g, Box box, const float* __restrict__ u, float* __restrict__ nut, float c2) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < D; j++)
+#pragma unroll
+    for (int i = 0; i < D; i++) {  // column-major, like the generic dot of the two views
+      const float Sij = (sgs_dudx(g, u, o, i, j) + sgs_dudx(g, u, o, j, i)) / 2.f;
+      s += Sij * Sij;
+    }
+  nut[o] = c2 * sqrtf(s);
+}
+// The flux loops of sgs! in gather form, then accelerate! and BDIM-1 (src/util.jl:69-75; src/Flow.jl:64-73,178): for every cell K and
+// component i, in the reference's order  j = 1…D:  r += σᵢⱼ(K) if K ∈ inside_u(N,j);  r −= σᵢⱼ(K+δⱼ) if K+δⱼ ∈ inside_u(N,j),
+// σᵢⱼ(I) = −νₜ(I)·(u[I,i] − u[I−δⱼ,i]);  f = u⁰ + Δt·r − V over ALL cells (r: conv_diff!'s raw sum, k_conv_bdim1 mode 0).
+// flow.σ keeps the last value the (i=D, j) loops wrote on each upper-ghost cell (it enters maximum(σ) in CFL, App. A.9-1).
+template <int D>
+__global__ void __launch_bounds__(512) k_sgs_apply(Grid g, Box box, const float* __restrict__ ua, const float* __restrict__ nut,
+                                                   const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f,
+                                                   float* __restrict__ sigma, const float* __restrict__ dtp, const Force fc) {
+  int I[3];
+  if (!thread_cell<D>(box, I)) return;
+  const i64 o = cell_off(g, I);
+  const float dt = *dtp;
+  auto in_u = [&](const int* J, int j) -> bool {  // inside_u(N,j), 0-based: 2 … N_j−2 in j, 1 … N_k−1 elsewhere
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < D; d++) ok = ok && (d == j ? (J[d] >= 2 && J[d] <= g.N[d] - 2) : (J[d] >= 1 && J[d] <= g.N[d] - 1));
+    return ok;
+  };
+  float last = 0.f;
+  bool have = false;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    const float* ui = ua + (i64)i * g.sc;
+    const i64 oc = o + (i64)i * g.sc;
+    float r = f[oc];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      if (in_u(I, j)) {
+        const float s = -nut[o] * (ui[o] - ui[o - g.s[j]]);
+        r += s;
+        if (i == D - 1) {
+          last = s;
+          have = true;
+        }
+      }
+      int J[3] = {I[0], I[1], I[2]};
+      J[j]++;
+      if (in_u(J, j)) {
+        const i64 oj = o + g.s[j];
+        r -= -nut[oj] * (ui[oj] - ui[o]);
+      }
+    }
+    if (fc.on) r += fc.a[i];  // accelerate!
+    f[oc] = u0[oc] + dt * r - V[oc];
+  }
+  bool ghost = false;
+#pragma unroll
+  for (int d = 0; d < D; d++) ghost = ghost || (I[d] == g.N[d] - 1);
+  if (ghost && have) sigma[o] = last;
+}
+
 // Flags for k_bdim2's body-free fast path, same launch geometry as k_bdim2.
 template <int D>
 __global__ void __launch_bounds__(512) k_nobody_flags(Grid g, Box box, const float* __restrict__ V, const float* __restrict__ mu0,

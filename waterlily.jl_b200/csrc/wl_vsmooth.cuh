@@ -57,6 +57,7 @@ struct VsArgs {
   const float* wp;   // ω
   float L0, L1, L2, D, iD;
   int zchunk;
+  int cy, th;  // core rows of a tile (≤ VS_CY: the level's rows split evenly over the tiles) and tile rows cy + 2·VS_HALO
   // z slab (multi-GPU): the level holds planes 1 … n2 of a globally periodic extent of n2g planes starting after global plane
   // zoff; planes 0 and n2+1 of r are the exchanged ghost planes, the four planes beyond them on each side are in rext
   // ([side][4] planes, nearest-to-farthest from the slab on the lower side reversed: index t+4 for t = −4…−1, t−n2−2 above).
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
   const int par = warp & 1;  // parity class of this warp's rows
   const int qi = (warp >> 1) * 32 + lane;
   const int rc = qi / VS_NGX, gx = qi - rc * VS_NGX;
-  const int ry = min(2 * rc + par, VS_TH - 1);
-  const bool act = 2 * rc + par < VS_TH;
-  const int xb = 1 + VS_CX * blockIdx.x, yb = 1 + VS_CY * blockIdx.y;
+  const int ry = min(2 * rc + par, a.th - 1);
+  const bool act = 2 * rc + par < a.th;
+  const int xb = 1 + VS_CX * blockIdx.x, yb = 1 + a.cy * blockIdx.y;
   const int z0 = 1 + a.zchunk * blockIdx.z, z1 = min(z0 + a.zchunk, n2 + 1);
   const int xu = xb - 8 + 8 * gx, yu = yb - VS_HALO + ry;  // unwrapped coordinates of the group's first cell / of the row
   const int ypar = yu & 1;
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant
   constexpr int oY = VS_NGX * 4;
   // neighbour offsets of the sweeps; 0 where the neighbour would lie outside the tile (see vs_sweep)
   const int oSl = gx == 0 ? 0 : -1, oSr = gx == VS_NGX - 1 ? 0 : 4;
-  const int oYm = ry == 0 ? 0 : -oY, oYp = ry == VS_TH - 1 ? 0 : oY;
-  const bool core = act && gx >= 1 && gx <= VS_NGX - 2 && ry >= VS_HALO && ry < VS_TH - VS_HALO && xu <= n0 && yu <= n1;
+  const int oYm = ry == 0 ? 0 : -oY, oYp = ry == a.th - 1 ? 0 : oY;
+  const bool core = act && gx >= 1 && gx <= VS_NGX - 2 && ry >= VS_HALO && ry < a.th - VS_HALO && xu <= n0 && yu <= n1;
   // global offsets (in-plane)
   const int gin = g.xo + xs + g.px * yr;
   const int cy = (yr + 1) >> 1;

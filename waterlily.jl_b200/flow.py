@@ -41,6 +41,17 @@ class TimeBC:
         return len(self.U0)
 
 
+def sgs(*a, **k):
+    """sgs!(flow,u,t;νₜ,S,Cs,Δ) (src/util.jl:46-76) — a marker: `sim_step(sim, udf=sgs, νₜ=smagorinsky, Cs=…, Δ=…)` selects the
+    library's built-in device implementation (wl_set_sgs); it cannot be called on the host."""
+    raise _lib.WLError("sgs is evaluated on the device: pass it as sim_step(sim, udf=sgs, νₜ=smagorinsky, Cs=…, Δ=…)")
+
+
+def smagorinsky(*a, **k):
+    """smagorinsky(I;S,Cs,Δ) = (Cs·Δ)²·√(S[I,:,:]⋅S[I,:,:]) (src/util.jl:57-62) — a marker for the `νₜ` keyword of `sim_step`."""
+    raise _lib.WLError("smagorinsky is evaluated on the device: pass it as the νₜ keyword of sim_step together with udf=sgs")
+
+
 def loc_grid(N, i, zoff=0):
     """loc(i,I) for all cells of a ghost-padded grid (src/core.jl:177): list of D broadcastable coordinate arrays."""
     from .body import _loc

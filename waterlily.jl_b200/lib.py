@@ -113,6 +113,7 @@ def load_library(fmad=False):
         "wl_time_next": [H, C.POINTER(C.c_double)],
         "wl_body_forces": [H, C.POINTER(C.c_float), C.POINTER(C.c_double)],
         "wl_set_forcing": [H, fp, fp, fp, fp],
+        "wl_set_sgs": [H, C.c_float, C.c_float],
         "wl_meanflow_init": [H, C.c_int],
         "wl_meanflow_update": [H],
         "wl_meanflow_reset": [H, C.c_float],
@@ -136,7 +137,7 @@ def load_library(fmad=False):
 
 
 FLAGS = {"general_coeff": 1, "unfused_gs": 2, "no_persistent": 4, "nccl_halo": 8, "no_vsmooth": 16, "no_conv4": 32,
-         "no_fused_uni": 64, "no_semi": 128, "no_tiny": 256}  # WL_FLAG_* (include/wl_b200.h)
+         "no_fused_uni": 64, "no_semi": 128, "no_tiny": 256, "no_fast_read": 512}  # WL_FLAG_* (include/wl_b200.h)
 
 
 def check(L, rc):

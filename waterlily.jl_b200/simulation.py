@@ -5,7 +5,7 @@ import numpy as np
 
 from . import lib as _lib
 from .body import NoBody, _Parametrised, measure_body, prim_array
-from .flow import Flow, MultiLevelPoisson, Poisson, quick
+from .flow import Flow, MultiLevelPoisson, Poisson, quick, sgs, smagorinsky
 
 F = np.float32
 
@@ -74,13 +74,22 @@ def sim_time(sim):
     return sim.flow.time() * sim.U / sim.L
 
 
-def sim_step(sim, t_end=None, remeasure=False, max_steps=2**62, verbose=False, udf=None):
-    """sim_step!(sim,t_end;remeasure,max_steps,verbose) and sim_step!(sim;remeasure) (src/WaterLily.jl:128-139).
+def sim_step(sim, t_end=None, remeasure=False, max_steps=2**62, verbose=False, udf=None, νₜ=None, S=None, Cs=None, Δ=None, **kwargs):
+    """sim_step!(sim,t_end;remeasure,max_steps,verbose,udf,kwargs...) and sim_step!(sim;remeasure,udf,kwargs...) (src/WaterLily.jl:128-139).
     `remeasure=True` re-measures a parametrised (device-measured) body at t = sum(Δt) before every step, inside the library;
-    a body given as a host closure cannot be re-measured per step through the C ABI."""
-    if udf is not None:
-        raise _lib.WLError("udf is a host closure: not supported by the B200 C ABI")
+    a body given as a host closure cannot be re-measured per step through the C ABI.
+    `udf`: the one user-defined function the library has built in is the reference's own LES model,
+    `sim_step(sim; udf=sgs, νₜ=smagorinsky, Cs, Δ)` (src/util.jl:46-76; `S` is scratch the library owns, accepted and ignored);
+    any other udf is a host closure and is rejected."""
     fl = sim.flow
+    if udf is sgs:
+        if νₜ is not smagorinsky or Cs is None or Δ is None:
+            raise _lib.WLError("udf=sgs needs νₜ=smagorinsky (the built-in eddy viscosity), Cs and Δ")
+        _lib.check(fl.L, fl.L.wl_set_sgs(fl.h, float(Cs), float(Δ)))
+    elif udf is not None or kwargs:
+        raise _lib.WLError("udf is a host closure: not supported by the B200 C ABI (built in: udf=sgs with νₜ=smagorinsky)")
+    else:
+        _lib.check(fl.L, fl.L.wl_set_sgs(fl.h, 0.0, 0.0))
     if remeasure and not isinstance(sim.body, NoBody):
         if not getattr(sim, "device_body", False):
             raise _lib.WLError("remeasure=true needs a parametrised body (Sphere, Torus, set operations): an AutoBody closure "
