@@ -71,6 +71,8 @@ enum {
   WL_FLAG_NO_FUSED_UNI = 64, /* constant-coefficient mode: f_div_residual / f_jacobi / f_correct + f_cfl instead of their fused forms */
   WL_FLAG_NO_TINY = 256,     /* run the coarsest levels (≤ 8192 cells) inside the cooperative coarse-level kernel instead of the one-block kernel */
   WL_FLAG_NO_SEMI = 128,     /* general mode: always read the face coefficients L (no semi-uniform march blocks, no body-free BDIM blocks) */
+  WL_FLAG_NO_PREFETCH = 1024, /* z slabs: push the halo of r that f_vsmooth reads right before that kernel instead of on a side stream after Jacobi! */
+  WL_FLAG_NCCL_ALLREDUCE = 2048, /* z slabs: ncclAllReduce for the solver's and CFL's scalars instead of the one-warp all-reduce over peer memory */
   WL_FLAG_NO_FAST_READ = 512, /* read the solver's residual norms with a copy + stream synchronisation instead of polling the mapped mirror the reduction writes */
 };
 

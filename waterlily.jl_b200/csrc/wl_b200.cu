@@ -171,6 +171,21 @@ struct wl_handle {
   std::vector<char*> peer_base[2];  // [0] lower neighbour, [1] upper neighbour
   int* mbox = nullptr;              // ready[2], arrived[2], block counter, error
   int halo_seq = 0;
+  // second exchange lane (own stream, own mailbox words mbox+16…, own sequence): pushes whose data is final long before its reader runs
+  // — the 4+1-plane halo of r that f_vsmooth reads is final after the level's Jacobi! — overlap the coarse part of the V-cycle
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_pre[4] = {nullptr, nullptr, nullptr, nullptr};  // per level: the prefetch push of that level's r halo is complete
+  bool pre_done[4] = {false, false, false, false};
+  int halo_seq2 = 0;
+  bool prefetch = true;
+  // own all-reduce of the solver's / CFL's scalars over peer memory (k_allreduce): every rank's mailbox mapped on every rank
+  double* armb = nullptr;
+  ArPeers ar_peers{};
+  std::vector<void*> ar_opened;  // IPC mappings opened for it beyond the neighbours'
+  bool ar_on = false;
+  long long ar_seq = 0;
+  bool slot_ar[NSLOTS] = {false};  // the slot's latest value came from k_allreduce (its tag is in slot_tag: the host may poll it)
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
   int slab_min_planes = 8;
@@ -342,7 +357,8 @@ struct PlaneMove {
   int side;
   const float* dst_local;
 };
-static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, bool carries_u = false) {
+// `lane` 1: on the side stream (after everything enqueued on the main stream so far), see wl_handle::st2
+static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, bool carries_u = false, int lane = 0) {
   HaloSegs segs;
   memset(&segs, 0, sizeof segs);
   const Dist& d = h->dist;
@@ -357,16 +373,24 @@ static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, boo
   }
   segs.nseg = m;
   const int cnt4 = (int)(g.s[2] / 4);
-  int* plo = d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)h->mbox) : nullptr;
-  int* phi = d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)h->mbox) : nullptr;
-  const int seq = ++h->halo_seq;
+  int* const mb = h->mbox + (lane ? 16 : 0);
+  int* plo = d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)mb) : nullptr;
+  int* phi = d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)mb) : nullptr;
+  const int seq = lane ? ++h->halo_seq2 : ++h->halo_seq;
   const long long total4 = (long long)m * cnt4;
-  const int nb = (int)std::max<long long>(1, std::min<long long>(128, (total4 + 2047) / 2048));
-  prof_begin(h, "halo_exchange_p2p");
+  const int nb = (int)std::max<long long>(1, std::min<long long>(lane ? 64 : 128, (total4 + 2047) / 2048));
   const int* myf = carries_u ? h->d_flags : nullptr;
   int* flo = carries_u && d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)h->d_flags) : nullptr;
   int* fhi = carries_u && d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)h->d_flags) : nullptr;
-  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, h->mbox, plo, phi, 60000000000LL, myf, flo, fhi);
+  if (lane) {
+    CK(cudaEventRecord(h->ev_fork, h->st));
+    CK(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+    k_halo_push<<<nb, 256, 0, h->st2>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi);
+    h->launches++;
+    return 0;
+  }
+  prof_begin(h, "halo_exchange_p2p");
+  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi);
   prof_end(h);
   h->launches++;
   return 0;
@@ -501,6 +525,18 @@ static int exch_uz_up(wl_handle* h, float* u) {
 // In-place all-reduce of one reduction slot (double) across the ranks, on the compute stream.
 static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `count` adjacent slots in one call
   if (!h->dist.on()) return 0;
+  if (h->ar_on && count <= 2) {
+    if (++h->tag_ctr == 0) h->tag_ctr = 1;
+    const unsigned int tag = h->tag_ctr;
+    h->slot_tag[slot] = tag;
+    h->slot_ar[slot] = true;
+    prof_begin(h, "allreduce_p2p");
+    k_allreduce<<<1, 32, 0, h->st>>>(h->ar_peers, h->dist.P, h->dist.rank, ++h->ar_seq, op == WL_NCCL_SUM ? RED_SUM : RED_MAX, count, h->red.out + slot,
+                                     h->red.hout + slot, h->red.hseq + slot, tag, h->mbox + 40, 60000000000LL);
+    prof_end(h);
+    h->launches++;
+    return 0;
+  }
   prof_begin(h, "allreduce");
   NCK(g_nccl.AllReduce(h->red.out + slot, h->red.out + slot, count, WL_NCCL_DOUBLE, op, h->dist.comm, h->st));
   prof_end(h);
@@ -759,8 +795,10 @@ static RedBuf red_for(wl_handle* h, int slot, bool active = true) {
 // z slabs: the slot was all-reduced on the stream after the kernel — copy and synchronise.
 static int read_slot(wl_handle* h, int slot, double* out, int n = 1) {
   const unsigned int want = h->slot_tag[slot];
+  const bool reduced_here = !h->dist.on() || h->slot_ar[slot];  // (NCCL all-reduce: the mirror holds this rank's partial value)
   h->slot_tag[slot] = 0;
-  if (h->fast_read && want && !h->dist.on()) {
+  h->slot_ar[slot] = false;
+  if (h->fast_read && want && reduced_here) {
     volatile unsigned int* sq = h->red.hseq + slot;
     bool ok = true;
     for (unsigned int spins = 1; *sq != want; spins++) {
@@ -833,6 +871,7 @@ static int gs_smooth(wl_handle* h, Level& l, const float* wp, int x_is_zero, int
     LAUNCH_D(h, k_increment, grd(in, b), b, d, in, wp, x_is_zero, with_l2, red_for(h, SLOT_R2, with_l2), SLOT_R2);
   return 0;
 }
+static int vs_push_r(wl_handle* h, size_t li, int lane);
 // Jacobi!(p;ω=1)  src/Poisson.jl:111-114
 // With `coarse` given (full coarsening, march kernels) restrict!(coarse.r, fine.r) is fused in; *fused tells whether it was.
 // `skip_r_exch`: the caller follows up with vsmooth on this level, which pushes r's ghost plane together with its deeper halo
@@ -859,7 +898,12 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     LAUNCH_D(h, k_jacobi, grd(in, b), b, l.dev(), in, x_is_zero);
   }
   std::swap(l.r, l.r2);
-  if (!skip_r_exch) TRY(exch(h, l, l.r, 1));
+  if (!skip_r_exch)
+    TRY(exch(h, l, l.r, 1));
+  else if (h->p2p && h->prefetch && h->st2) {
+    const size_t li = (size_t)(&l - h->levels.data());
+    if (li < 4) TRY(vs_push_r(h, li, 1));  // r is final: its halo for f_vsmooth travels while the coarse levels run
+  }
   if (fused && h->dist.on()) {
     if (l.slab && !coarse->slab)
       TRY(allgather_planes(h, *coarse, coarse->r, (l.g.N[2] - 2) / 2));
@@ -923,6 +967,27 @@ static bool vs_fusable(const wl_handle* h, size_t li) {
     return f.fast && c.fullc && n0 % 8 == 0 && n1 % 2 == 0 && n0 >= 64 && n1 >= 32;
   }
   return f.fast && c.fullc && n0 % 8 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && n0 >= 64 && n1 >= 32 && n2 >= 64;
+}
+// The halo of r that f_vsmooth needs on a z slab: the ghost planes (Jacobi! left them to this push) and the four planes beyond them
+// on each side, into the neighbours' r / rext.  lane 1: on the side stream, complete at ev_pre[li].
+static int vs_push_r(wl_handle* h, size_t li, int lane) {
+  Level& f = h->levels[li];
+  const int n2 = f.g.N[2] - 2;
+  PlaneMove mv[10];
+  int m = 0;
+  const i64 s2 = f.g.s[2];
+  mv[m++] = {f.r + s2 * n2, 1, f.r};
+  mv[m++] = {f.r + s2 * 1, 0, f.r + s2 * (n2 + 1)};
+  for (int k = 0; k < 4; k++) {
+    mv[m++] = {f.r + s2 * (n2 - 4 + k), 1, f.rext + s2 * k};
+    mv[m++] = {f.r + s2 * (2 + k), 0, f.rext + s2 * (4 + k)};
+  }
+  TRY(p2p_push(h, f.g, mv, m, false, lane));
+  if (lane) {
+    CK(cudaEventRecord(h->ev_pre[li], h->st2));
+    h->pre_done[li] = true;
+  }
+  return 0;
 }
 // prolongate! + increment! + GaussSeidelRB! + increment! (+ L₂) of level li in one launch (wl_vsmooth.cuh)
 static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
@@ -988,16 +1053,13 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   if (f.slab) {
     // planes −4 … −1 and n2+2 … n2+5 of r (the ghost planes 0 and n2+1 are current since Jacobi!'s exchange), and, when the coarse
     // level is a slab too, its planes −2, −1 and nc+2, nc+3 of x: pushed straight into the neighbours' rext / xext
+    if (li < 4 && h->pre_done[li]) {  // (the r planes went out on the side stream right after Jacobi!, vs_push_r)
+      CK(cudaStreamWaitEvent(h->st, h->ev_pre[li], 0));
+      h->pre_done[li] = false;
+    } else
+      TRY(vs_push_r(h, li, 0));
     PlaneMove mv[10];
     int m = 0;
-    const i64 s2 = f.g.s[2];
-    mv[m++] = {f.r + s2 * n2, 1, f.r};                  // the ghost planes themselves (Jacobi! left them to this push)
-    mv[m++] = {f.r + s2 * 1, 0, f.r + s2 * (n2 + 1)};
-    for (int k = 0; k < 4; k++) {
-      mv[m++] = {f.r + s2 * (n2 - 4 + k), 1, f.rext + s2 * k};
-      mv[m++] = {f.r + s2 * (2 + k), 0, f.rext + s2 * (4 + k)};
-    }
-    TRY(p2p_push(h, f.g, mv, m));
     if (c.slab && !vs_fusable(h, li + 1)) {  // (a coarse level that ran vsmooth itself has pushed its xext planes already)
       const i64 c2 = c.g.s[2];
       const int nc = c.g.N[2] - 2;
@@ -1534,8 +1596,11 @@ static int ensure_dt_capacity(wl_handle* h, size_t need) {
 static int check_flags(wl_handle* h) {
   int f = 0, e = 0;
   CK(cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  int e2 = 0;
   if (h->mbox) CK(cudaMemcpyAsync(&e, h->mbox + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  if (h->mbox) CK(cudaMemcpyAsync(&e2, h->mbox + 16 + 5, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
+  e |= e2;
   if (f) return fail("the flux kernel met a non-finite velocity (or |u| > 1e37): the velocity field has diverged");
   if (e) return fail("peer-to-peer halo exchange timed out waiting for a neighbouring rank (the ring is marked failed; results after the timeout are invalid)");
   return 0;
@@ -1736,6 +1801,34 @@ static int setup_p2p(wl_handle* h) {
     }
   }
   h->p2p = true;
+  // every rank's all-reduce mailbox (the chunk it lives in: neighbours' mappings are reused, the others are opened here)
+  if (d.P <= 8 && h->armb && !(h->cfg.flags & WL_FLAG_NCCL_ALLREDUCE)) {
+    int k0 = -1;
+    size_t off = 0;
+    for (int k = 0; k < nch; k++)
+      if ((char*)h->armb >= h->chunks[k].base && (char*)h->armb < h->chunks[k].base + h->chunks[k].size) k0 = k, off = (size_t)((char*)h->armb - h->chunks[k].base);
+    if (k0 < 0) return fail("all-reduce mailbox outside the chunks");
+    for (int q = 0; q < d.P; q++) {
+      char* base = nullptr;
+      if (q == d.rank)
+        base = h->chunks[k0].base;
+      else if (q == d.down)
+        base = h->peer_base[0][k0];
+      else if (q == d.up)
+        base = h->peer_base[1][k0];
+      else {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, all.data() + per * q + (size_t)k0 * rec, rec);
+        void* m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle (all-reduce mailbox of rank %d): %s", q, cudaGetErrorString(e));
+        h->ar_opened.push_back(m);
+        base = (char*)m;
+      }
+      h->ar_peers.p[q] = (double*)(base + off);
+    }
+    h->ar_on = true;
+  }
   return 0;
 }
 
@@ -1787,6 +1880,15 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->perz_global = cfg->D == 3 && cfg->perdir[2] != 0;
   int rc = 0;
   do {
+    if (nranks > 1) {
+      bool ok = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int q = 0; q < 4 && ok; q++) ok = cudaEventCreateWithFlags(&h->ev_pre[q], cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) {
+        rc = fail("side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+      h->prefetch = !(cfg->flags & WL_FLAG_NO_PREFETCH);
+    }
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
       rc = fail("cudaStreamCreate failed");
       break;
@@ -1826,6 +1928,8 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         float* q = nullptr;
         if ((rc = dalloc(h, &q, 64))) break;
         h->mbox = (int*)q;
+        if ((rc = dalloc(h, &q, 2 * 8 * 4 * 2))) break;  // k_allreduce mailbox: [2][8][4] doubles
+        h->armb = (double*)q;
       }
     }
     const size_t n = (size_t)h->g.sc;
@@ -1948,6 +2052,7 @@ int wl_destroy(wl_handle* h) {
       for (char* q : h->peer_base[side])
         if (q) cudaIpcCloseMemHandle(q);
     }
+    for (void* q : h->ar_opened) cudaIpcCloseMemHandle(q);
   }
   // (the communicator belongs to the process-wide cache and outlives the handle)
   for (void* q : h->allocs) cudaFree(q);
@@ -1958,6 +2063,13 @@ int wl_destroy(wl_handle* h) {
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->red.hout) cudaFreeHost(h->red.hout);
   if (h->h_ops) cudaFreeHost(h->h_ops);
+  if (h->st2) {
+    cudaStreamSynchronize(h->st2);
+    cudaStreamDestroy(h->st2);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int q = 0; q < 4; q++)
+    if (h->ev_pre[q]) cudaEventDestroy(h->ev_pre[q]);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;

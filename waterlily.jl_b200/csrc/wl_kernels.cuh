@@ -955,6 +955,55 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int 
   }
 }
 
+// All-reduce of one or two doubles across ≤ 8 ranks over NVLink peer memory, one warp: every rank stores its values and then the
+// sequence number into its own row of every rank's mailbox (two buffers alternate with the sequence's parity: a rank can be at most
+// one all-reduce ahead of another, because it needs everybody's values of call n to finish call n), waits until all rows of its own
+// mailbox carry the sequence, and folds them in rank order — the same order on every rank, so all ranks get the same bits.
+// The result goes to out[] and, tagged, to the host-visible mirror (RedBuf::hout / hseq) like a local reduction's.
+struct ArPeers {
+  double* p[8];  // rank q's mailbox as mapped into this process: [2 buffers][8 source ranks][4 doubles: v0, v1, sequence, pad]
+};
+__global__ void __launch_bounds__(32) k_allreduce(ArPeers peers, int P, int rank, long long seq, int op, int count, double* out, double* hout,
+                                                  unsigned int* hseq, unsigned int tag, int* err, long long timeout) {
+  const int t = threadIdx.x;
+  const int b = (int)(seq & 1);
+  const double v0 = out[0], v1 = count > 1 ? out[1] : 0.0;
+  if (t < P) {
+    volatile double* dst = peers.p[t] + (b * 8 + rank) * 4;
+    dst[0] = v0;
+    dst[1] = v1;
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>(dst + 2) = seq;
+    volatile double* src = peers.p[rank] + (b * 8 + t) * 4;
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile long long*>(src + 2) != seq) {
+      if (clock64() - t0 > timeout || ld_flag(err) != 0) {
+        st_flag_sys(err, 1);
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (t == 0) {
+    __threadfence_system();
+    volatile double* mine = peers.p[rank] + b * 8 * 4;
+    double a0 = op == RED_SUM ? 0.0 : -1.0e300, a1 = a0;
+    for (int q = 0; q < P; q++) {
+      const double w0 = mine[q * 4], w1 = mine[q * 4 + 1];
+      a0 = op == RED_SUM ? a0 + w0 : (a0 > w0 ? a0 : w0);
+      a1 = op == RED_SUM ? a1 + w1 : (a1 > w1 ? a1 : w1);
+    }
+    out[0] = a0;
+    if (count > 1) out[1] = a1;
+    if (tag) {
+      hout[0] = a0;
+      if (count > 1) hout[1] = a1;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int*>(hseq) = tag;
+    }
+  }
+}
+
 // Range check of a velocity field the library did not write itself (uploads, wl_apply_bc, kernels without the built-in check):
 // raises flags[2] / flags[0] as described at range_note (wl_common.cuh).  n4 = number of float4 to scan.
 __global__ void __launch_bounds__(256) k_range_check(const float4* __restrict__ a, long long n4, int* __restrict__ flags) {
