@@ -179,12 +179,15 @@ struct wl_handle {
   bool pre_done[4] = {false, false, false, false};
   int halo_seq2 = 0;
   bool prefetch = true;
+  bool skip_ready = true;
   // own all-reduce of the solver's / CFL's scalars over peer memory (k_allreduce): every rank's mailbox mapped on every rank
   double* armb = nullptr;
   ArPeers ar_peers{};
   std::vector<void*> ar_opened;  // IPC mappings opened for it beyond the neighbours'
   bool ar_on = false;
-  long long ar_seq = 0;
+  long long ar_seq = 0, bc_seq = 0;
+  std::vector<char> ipc_all;                 // every rank's chunk handles (setup_p2p), for mappings opened later
+  std::vector<std::vector<char*>> any_base;  // [rank][chunk] → base of that chunk as mapped here (null: not mapped yet)
   bool slot_ar[NSLOTS] = {false};  // the slot's latest value came from k_allreduce (its tag is in slot_tag: the host may poll it)
   float* uext = nullptr;  // second halo planes of the velocity beyond open z faces: [side][component][plane]
   int perz_global = 0;
@@ -358,7 +361,10 @@ struct PlaneMove {
   const float* dst_local;
 };
 // `lane` 1: on the side stream (after everything enqueued on the main stream so far), see wl_handle::st2
-static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, bool carries_u = false, int lane = 0) {
+// `war_safe`: at least one other exchange lies between the neighbours' last read of the destination planes and this push (true for
+// every exchange of the uniform-mode step: each set of ghost planes is rewritten once per V-cycle / projection) → k_halo_push
+// skips its "ready" round trip.  Only honoured in uniform mode: the general smoother refreshes ϵ's ghosts after every half-sweep.
+static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, bool carries_u = false, int lane = 0, bool war_safe = false) {
   HaloSegs segs;
   memset(&segs, 0, sizeof segs);
   const Dist& d = h->dist;
@@ -382,21 +388,22 @@ static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, boo
   const int* myf = carries_u ? h->d_flags : nullptr;
   int* flo = carries_u && d.down >= 0 ? (int*)peer_ptr(h, 0, (const float*)h->d_flags) : nullptr;
   int* fhi = carries_u && d.up >= 0 ? (int*)peer_ptr(h, 1, (const float*)h->d_flags) : nullptr;
+  const int no_ready = (war_safe && h->uni && h->skip_ready) ? 1 : 0;
   if (lane) {
     CK(cudaEventRecord(h->ev_fork, h->st));
     CK(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
-    k_halo_push<<<nb, 256, 0, h->st2>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi);
+    k_halo_push<<<nb, 256, 0, h->st2>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi, no_ready);
     h->launches++;
     return 0;
   }
   prof_begin(h, "halo_exchange_p2p");
-  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi);
+  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi, no_ready);
   prof_end(h);
   h->launches++;
   return 0;
 }
 
-static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
+static int exch(wl_handle* h, const Level& l, float* a, int ncomp, bool war_safe = false) {
   if (!h->dist.on() || !l.slab) return 0;
   const Grid& g = l.g;
   const size_t cnt = (size_t)g.s[2];
@@ -409,7 +416,7 @@ static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
       mv[n++] = {b + g.s[2] * (g.N[2] - 2), 1, b};                      // my top interior plane → upper neighbour's lower ghost
       mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};         // my bottom interior plane → lower neighbour's upper ghost
     }
-    return p2p_push(h, g, mv, n);
+    return p2p_push(h, g, mv, n, false, 0, war_safe);
   }
   if (h->p2p) {  // more than 8 components (μ₁): in two batches
     TRY(exch(h, l, a, 8));
@@ -429,7 +436,7 @@ static int exch(wl_handle* h, const Level& l, float* a, int ncomp) {
   return 0;
 }
 // Two scalar fields in one NCCL group (r and x after increment!)
-static int exch2(wl_handle* h, const Level& l, float* a0, float* a1) {
+static int exch2(wl_handle* h, const Level& l, float* a0, float* a1, bool war_safe = false) {
   if (!h->dist.on() || !l.slab) return 0;
   const Grid& g = l.g;
   const size_t cnt = (size_t)g.s[2];
@@ -443,7 +450,7 @@ static int exch2(wl_handle* h, const Level& l, float* a0, float* a1) {
       mv[n++] = {b + g.s[2] * (g.N[2] - 2), 1, b};
       mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};
     }
-    return p2p_push(h, g, mv, n);
+    return p2p_push(h, g, mv, n, false, 0, war_safe);
   }
   prof_begin(h, "halo_exchange");
   NCK(g_nccl.GroupStart());
@@ -482,7 +489,7 @@ static int exch_u(wl_handle* h, float* u, float* p = nullptr) {
       mv[n++] = {b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)};
       mv[n++] = {b + g.s[2] * 2, 0, ehi};
     }
-    return p2p_push(h, g, mv, n, true);
+    return p2p_push(h, g, mv, n, true, 0, true);
   }
   prof_begin(h, "halo_exchange_u");
   NCK(g_nccl.GroupStart());
@@ -520,7 +527,7 @@ static int exch_uz_up(wl_handle* h, float* u) {
   const Grid& g = h->g;
   float* b = u + (size_t)2 * g.sc;
   PlaneMove mv[1] = {{b + g.s[2] * 1, 0, b + g.s[2] * (g.N[2] - 1)}};  // my bottom interior plane → the lower neighbour's upper ghost plane
-  return p2p_push(h, g, mv, 1);
+  return p2p_push(h, g, mv, 1, false, 0, true);
 }
 // In-place all-reduce of one reduction slot (double) across the ranks, on the compute stream.
 static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `count` adjacent slots in one call
@@ -543,11 +550,74 @@ static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `
   return 0;
 }
 // Gather the interior planes of a replicated level's field from the ranks that each restricted their own slab into it.
-static int allgather_planes(wl_handle* h, const Level& lc, float* a, int planes_per_rank) {
+// Base of chunk k of rank q as mapped into this process (opened on first use; the neighbours' mappings are reused).
+static float* any_peer_ptr(wl_handle* h, int q, const float* local) {
+  const Dist& d = h->dist;
+  const char* lp = (const char*)local;
+  for (size_t k = 0; k < h->chunks.size(); k++) {
+    const Chunk& c = h->chunks[k];
+    if (lp < c.base || lp >= c.base + c.size) continue;
+    if (q == d.rank) return (float*)local;
+    if (h->any_base.size() != (size_t)d.P) h->any_base.assign(d.P, std::vector<char*>());
+    std::vector<char*>& tab = h->any_base[q];
+    if (tab.size() < h->chunks.size()) tab.resize(h->chunks.size(), nullptr);
+    if (!tab[k]) {
+      if (q == d.down && k < h->peer_base[0].size() && h->peer_base[0][k])
+        tab[k] = h->peer_base[0][k];
+      else if (q == d.up && k < h->peer_base[1].size() && h->peer_base[1][k])
+        tab[k] = h->peer_base[1][k];
+      else {
+        const size_t rec = sizeof(cudaIpcMemHandle_t);
+        const size_t per = h->ipc_all.size() / d.P;
+        if ((k + 1) * rec > per) {
+          fail("chunk %zu was allocated after the IPC handles were exchanged", k);
+          return nullptr;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, h->ipc_all.data() + per * q + k * rec, rec);
+        void* m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          fail("cudaIpcOpenMemHandle (rank %d chunk %zu): %s", q, k, cudaGetErrorString(e));
+          return nullptr;
+        }
+        h->ar_opened.push_back(m);
+        tab[k] = (char*)m;
+      }
+    }
+    return (float*)(tab[k] + (lp - c.base));
+  }
+  fail("address outside the IPC-mapped chunks");
+  return nullptr;
+}
+// `p2p_ok`: the call sits inside the V-cycle, where an all-reduce separates two gathers of the same array (the peer-memory version
+// writes into the other ranks' copies without asking whether they are done reading the previous contents)
+static int allgather_planes(wl_handle* h, const Level& lc, float* a, int planes_per_rank, bool p2p_ok = false) {
   if (!h->dist.on()) return 0;
   const Grid& g = lc.g;
   const size_t cnt = (size_t)g.s[2] * planes_per_rank;
   float* base = a + g.s[2];  // plane 1
+  if (h->ar_on && p2p_ok && cnt % 4 == 0) {
+    const Dist& d = h->dist;
+    float* mine = base + cnt * d.rank;
+    BcastDst dst;
+    memset(&dst, 0, sizeof dst);
+    for (int q = 0; q < d.P; q++) {
+      if (q == d.rank) continue;
+      float* pq = any_peer_ptr(h, q, mine);
+      if (!pq) return 1;
+      dst.p[q] = reinterpret_cast<float4*>(pq);
+    }
+    ArPeers bar = h->ar_peers;
+    for (int q = 0; q < d.P; q++) bar.p[q] += 64;  // the barrier's region of the mailbox
+    const long long n4 = (long long)(cnt / 4);
+    const int nb = (int)std::max<long long>(1, std::min<long long>(96, (n4 + 1023) / 1024));
+    prof_begin(h, "allgather_p2p");
+    k_bcast_planes<<<nb, 256, 0, h->st>>>(reinterpret_cast<const float4*>(mine), dst, n4, bar, d.P, d.rank, ++h->bc_seq, h->mbox + 44, h->mbox + 40, 60000000000LL);
+    prof_end(h);
+    h->launches++;
+    return 0;
+  }
   prof_begin(h, "allgather");
   NCK(g_nccl.AllGather(base + cnt * h->dist.rank, base, cnt, WL_NCCL_FLOAT, h->dist.comm, h->st));
   prof_end(h);
@@ -906,9 +976,9 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
   }
   if (fused && h->dist.on()) {
     if (l.slab && !coarse->slab)
-      TRY(allgather_planes(h, *coarse, coarse->r, (l.g.N[2] - 2) / 2));
+      TRY(allgather_planes(h, *coarse, coarse->r, (l.g.N[2] - 2) / 2, true));
     else
-      TRY(exch(h, *coarse, coarse->r, 1));
+      TRY(exch(h, *coarse, coarse->r, 1, h->vsmooth));
   }
   if (fused_out) *fused_out = fused;
   return 0;
@@ -982,7 +1052,7 @@ static int vs_push_r(wl_handle* h, size_t li, int lane) {
     mv[m++] = {f.r + s2 * (n2 - 4 + k), 1, f.rext + s2 * k};
     mv[m++] = {f.r + s2 * (2 + k), 0, f.rext + s2 * (4 + k)};
   }
-  TRY(p2p_push(h, f.g, mv, m, false, lane));
+  TRY(p2p_push(h, f.g, mv, m, false, lane, true));
   if (lane) {
     CK(cudaEventRecord(h->ev_pre[li], h->st2));
     h->pre_done[li] = true;
@@ -1091,9 +1161,9 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
       mv[m++] = {f.x + s2 * (n2 - 2 + k), 1, f.xext + s2 * k};
       mv[m++] = {f.x + s2 * (2 + k), 0, f.xext + s2 * (2 + k)};
     }
-    TRY(p2p_push(h, f.g, mv, m));
+    TRY(p2p_push(h, f.g, mv, m, false, 0, true));
   } else
-    TRY(exch2(h, f, f.r, f.x));
+    TRY(exch2(h, f, f.r, f.x, true));
   if (with_l2) TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
   return 0;
 }
@@ -1334,9 +1404,9 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
     if (std::fabs(s) > 2.f * 1.1920929e-7f) {
       LAUNCH(h, f_resid_fix, l.fgrid(), dim3(32, FTY), l.g, l.r, count, l.zchunk(), red_for(h, SLOT_R2), SLOT_RSUM, SLOT_R2);
       TRY(allreduce_slot(h, SLOT_R2, WL_NCCL_SUM));
-      TRY(exch(h, l, l.r, 1));
+      TRY(exch(h, l, l.r, 1, true));
     } else {
-      TRY(exch(h, l, l.r, 1));
+      TRY(exch(h, l, l.r, 1, true));
       *r2 = (float)sums[1];
       return 0;
     }
@@ -1801,31 +1871,12 @@ static int setup_p2p(wl_handle* h) {
     }
   }
   h->p2p = true;
+  h->ipc_all = all;
   // every rank's all-reduce mailbox (the chunk it lives in: neighbours' mappings are reused, the others are opened here)
   if (d.P <= 8 && h->armb && !(h->cfg.flags & WL_FLAG_NCCL_ALLREDUCE)) {
-    int k0 = -1;
-    size_t off = 0;
-    for (int k = 0; k < nch; k++)
-      if ((char*)h->armb >= h->chunks[k].base && (char*)h->armb < h->chunks[k].base + h->chunks[k].size) k0 = k, off = (size_t)((char*)h->armb - h->chunks[k].base);
-    if (k0 < 0) return fail("all-reduce mailbox outside the chunks");
     for (int q = 0; q < d.P; q++) {
-      char* base = nullptr;
-      if (q == d.rank)
-        base = h->chunks[k0].base;
-      else if (q == d.down)
-        base = h->peer_base[0][k0];
-      else if (q == d.up)
-        base = h->peer_base[1][k0];
-      else {
-        cudaIpcMemHandle_t hd;
-        memcpy(&hd, all.data() + per * q + (size_t)k0 * rec, rec);
-        void* m = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&m, hd, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle (all-reduce mailbox of rank %d): %s", q, cudaGetErrorString(e));
-        h->ar_opened.push_back(m);
-        base = (char*)m;
-      }
-      h->ar_peers.p[q] = (double*)(base + off);
+      h->ar_peers.p[q] = (double*)any_peer_ptr(h, q, (const float*)h->armb);
+      if (!h->ar_peers.p[q]) return 1;
     }
     h->ar_on = true;
   }
@@ -1888,6 +1939,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         break;
       }
       h->prefetch = !(cfg->flags & WL_FLAG_NO_PREFETCH);
+      h->skip_ready = !(cfg->flags & WL_FLAG_NO_PREFETCH);
     }
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
       rc = fail("cudaStreamCreate failed");
@@ -1928,7 +1980,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         float* q = nullptr;
         if ((rc = dalloc(h, &q, 64))) break;
         h->mbox = (int*)q;
-        if ((rc = dalloc(h, &q, 2 * 8 * 4 * 2))) break;  // k_allreduce mailbox: [2][8][4] doubles
+        if ((rc = dalloc(h, &q, 2 * 2 * 8 * 4 * 2))) break;  // k_allreduce mailbox [2][8][4] doubles, then the same for k_bcast_planes' barrier
         h->armb = (double*)q;
       }
     }
