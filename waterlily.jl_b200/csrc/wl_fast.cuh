@@ -1527,12 +1527,50 @@ struct TinyLvl {
   int n0, n1, n2, cells;
   unsigned m0, m1, mh;  // ⌈2³²/n0⌉, ⌈2³²/n1⌉, ⌈2³²/(n0/2)⌉: c / n = umulhi(c, m) exactly for c·n < 2³² (cells ≤ 8192)
   float L0, L1, L2, D, iD;
+  int sh0, shp;  // log2(n0), log2(n0·n1) when both are powers of two and the plane has ≤ 1024 cells, else −1 (see each_cell)
   // cell index → (i, j, k) with two multiply-high divisions
   __device__ __forceinline__ void ijk(int c, int& i, int& j, int& k) const {
     const int row = (int)__umulhi((unsigned)c, m0);
     i = c - row * n0;
     k = (int)__umulhi((unsigned)row, m1);
     j = row - k * n1;
+  }
+  // body(c, i, j, k) for the cells of the level this thread owns.  Power-of-two planes of ≤ 1024 cells: a thread keeps its (i, j) and
+  // walks k — the index arithmetic and the x / y neighbour wraps are loop invariants; otherwise cells are dealt out linearly.
+  template <class F>
+  __device__ __forceinline__ void each_cell(int tid, F body) const {
+    if (shp >= 0) {
+      const int c0 = tid & ((1 << shp) - 1), i = c0 & (n0 - 1), j = c0 >> sh0;
+      const int kstep = 1024 >> shp;
+      for (int k = tid >> shp; k < n2; k += kstep) body(c0 + (k << shp), i, j, k);
+    } else {
+      for (int c = tid; c < cells; c += 1024) {
+        int i, j, k;
+        ijk(c, i, j, k);
+        body(c, i, j, k);
+      }
+    }
+  }
+  // the same over the cells of one colour: body(c, i, j, k) with i + j + k ≡ par (mod 2)
+  template <class F>
+  __device__ __forceinline__ void each_half(int tid, int par, F body) const {
+    const int h0 = n0 >> 1, s1 = n0, s2 = n0 * n1;
+    if (shp >= 1) {
+      const int hp = shp - 1;  // log2 of a half plane
+      const int q0 = tid & ((1 << hp) - 1), ih = q0 & (h0 - 1), j = q0 >> (sh0 - 1);
+      const int kstep = 1024 >> hp;
+      for (int k = tid >> hp; k < n2; k += kstep) {
+        const int i = 2 * ih + ((par + j + k) & 1);
+        body(i + s1 * j + s2 * k, i, j, k);
+      }
+    } else {
+      for (int q = tid; q < (cells >> 1); q += 1024) {
+        const int row = h0 == 1 ? q : (int)__umulhi((unsigned)q, mh), ih = q - row * h0;
+        const int k = n1 == 1 ? row : (int)__umulhi((unsigned)row, m1), j = row - k * n1;
+        const int i = 2 * ih + ((par + j + k) & 1);
+        body(i + s1 * j + s2 * k, i, j, k);
+      }
+    }
   }
 };
 __host__ __device__ inline unsigned tiny_magic(int n) { return n <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n); }
@@ -1543,13 +1581,9 @@ __device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero
   const int s1 = l.n0, s2 = l.n0 * l.n1;
   for (int c = tid; c < l.cells; c += 1024) l.E[c] = l.R[c] * l.iD;
   __syncthreads();
-  const int h0 = l.n0 >> 1;
   for (int k0 = 1; k0 <= 4; k0++) {
-    for (int q = tid; q < (l.cells >> 1); q += 1024) {
-      const int row = h0 == 1 ? q : (int)__umulhi((unsigned)q, l.mh), ih = q - row * h0;
-      const int k = l.n1 == 1 ? row : (int)__umulhi((unsigned)row, l.m1), j = row - k * l.n1;
-      const int i = 2 * ih + ((1 + k0 + j + k) & 1);  // Σ(1-based indices) ≡ 1+k₀ (mod 2)  ⇔  i+j+k ≡ 1+k₀
-      const int c = i + s1 * j + s2 * k;
+    // Σ(1-based indices) ≡ 1+k₀ (mod 2)  ⇔  i+j+k ≡ 1+k₀
+    l.each_half(tid, 1 + k0, [&](int c, int i, int j, int k) {
       float s = l.R[c];
       // across a periodic face the sweep sees the stale ϵ⁰ = r·iD of the wrapped cell (perBC! runs once, before the sweeps)
       const float xlo = i == 0 ? l.R[c + (l.n0 - 1)] * l.iD : l.E[c - 1], xhi = i == l.n0 - 1 ? l.R[c - (l.n0 - 1)] * l.iD : l.E[c + 1];
@@ -1559,12 +1593,10 @@ __device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero
       const float zlo = k == 0 ? l.R[c + s2 * (l.n2 - 1)] * l.iD : l.E[c - s2], zhi = k == l.n2 - 1 ? l.R[c - s2 * (l.n2 - 1)] * l.iD : l.E[c + s2];
       s -= zlo * l.L2 + zhi * l.L2;
       l.E[c] = s * l.iD;
-    }
+    });
     __syncthreads();
   }
-  for (int c = tid; c < l.cells; c += 1024) {
-    int i, j, k;
-    l.ijk(c, i, j, k);
+  l.each_cell(tid, [&](int c, int i, int j, int k) {
     const float e = l.E[c];
     float Ae = e * l.D;
     Ae += l.E[c - i + tiny_wrap(i - 1, l.n0)] * l.L0 + l.E[c - i + tiny_wrap(i + 1, l.n0)] * l.L0;
@@ -1572,7 +1604,7 @@ __device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero
     Ae += l.E[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.L2 + l.E[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.L2;
     l.R[c] = l.R[c] - w * Ae;
     l.X[c] = x_is_zero ? w * e : l.X[c] + w * e;
-  }
+  });
   __syncthreads();
 }
 
@@ -1590,6 +1622,10 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
       l.cells = l.n0 * l.n1 * l.n2;
       l.m0 = tiny_magic(l.n0), l.m1 = tiny_magic(l.n1), l.mh = tiny_magic(l.n0 >> 1);
       l.L0 = a.L[q][0], l.L1 = a.L[q][1], l.L2 = a.L[q][2], l.D = a.D[q], l.iD = a.iD[q];
+      const int plane = l.n0 * l.n1;
+      const bool pow2 = (l.n0 & (l.n0 - 1)) == 0 && (l.n1 & (l.n1 - 1)) == 0 && plane <= 1024 && l.n0 >= 2;
+      l.sh0 = pow2 ? 31 - __clz(l.n0) : -1;
+      l.shp = pow2 ? 31 - __clz(plane) : -1;
       l.X = p, l.R = p + l.cells, l.E = p + 2 * l.cells;
       p += 3 * l.cells;
     }
@@ -1598,11 +1634,7 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
   const float w = *a.wp;
   {  // r of level T from global memory
     const TinyLvl l = lv[0];
-    for (int c = tid; c < l.cells; c += 1024) {
-      int i, j, k;
-      l.ijk(c, i, j, k);
-      l.R[c] = a.r0[(i64)(a.g0.xo + i + 1) + a.g0.s[1] * (j + 1) + a.g0.s[2] * (k + 1)];
-    }
+    l.each_cell(tid, [&](int c, int i, int j, int k) { l.R[c] = a.r0[(i64)(a.g0.xo + i + 1) + a.g0.s[1] * (j + 1) + a.g0.s[2] * (k + 1)]; });
   }
   __syncthreads();
   // ---- down-stroke: Jacobi! (x = ϵ: the level starts from x = 0) and restrict! ----
@@ -1610,9 +1642,7 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
   for (int q = 0; q < a.nlev - 1; q++) {
     TinyLvl l = lv[q];
     const int s1 = l.n0, s2 = l.n0 * l.n1;
-    for (int c = tid; c < l.cells; c += 1024) {
-      int i, j, k;
-      l.ijk(c, i, j, k);
+    l.each_cell(tid, [&](int c, int i, int j, int k) {
       const float e = l.R[c] * l.iD;
       float s = e * l.D;
       s += (l.R[c - i + tiny_wrap(i - 1, l.n0)] * l.iD) * l.L0 + (l.R[c - i + tiny_wrap(i + 1, l.n0)] * l.iD) * l.L0;
@@ -1620,7 +1650,7 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
       s += (l.R[c + s2 * (tiny_wrap(k - 1, l.n2) - k)] * l.iD) * l.L2 + (l.R[c + s2 * (tiny_wrap(k + 1, l.n2) - k)] * l.iD) * l.L2;
       l.E[c] = l.R[c] - 1.f * s;
       l.X[c] = e;
-    }
+    });
     __syncthreads();
     {  // the new residual is in E: swap the roles (Jacobi! writes r out of place), also in the table the up-stroke reads
       float* t = l.R;
@@ -1632,15 +1662,13 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
       }
     }
     const TinyLvl cl = lv[q + 1];
-    for (int c = tid; c < cl.cells; c += 1024) {
-      int i, j, k;
-      cl.ijk(c, i, j, k);
+    cl.each_cell(tid, [&](int c, int i, int j, int k) {
       float s = 0.f;
       for (int kk = 2 * k; kk <= 2 * k + 1; kk++)
         for (int jj = 2 * j; jj <= 2 * j + 1; jj++)
           for (int ii = 2 * i; ii <= 2 * i + 1; ii++) s += l.R[ii + s1 * jj + s2 * kk];
       cl.R[c] = s;
-    }
+    });
     __syncthreads();
   }
   // ---- coarsest level: smooth! from x = 0; then the up-stroke: prolongate! + increment!, smooth! ----
@@ -1651,9 +1679,7 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
     if (!coarsest) {
       const TinyLvl cl = lv[q + 1];
       const int s2 = l.n0 * l.n1, c1 = cl.n0, c2 = cl.n0 * cl.n1;
-      for (int c = tid; c < l.cells; c += 1024) {
-        int i, j, k;
-        l.ijk(c, i, j, k);
+      l.each_cell(tid, [&](int c, int i, int j, int k) {
         // ϵ[J] = x_c[down(J)] on the periodic image of J
         auto ec = [&](int ii, int jj, int kk) -> float {
           return cl.X[(tiny_wrap(ii, l.n0) >> 1) + c1 * (tiny_wrap(jj, l.n1) >> 1) + c2 * (tiny_wrap(kk, l.n2) >> 1)];
@@ -1665,19 +1691,17 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
         s += ec(i, j, k - 1) * l.L2 + ec(i, j, k + 1) * l.L2;
         l.R[c] = l.R[c] - w * s;
         l.X[c] = l.X[c] + w * e;
-      }
+      });
       __syncthreads();
     }
     tiny_gs(l, w, coarsest ? 1 : 0, tid);
   }
   {  // x (and r) of level T back to global memory
     const TinyLvl l = lv[0];
-    for (int c = tid; c < l.cells; c += 1024) {
-      int i, j, k;
-      l.ijk(c, i, j, k);
+    l.each_cell(tid, [&](int c, int i, int j, int k) {
       const i64 o = (i64)(a.g0.xo + i + 1) + a.g0.s[1] * (j + 1) + a.g0.s[2] * (k + 1);
       a.x0[o] = l.X[c];
       a.r0out[o] = l.R[c];
-    }
+    });
   }
 }
