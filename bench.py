@@ -350,7 +350,7 @@ def main():
             "config": {"workload": args.workload, "dims": list(case["dims"]), "periodic": list(case["perdir"]), "body": bool(case["body"]),
                        "poisson_iters_per_step": round(n_v, 3), "l2_flush": "state (%.1f GB) exceeds L2" % (padded * 32 * 4 / 1e9),
                        "kernels": "uniform-coefficient march kernels" if uni else "general variable-coefficient (semi-uniform blocks away from the body)",
-                       "parallelism": "single GPU" if world == 1 else "z-slab x%d (NCCL halo planes + all-reduce; coarse levels replicated)" % world},
+                       "parallelism": "single GPU" if world == 1 else "z-slab x%d (halo planes, all-reduce and coarse-level all-gather over NVLink peer memory; NCCL for set-up; coarse levels replicated)" % world},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "kernel_times": ksum}
 
     # ---- end to end through the host API: host u0 → Simulation → K × sim_step (+Δt readback) → u,p to host ----

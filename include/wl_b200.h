@@ -84,6 +84,9 @@ int wl_device_count(void);
  * solver like pois_ctor(flow) (src/WaterLily.jl:105; MultiLevelPoisson ctor src/MultiLevelPoisson.jl:68-76). */
 int wl_create(const wl_config* cfg, wl_handle** out);
 int wl_destroy(wl_handle* h);
+/* The device memory of destroyed handles is kept for the next handle of the process (same device, same chunk sizes), so that a second
+ * Simulation of the same shape starts without the cudaFree + cudaMalloc of the whole state; this returns it to the driver. */
+int wl_release_pool(void);
 
 /* Multi-GPU (new functionality; the reference has none, README.md:155): the domain is decomposed into z slabs, one process per
  * GPU.  Rank 0 obtains a 128-byte NCCL id with wl_dist_unique_id and the host broadcasts it (torch.distributed, MPI, …); every

@@ -89,9 +89,18 @@ function sync_histories!(a::B200Flow, b::B200Poisson)
     resize!(b.n, len[]); check(ccall((:wl_get_iters, lib), Cint, (Ptr{Cvoid}, Ptr{Int16}, Ref{Cint}), a.h, b.n, len))
 end
 
-"mom_step!(a,b) (src/Flow.jl:156-167).  `udf` is a host closure and is rejected."
-function mom_step!(a::B200Flow, b::B200Poisson; udf=nothing, kwargs...)
-    isnothing(udf) || error("B200WaterLily: udf is not supported (host closure)")
+"""mom_step!(a,b;udf,kwargs...) (src/Flow.jl:156-167).  The one udf the library has built in is WaterLily's own LES model,
+`sim_step!(sim; udf=sgs!, νₜ=smagorinsky, S, Cs, Δ)` (src/util.jl:46-76): `wl_set_sgs` switches the device implementation on for the
+step (νₜ must be the docstring's Smagorinsky–Lilly function — the library evaluates exactly that; `S` is scratch the library owns).
+Any other udf is a host closure and is rejected."""
+function mom_step!(a::B200Flow, b::B200Poisson; udf=nothing, νₜ=nothing, S=nothing, Cs=0, Δ=0, kwargs...)
+    if udf === WaterLily.sgs!
+        check(ccall((:wl_set_sgs, lib), Cint, (Ptr{Cvoid}, Cfloat, Cfloat), a.h, Cs, Δ))
+    elseif isnothing(udf)
+        check(ccall((:wl_set_sgs, lib), Cint, (Ptr{Cvoid}, Cfloat, Cfloat), a.h, 0, 0))
+    else
+        error("B200WaterLily: udf is a host closure (built in: udf=sgs! with νₜ=smagorinsky)")
+    end
     check(ccall((:wl_mom_step, lib), Cint, (Ptr{Cvoid},), a.h)); sync_histories!(a, b)
 end
 
@@ -106,5 +115,29 @@ function measure!(a::B200Flow{D}, body::WaterLily.AbstractBody; t=0f0, ϵ=1) whe
 end
 time(a::B200Flow) = sum(@view(a.Δt[1:end-1]))
 CFL(a::B200Flow) = (v = Ref{Float32}(); check(ccall((:wl_cfl, lib), Cint, (Ptr{Cvoid}, Ref{Float32}), a.h, v)); v[])
+
+# ---- device-side versions of the user-facing helpers around the step (SURVEY.md §8f); each is one ccall ------------------------
+struct WLBodyPrim          # struct wl_body_prim: AutoBody(sphere | x-axis torus, (x,t) -> x .- vel.*t), combined by ∪ ∩ −
+    kind::Int32; op::Int32; center::NTuple{3,Float32}; R::Float32; r::Float32; vel::NTuple{3,Float32}
+end
+"Registers a parametrised body; measure!(sim) and sim_step!(sim; remeasure=true) then run on the device (src/Body.jl:28-51)."
+set_body!(a::B200Flow, prims::Vector{WLBodyPrim}; ϵ=1) =
+    check(ccall((:wl_set_body, lib), Cint, (Ptr{Cvoid}, Ptr{WLBodyPrim}, Cint, Cfloat), a.h, prims, length(prims), ϵ))
+measure_device!(a::B200Flow; t) = check(ccall((:wl_measure, lib), Cint, (Ptr{Cvoid}, Cfloat), a.h, t))
+remeasure!(a::B200Flow, on::Bool) = check(ccall((:wl_set_remeasure, lib), Cint, (Ptr{Cvoid}, Cint), a.h, on))
+"pressure_force, viscous_force, pressure_moment(x₀), viscous_moment(x₀) of the registered body (src/Metrics.jl:111-190): 4×3 Float64."
+function body_forces(a::B200Flow; x₀=(0f0, 0f0, 0f0))
+    out = zeros(Float64, 12); x = Float32[x₀...]
+    check(ccall((:wl_body_forces, lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float64}), a.h, x, out)); reshape(out, 3, 4)
+end
+"MeanFlow on the device (src/Metrics.jl:205-257): init / update! / reset! / copy!(flow, meanflow)."
+meanflow_init!(a::B200Flow; uu_stats=false) = check(ccall((:wl_meanflow_init, lib), Cint, (Ptr{Cvoid}, Cint), a.h, uu_stats))
+meanflow_update!(a::B200Flow) = check(ccall((:wl_meanflow_update, lib), Cint, (Ptr{Cvoid},), a.h))
+meanflow_reset!(a::B200Flow; t_init=0f0) = check(ccall((:wl_meanflow_reset, lib), Cint, (Ptr{Cvoid}, Cfloat), a.h, t_init))
+meanflow_copy!(a::B200Flow) = check(ccall((:wl_meanflow_copy_to_flow, lib), Cint, (Ptr{Cvoid},), a.h))
+"Enumerated forcings in place of the closures g(i,x,t), uBC(i,x,t) (src/Flow.jl:64-73): g = g0 + g1·t, U = uBC + U1·t + ½U2·t²."
+set_forcing!(a::B200Flow; g0=zeros(Float32, 3), g1=zeros(Float32, 3), U1=zeros(Float32, 3), U2=zeros(Float32, 3)) =
+    check(ccall((:wl_set_forcing, lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), a.h,
+                Float32.(g0), Float32.(g1), Float32.(U1), Float32.(U2)))
 
 end # module

@@ -74,6 +74,7 @@ def load_library(fmad=False):
     sig = {
         "wl_create": [C.POINTER(Config), C.POINTER(H)],
         "wl_destroy": [H],
+        "wl_release_pool": [],
         "wl_upload": [H, C.c_int, C.c_void_p, C.c_int],
         "wl_download": [H, C.c_int, C.c_void_p, C.c_int],
         "wl_upload_component": [H, C.c_int, C.c_int, C.c_void_p, C.c_int],
