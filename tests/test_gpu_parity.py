@@ -789,3 +789,28 @@ def test_sgs_udf_matches_oracle(name):
     assert np.array_equal(s.flow.u, o.field("u"))
     with pytest.raises(wl.WLError):
         wl.sim_step(s, udf=lambda flow, t: None)
+
+
+def test_large_host_transfers_round_trip():
+    """Fields of ≥ 64 MB per component take the pinned-ring path between the device and ordinary (pageable) host memory
+    (copy_in / copy_out, wl_b200.cu): a 256³ velocity and pressure field must survive upload → download bit for bit, from pageable and
+    from pinned host memory, and a second handle (memory from the chunk pool of the first) must start from clean state."""
+    import torch
+    import wl_b200 as wl
+    dims = (256, 256, 256)
+    rng = np.random.default_rng(11)
+    shape = (3,) + tuple(d + 2 for d in reversed(dims))
+    a = rng.standard_normal(shape, dtype=np.float32)
+    fl = wl.Flow(dims, (0.0, 0.0, 0.0), perdir=(1, 2, 3))
+    fl.upload("u0", a)                                   # pageable source → ring
+    assert np.array_equal(fl.u0, a)                      # pageable destination → ring
+    pinned = torch.from_numpy(a[0].copy()).pin_memory().numpy()
+    fl.upload("sigma", pinned)                           # pinned source → direct DMA
+    assert np.array_equal(fl.σ, a[0])
+    for i in range(3):
+        fl.upload_component("u0", i, a[2 - i])
+    assert np.array_equal(fl.u0, a[::-1])
+    fl.close()
+    fl2 = wl.Flow(dims, (0.0, 0.0, 0.0), perdir=(1, 2, 3))  # chunks come back from the pool: everything is zeroed again
+    assert not fl2.σ.any() and not fl2.f.any()
+    fl2.close()
