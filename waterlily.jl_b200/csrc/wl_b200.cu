@@ -18,6 +18,7 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
 #include <sys/mman.h>
 #include <thread>
 #include "../../include/wl_b200.h"
@@ -27,6 +28,12 @@
 #include "wl_vsmooth.cuh"
 
 // ---------------------------------------------------------------------------------------
+// NVTX ranges around the phases of a step (mom_step!, predictor, projection, V-cycle, corrector): header-only NVTX3 — a no-op costing
+// a few nanoseconds unless a tool (nsys, ncu --nvtx) has injected itself.
+struct Nvtx {
+  explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
 static thread_local std::string g_err;
 static int fail(const char* fmt, ...) {
   char buf[1024];
@@ -1494,6 +1501,7 @@ static int solve_after_residual(wl_handle* h, float r2, int* iters_out) {
     float w = 1.f;
     log_row(h, np, rinf, r2, w);
     while (np < h->itmx) {
+      Nvtx rv("Vcycle! + smooth!");
       set_scalar(h, 0, w);
       if (vs_fusable(h, 0)) {
         TRY(vcycle(h, 0, h->d_scal + 0, true));
@@ -1679,6 +1687,7 @@ static void cfl(wl_handle* h, float* dt_out) {
 // `dt_cfl`: (corrector) the caller wants push!(Δt, CFL(a)) right after this projection: in uniform mode the correction kernel
 // computes it on the way (f_correct_cfl) and *cfl_done is set
 static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_done = nullptr) {
+  Nvtx rg(w == 1.f ? "mom_project!(w=1)" : "mom_project!(w=0.5)");
   float r2;
   TRY(residual(h, 1, w, &r2));
   TRY(solve_after_residual(h, r2, nullptr));
@@ -1764,6 +1773,7 @@ static int time_sum(wl_handle* h, bool all, double* t) {
   return 0;
 }
 static int mom_step(wl_handle* h) {
+  Nvtx rg("mom_step!");
   TRY(ensure_hierarchy(h));
   TRY(ensure_dt_capacity(h, h->dt_dev_len + 1));
   float t0 = 0.f, t1 = 0.f;
@@ -1785,14 +1795,20 @@ static int mom_step(wl_handle* h) {
   std::swap(h->u, h->u0);  // u⁰ .= u ; the new u is rebuilt from scratch below (scale_u!(a,0))
   // predictor  src/Flow.jl:190-196
   stage_force(t0);
-  TRY(momentum(h, 0));
+  {
+    Nvtx r1("mom_predict! (conv_diff!, BDIM!)");
+    TRY(momentum(h, 0));
+  }
   step_bc(h, h->u0);
   if (h->cfg.exitBC) TRY(launch_exitbc(h, h->u, h->u0, 1.f));
   TRY(lazy_bc(h) ? exch_uz_up(h, h->u) : exch_u(h, h->u));
   TRY(project(h, 1.f));
   // corrector  src/Flow.jl:205-210
   stage_force(t1);
-  TRY(momentum(h, 1));
+  {
+    Nvtx r2("mom_correct! (conv_diff!, BDIM!)");
+    TRY(momentum(h, 1));
+  }
   step_bc(h, h->u);
   TRY(lazy_bc(h) ? exch_uz_up(h, h->u) : exch_u(h, h->u));
   bool cfl_done = false;
