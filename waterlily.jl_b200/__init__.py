@@ -5,7 +5,7 @@ The directory name contains a dot, so import it through the root-level shim:  `i
 Everything that computes runs in hand-written sm_100a kernels; there is no CPU fallback and this
 package never touches oracle/.
 """
-from .lib import load_library, build_library, WLError, library_path  # noqa: F401
+from .lib import load_library, build_library, WLError, library_path, release_pool  # noqa: F401
 from .body import AutoBody, NoBody, Sphere, Torus, measure_body, mu0_kernel, mu1_kernel  # noqa: F401
 from .flow import Flow, MultiLevelPoisson, Poisson, mom_step, quick, cds, vanLeer, loc_grid, dist_unique_id, Forcing, TimeBC, sgs, smagorinsky  # noqa: F401
 from .simulation import Simulation, sim_step, sim_time, measure, sim_info  # noqa: F401

@@ -144,3 +144,8 @@ FLAGS = {"general_coeff": 1, "unfused_gs": 2, "no_persistent": 4, "nccl_halo": 8
 def check(L, rc):
     if rc != 0:
         raise WLError(L.wl_last_error().decode())
+
+
+def release_pool(fmad=False):
+    """Returns the device memory pooled from closed simulations to the driver (wl_release_pool)."""
+    load_library(fmad).wl_release_pool()
