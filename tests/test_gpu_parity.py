@@ -814,3 +814,29 @@ def test_large_host_transfers_round_trip():
     fl2 = wl.Flow(dims, (0.0, 0.0, 0.0), perdir=(1, 2, 3))  # chunks come back from the pool: everything is zeroed again
     assert not fl2.σ.any() and not fl2.f.any()
     fl2.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["sphere_walls", "torus_periodic_y", "tgv_general_coeff"])
+def test_tiny_level_kernels_equal_the_cooperative_kernel(case):
+    """The one-block shared-memory kernels for the innermost multigrid levels (k_tiny_gen with bodies / walls / semi-coarsened
+    levels, k_tiny_uni in uniform mode) against the same levels run inside k_small_levels (WL_FLAG_NO_TINY), and the host reading
+    the residual norms from the mapped mirror against copy + synchronise (WL_FLAG_NO_FAST_READ): bit for bit over 8 steps."""
+    import wl_b200 as wl
+    outs = []
+    for flags in (0, wl.lib.FLAGS["no_tiny"] | wl.lib.FLAGS["no_fast_read"]):
+        if case == "sphere_walls":
+            s = wl.Simulation((128, 64, 64), (1.0, 0.0, 0.0), 16.0, ν=0.01, body=wl.Sphere((31.0, 31.0, 31.0), 8.0), exitBC=True, flags=flags)
+        elif case == "torus_periodic_y":
+            s = wl.Simulation((96, 64, 32), (1.0, 0.0, 0.0), 16.0, ν=0.02, perdir=(2,), body=wl.Torus((30.0, 32.0, 16.0), 9.0, 3.0), flags=flags)
+        else:
+            n = 64
+            u0 = tgv3d_u0((n + 2,) * 3, n)
+            s = wl.Simulation((n,) * 3, (0.0, 0.0, 0.0), float(n), ν=0.001, perdir=(1, 2, 3), u0=lambda i, x: u0[i],
+                              flags=flags | wl.lib.FLAGS["general_coeff"])
+        wl.lib.check(s.flow.L, s.flow.L.wl_sim_step_n(s.flow.h, 8))
+        outs.append((s.flow.u.copy(), s.flow.p.copy(), list(s.pois.n), np.asarray(s.flow.Δt).copy()))
+        s.close()
+    a, b = outs
+    assert a[2] == b[2] and np.array_equal(a[3], b[3])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

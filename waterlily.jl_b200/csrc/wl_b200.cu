@@ -295,6 +295,13 @@ struct wl_handle {
   // first (update!(pois), src/MultiLevelPoisson.jl:79-86), so a host that forgets wl_update cannot step with stale D/iD/coarse L
   bool pois_dirty = false;
   bool tiny_on = true;     // uniform mode: levels ≤ 8192 cells on one block in shared memory (k_tiny_uni); WL_FLAG_NO_TINY: all in k_small_levels
+  // general mode: levels ≥ tg_from run in k_tiny_gen (one block, dense copies in shared memory); its operation list and arguments
+  // are built once (the levels' arrays do not move: nothing outside that kernel swaps r/r2 of those levels)
+  int tg_from = 0;
+  bool tg_ready = false, attr_tg = false;
+  SmallOp* d_tgops = nullptr;
+  int tg_nops = 0;
+  TinyGenArgs tg_args;
   int tiny_from = 0;       // first level k_tiny_uni can take (0 = none): fully coarsened chain of 3-D periodic levels of ≤ 8192 cells
   bool attr_tiny = false;
   bool semi_on = true;     // general mode: semi-uniform march blocks (WL_SEMI=0: always read L)
@@ -1358,13 +1365,101 @@ static int launch_tiny(wl_handle* h, const float* wp) {
   h->launches++;
   return 0;
 }
+static void emit_vcycle(wl_handle* h, size_t li, int tiny, int* split);
+// k_tiny_gen's operation list: the list k_small_levels would run for "Vcycle!(ml; l=T); smooth!(levels[T])", emitted over shadow
+// copies of the levels ≥ T whose Grid is dense and whose pointers are arena offsets (encoded (offset+1)·4, tinyg_fix).
+static int build_tinyg(wl_handle* h) {
+  const size_t T = (size_t)h->tg_from, nl = h->levels.size();
+  TinyGenArgs& a = h->tg_args;
+  memset(&a, 0, sizeof a);
+  a.nlev = (int)(nl - T);
+  std::vector<Level> real(h->levels.begin() + T, h->levels.end());
+  auto enc = [](size_t off) { return reinterpret_cast<float*>((uintptr_t)(off + 1) * 4); };
+  size_t off = 0;
+  for (size_t q = T; q < nl; q++) {
+    Level& l = h->levels[q];
+    const size_t n = (size_t)l.g.N[0] * l.g.N[1] * l.g.N[2];
+    TinyGenLvl& t = a.lv[q - T];
+    t.g = l.g;
+    t.L = l.L;
+    t.Dg = l.Dg;
+    t.iD = l.iD;
+    t.off = (int)off;
+    t.cells = (int)n;
+    t.x = l.x;
+    t.r = l.r;
+    Grid d = l.g;  // dense: no pitch, no offset
+    d.xo = 0;
+    d.px = l.g.N[0];
+    d.s[0] = 1;
+    d.s[1] = l.g.N[0];
+    d.s[2] = (i64)l.g.N[0] * l.g.N[1];
+    d.sc = (i64)n;
+    l.g = d;
+    l.L = enc(off);
+    l.Dg = enc(off + 3 * n);
+    l.iD = enc(off + 4 * n);
+    l.x = enc(off + 5 * n);
+    l.eps = enc(off + 6 * n);
+    l.r = enc(off + 7 * n);
+    l.r2 = enc(off + 8 * n);
+    l.z = nullptr;
+    l.fast = false;
+    l.semi = nullptr;
+    off += 9 * n;
+  }
+  a.arena_floats = (int)off;
+  a.r0 = real[0].r;
+  a.r_in_off = a.lv[0].off + 7 * a.lv[0].cells;
+  std::vector<SmallOp> saved;
+  saved.swap(h->ops);
+  int split = -1;
+  const bool last = (T + 1 >= nl);
+  if (!last) emit_vcycle(h, T, 0, &split);
+  emit_gs(h, h->levels[T], last ? 1 : 0);
+  // where every level's residual ended up (Jacobi! writes it out of place and the roles swap)
+  for (size_t q = T; q < nl; q++) a.lv[q - T].r_out_off = (int)(((uintptr_t)h->levels[q].r >> 2) - 1);
+  std::vector<SmallOp> ops;
+  ops.swap(h->ops);
+  h->ops.swap(saved);
+  for (size_t q = T; q < nl; q++) h->levels[q] = real[q - T];
+  for (const SmallOp& o : ops)
+    if (o.type < OP_K_JACOBI) return fail("k_tiny_gen: unexpected march operation in the list");
+  h->tg_nops = (int)ops.size();
+  if (!h->d_tgops) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, 256 * sizeof(SmallOp)));
+    h->d_tgops = (SmallOp*)q;
+    h->allocs.push_back(q);
+  }
+  if (h->tg_nops > 256) return fail("too many tiny-level operations (%d)", h->tg_nops);
+  CK(cudaMemcpyAsync(h->d_tgops, ops.data(), ops.size() * sizeof(SmallOp), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));  // (ops is a local)
+  h->tg_ready = true;
+  return 0;
+}
+static int launch_tinyg(wl_handle* h, const float* wp) {
+  if (!h->tg_ready) TRY(build_tinyg(h));
+  const size_t bytes = (size_t)((h->tg_args.arena_floats + 3) & ~3) * sizeof(float) + (size_t)h->tg_nops * sizeof(SmallOp);
+  if (bytes > (size_t)220 * 1024) return fail("k_tiny_gen: %zu bytes of shared memory", bytes);
+  if (!h->attr_tg) {
+    CK(cudaFuncSetAttribute(k_tiny_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    h->attr_tg = true;
+  }
+  prof_begin(h, "k_tiny_gen");
+  k_tiny_gen<<<1, dim3(16, 8, 8), bytes, h->st>>>(h->d_tgops, h->tg_nops, wp, h->tg_args);
+  prof_end(h);
+  h->launches++;
+  return 0;
+}
 // Runs "Vcycle!(ml; l=small_from) ; smooth!(levels[small_from])" — everything a V-cycle does at and below level small_from:
 // the levels ≥ small_from in the cooperative k_small_levels, except (uniform mode) the innermost levels ≥ tiny_from, which
 // k_tiny_uni runs on one block in shared memory between the two halves of the list.
 static int run_small_levels(wl_handle* h, const float* wp) {
   const size_t ls = (size_t)h->small_from;
-  const int tiny = (h->uni && h->tiny_on) ? h->tiny_from : 0;
-  if (tiny > 0 && (size_t)tiny <= ls) return launch_tiny(h, wp);  // the whole coarse end is tiny
+  const int tiny = !h->tiny_on ? 0 : (h->uni ? h->tiny_from : h->tg_from);
+  auto run_tiny = [&]() -> int { return h->uni ? launch_tiny(h, wp) : launch_tinyg(h, wp); };
+  if (tiny > 0 && (size_t)tiny <= ls) return run_tiny();  // the whole coarse end is tiny
   h->ops.clear();
   int split = -1;
   const bool last = (ls + 1 >= h->levels.size());
@@ -1388,7 +1483,7 @@ static int run_small_levels(wl_handle* h, const float* wp) {
   };
   if (split < 0) return coop(0, nops);
   TRY(coop(0, split));
-  TRY(launch_tiny(h, wp));
+  TRY(run_tiny());
   return coop(split, nops - split);
 }
 
@@ -2152,6 +2247,17 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
         };
         while (t - 1 >= h->small_from && t - 1 >= 1 && nl - (t - 1) <= TINY_MAXLEV && ok(t - 1) && (t == nl || h->levels[t].fullc)) t--;
         h->tiny_from = t < nl ? t : 0;
+        // general mode: the innermost levels whose nine arrays (ghost cells included) fit the shared-memory arena together
+        int tg = nl;
+        size_t fl = 0;
+        while (tg - 1 >= h->small_from && tg - 1 >= 1 && nl - (tg - 1) <= TINYG_MAXLEV && !h->levels[tg - 1].slab) {
+          const Level& l = h->levels[tg - 1];
+          const size_t n = (size_t)l.g.N[0] * l.g.N[1] * l.g.N[2];
+          if ((fl + 9 * n) * sizeof(float) > (size_t)176 * 1024) break;  // (the operation list, ≤ 64 × sizeof(SmallOp), follows the arena)
+          fl += 9 * n;
+          tg--;
+        }
+        h->tg_from = tg < nl ? tg : 0;
       }
       if (h->small_from > 0) {
         int dev = 0, nsm = 0, coop = 0, per_sm = 0;

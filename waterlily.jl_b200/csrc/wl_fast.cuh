@@ -1705,3 +1705,128 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
     });
   }
 }
+
+// ================================================================================================
+// k_tiny_gen — the innermost levels of the V-cycle in GENERAL mode (bodies, walls, semi-coarsened levels) on ONE block in shared
+// memory: the counterpart of k_tiny_uni for variable coefficients.  The levels' arrays (L, D, iD, x, ϵ, r, r2; ghost cells
+// included) live in a shared-memory arena as dense copies; the operations are the SAME SmallOp list k_small_levels would run, with
+// the general one-thread-per-cell bodies (b_k_jacobi, b_k_restrict, b_k_gs_init, b_k_gs_sweep, b_k_increment, b_k_prolong_inc —
+// identical arithmetic, identical bits), whose Grid and pointers the host has redirected to the dense copies (pointers are arena
+// offsets, encoded (offset+1)·4), separated by block barriers instead of grid barriers (≈ 0.3 µs instead of ≈ 4.4 µs per operation:
+// the sphere wake's coarse end is 63 operations per V-cycle, 36 of them on levels of ≤ 1 800 cells).
+// ================================================================================================
+#define TINYG_MAXLEV 8
+struct TinyGenLvl {
+  Grid g;        // the level's layout in global memory
+  const float* L;   // D components
+  const float* Dg;
+  const float* iD;
+  int off;       // arena offset (floats) of the level's 9 dense arrays: L0 L1 L2 Dg iD x eps r r2
+  int cells;     // N0·N1·N2
+  float* x;      // the level's x and r in global memory: written back at the end (level T: the result; deeper levels: for observers)
+  float* r;
+  int r_out_off; // arena offset of the level's residual at exit (Jacobi! writes it out of place and the roles swap)
+};
+struct TinyGenArgs {
+  int nlev;
+  TinyGenLvl lv[TINYG_MAXLEV];
+  const float* r0;  // residual of the first tiny level in global memory (input)
+  float* x0;        // its solution (output)
+  float* r0out;     // its residual after the smoother (output)
+  int r_in_off;      // arena offset of level T's r at entry
+  int arena_floats;  // the operation list follows the arena in shared memory (16-byte aligned)
+};
+__device__ __forceinline__ float* tinyg_fix(float* arena, const float* p) {
+  return p ? arena + ((reinterpret_cast<uintptr_t>(p) >> 2) - 1) : nullptr;
+}
+__global__ void __launch_bounds__(1024, 1) k_tiny_gen(const SmallOp* __restrict__ ops, int nops, const float* wp, const __grid_constant__ TinyGenArgs a) {
+  extern __shared__ float tinyg_arena[];
+  float* const arena = tinyg_arena;
+  SmallOp* const sops = reinterpret_cast<SmallOp*>(arena + ((a.arena_floats + 3) & ~3));
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  for (int q = tid; q < a.arena_floats; q += 1024) arena[q] = 0.f;
+  {  // the whole operation list into shared memory once (a descriptor fetched from global memory per operation was ≈ 1 µs each)
+    const int* src = reinterpret_cast<const int*>(ops);
+    int* dst = reinterpret_cast<int*>(sops);
+    for (int q = tid; q < nops * (int)(sizeof(SmallOp) / sizeof(int)); q += 1024) dst[q] = src[q];
+  }
+  __syncthreads();
+  // coefficients of every tiny level and r of the first one: dense copies, ghost cells included
+  for (int l = 0; l < a.nlev; l++) {
+    const TinyGenLvl& t = a.lv[l];
+    const int N0 = t.g.N[0], N01 = t.g.N[0] * t.g.N[1];
+    for (int c = tid; c < t.cells; c += 1024) {
+      const int k = c / N01, rem = c - k * N01, j = rem / N0, i = rem - j * N0;
+      const i64 o = (i64)(t.g.xo + i) + t.g.s[1] * j + t.g.s[2] * k;
+      float* d = arena + t.off + c;
+      d[0] = t.L[o];
+      d[t.cells] = t.L[o + t.g.sc];
+      d[2 * t.cells] = t.L[o + 2 * t.g.sc];
+      d[3 * t.cells] = t.Dg[o];
+      d[4 * t.cells] = t.iD[o];
+      if (l == 0) arena[a.r_in_off + c] = a.r0[o];
+    }
+  }
+  RedBuf nored{nullptr, nullptr, nullptr};
+  for (int o = 0; o < nops; o++) {
+    __syncthreads();
+    const SmallOp& op = sops[o];
+    // the block is 16 × 8 × 8 threads (the first tiny level of a wake domain is 16 × 8 × 8 cells: one pass, every lane busy);
+    // threads beyond the operation's box in y or z have no cell in any virtual block and skip it (the kernel is issue-bound:
+    // on the 4 × 2 × 2 and 2 × 2 × 2 levels 28 of the 32 warps have nothing to do)
+    if ((int)threadIdx.y >= op.box.n[1] || (int)threadIdx.z >= op.box.n[2]) continue;
+    Lvl lv = op.lvl;
+    lv.L = tinyg_fix(arena, lv.L);
+    lv.Dg = tinyg_fix(arena, lv.Dg);
+    lv.iD = tinyg_fix(arena, lv.iD);
+    lv.x = tinyg_fix(arena, lv.x);
+    lv.eps = tinyg_fix(arena, lv.eps);
+    lv.r = tinyg_fix(arena, lv.r);
+    lv.r2 = tinyg_fix(arena, lv.r2);
+    lv.z = nullptr;
+    float* const other = tinyg_fix(arena, op.other);
+    const int bx = (int)blockDim.x, by = (int)blockDim.y, bz = (int)blockDim.z;
+    const int nx = op.type == OP_K_GSSWEEP ? (op.box.n[0] + 1) / 2 : op.box.n[0];  // (a half-sweep's threads own every other cell)
+    const int vg0 = (nx + bx - 1) / bx, vg1 = (op.box.n[1] + by - 1) / by, vg2 = (op.box.n[2] + bz - 1) / bz;
+    const int nvb = vg0 * vg1 * vg2;
+    for (int v = 0; v < nvb; v++) {
+      const int3 vb = make_int3(v % vg0, (v / vg0) % vg1, v / (vg0 * vg1));
+      switch (op.type) {
+        case OP_K_JACOBI:
+          b_k_jacobi<3>(lv, op.box, op.x_is_zero, vb);
+          break;
+        case OP_K_RESTRICT:
+          b_k_restrict<3>(op.gc, op.g, op.box, other, lv.r, op.cm[0], op.cm[1], op.cm[2], vb);
+          break;
+        case OP_K_GSINIT:
+          b_k_gs_init<3>(lv, op.box, vb);
+          break;
+        case OP_K_GSSWEEP:
+          b_k_gs_sweep<3>(lv, op.box, op.k0, vb);
+          break;
+        case OP_K_INC:
+          b_k_increment<3>(lv, op.box, wp, op.x_is_zero, 0, nored, 0, vb);
+          break;
+        case OP_K_PROLONG:
+          b_k_prolong_inc<3>(lv, op.gc, other, op.box, wp, op.cm[0], op.cm[1], op.cm[2], vb);
+          break;
+        default:
+          break;
+      }
+    }
+  }
+  __syncthreads();
+  // x and r of every tiny level back to global memory (interior cells): level T's are the result, the deeper ones keep the levels
+  // observable (wl_download_level)
+  for (int l = 0; l < a.nlev; l++) {
+    const TinyGenLvl& t = a.lv[l];
+    const int n0 = t.g.N[0] - 2, n1 = t.g.N[1] - 2, n2 = t.g.N[2] - 2;
+    for (int c = tid; c < n0 * n1 * n2; c += 1024) {
+      const int k = c / (n0 * n1), rem = c - k * n0 * n1, j = rem / n0, i = rem - j * n0;
+      const int cc = (i + 1) + t.g.N[0] * ((j + 1) + t.g.N[1] * (k + 1));
+      const i64 o = (i64)(t.g.xo + i + 1) + t.g.s[1] * (j + 1) + t.g.s[2] * (k + 1);
+      t.x[o] = arena[t.off + 5 * t.cells + cc];
+      t.r[o] = arena[t.r_out_off + cc];
+    }
+  }
+}
