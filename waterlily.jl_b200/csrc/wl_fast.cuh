@@ -1447,14 +1447,17 @@ __global__ void __launch_bounds__(32 * FTY, 4) k_small_levels(const SmallOp* __r
   __shared__ SmallOp op;
   const int tid = threadIdx.x + 32 * threadIdx.y;
   RedBuf nored{nullptr, nullptr, nullptr};
+  // the descriptor of the NEXT operation is fetched into a register while the current one runs (one int per thread: the global
+  // load's latency hides behind the work and the grid barrier) and stored to shared memory at the head of its own iteration
+  constexpr int NINT = (int)(sizeof(SmallOp) / sizeof(int));
+  static_assert(NINT <= 32 * FTY, "one descriptor word per thread");
+  int pre = 0;
+  if (nops > 0 && tid < NINT) pre = reinterpret_cast<const int*>(ops)[tid];
   for (int o = 0; o < nops; o++) {
     __syncthreads();
-    {  // stage the descriptor in shared memory
-      const int* src = reinterpret_cast<const int*>(ops + o);
-      int* dst = reinterpret_cast<int*>(&op);
-      for (int q = tid; q < (int)(sizeof(SmallOp) / sizeof(int)); q += 32 * FTY) dst[q] = src[q];
-    }
+    if (tid < NINT) reinterpret_cast<int*>(&op)[tid] = pre;
     __syncthreads();
+    if (o + 1 < nops && tid < NINT) pre = reinterpret_cast<const int*>(ops + o + 1)[tid];
     const int nvb = op.vg[0] * op.vg[1] * op.vg[2];
     for (int v = blockIdx.x; v < nvb; v += gridDim.x) {
       const int3 vb = make_int3(v % op.vg[0], (v / op.vg[0]) % op.vg[1], v / (op.vg[0] * op.vg[1]));
