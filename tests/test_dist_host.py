@@ -104,3 +104,14 @@ def test_python_body_kernels_match_reference_values():
     assert wl.mu0_kernel(0.0, 1.0) == 0.5
     assert wl.mu0_kernel(np.float32(np.finfo(np.float32).eps) - np.float32(1), 1.0) == 0.0
     assert abs(float(wl.mu1_kernel(0.0, 2.0)) - 2 * (1 / 4 - 1 / np.pi**2)) < 1e-7
+
+
+def test_flag_table_matches_the_header():
+    """waterlily.jl_b200/lib.py's FLAGS mirror the WL_FLAG_* bits of include/wl_b200.h (the parity tests select kernel variants by name)."""
+    import re
+    import wl_b200 as wl
+    hdr = open(os.path.join(ROOT, "include", "wl_b200.h")).read()
+    bits = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"WL_FLAG_([A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    assert bits and bits == wl.lib.FLAGS
+    vals = sorted(bits.values())
+    assert all(v & (v - 1) == 0 for v in vals) and len(set(vals)) == len(vals)  # distinct single bits
