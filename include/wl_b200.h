@@ -73,6 +73,7 @@ enum {
   WL_FLAG_NO_SEMI = 128,     /* general mode: always read the face coefficients L (no semi-uniform march blocks, no body-free BDIM blocks) */
   WL_FLAG_NO_PREFETCH = 1024, /* z slabs: push the halo of r that f_vsmooth reads right before that kernel instead of on a side stream after Jacobi! */
   WL_FLAG_NCCL_ALLREDUCE = 2048, /* z slabs: ncclAllReduce for the solver's and CFL's scalars instead of the one-warp all-reduce over peer memory */
+  WL_FLAG_NO_PDL = 4096, /* launch the uniform-mode step's kernels without programmatic dependent launch */
   WL_FLAG_NO_FAST_READ = 512, /* read the solver's residual norms with a copy + stream synchronisation instead of polling the mapped mirror the reduction writes */
 };
 

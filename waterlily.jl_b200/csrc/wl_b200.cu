@@ -245,6 +245,8 @@ struct wl_handle {
   int halo_seq2 = 0;
   bool prefetch = true;
   bool skip_ready = true;
+  bool coop_pdl = true;  // k_small_levels: cooperative launch with the PDL attribute as well (cleared if the driver refuses)
+  bool pdl = true;  // programmatic dependent launch of the uniform-mode step's kernels (WL_FLAG_NO_PDL)
   // own all-reduce of the solver's / CFL's scalars over peer memory (k_allreduce): every rank's mailbox mapped on every rank
   double* armb = nullptr;
   ArPeers ar_peers{};
@@ -371,10 +373,27 @@ static inline size_t nblocks(const Box& b, dim3 t) {
   return (size_t)g.x * g.y * g.z;
 }
 
+// Every launch of the step carries the programmatic-stream-serialization attribute, and every kernel of the library starts with
+// pdl_wait() (wl_common.cuh): kernel n+1 is scheduled into the tail of kernel n and waits there for its completion.
+template <typename... KArgs, typename... Args>
+static cudaError_t pdl_launch(wl_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 #define LAUNCH(h, kern, grid, block, ...)                \
   do {                                                   \
     prof_begin(h, #kern);                                \
-    kern<<<(grid), (block), 0, (h)->st>>>(__VA_ARGS__);  \
+    pdl_launch(h, kern, (grid), (block), 0, __VA_ARGS__); \
     prof_end(h);                                         \
     (h)->launches++;                                     \
   } while (0)
@@ -385,6 +404,14 @@ static inline size_t nblocks(const Box& b, dim3 t) {
       LAUNCH(h, kern<3>, grid, block, __VA_ARGS__);               \
     else                                                          \
       LAUNCH(h, kern<2>, grid, block, __VA_ARGS__);               \
+  } while (0)
+
+#define LAUNCH_PDL(h, kern, grid, block, smem, ...)                 \
+  do {                                                              \
+    prof_begin(h, #kern);                                           \
+    pdl_launch(h, kern, (grid), (block), (smem), __VA_ARGS__);      \
+    prof_end(h);                                                    \
+    (h)->launches++;                                                \
   } while (0)
 
 // Field memory comes from a few big chunks (bump allocation, identical on every rank), so that a neighbouring rank can address
@@ -925,7 +952,7 @@ static int update_levels(wl_handle* h) {  // update!(ml)  src/MultiLevelPoisson.
 static inline int ensure_hierarchy(wl_handle* h) { return h->pois_dirty ? update_levels(h) : 0; }
 
 static void set_scalar(wl_handle* h, int idx, float v) {
-  LAUNCH(h, k_set_scalar, 1, 1, h->d_scal + idx, v);
+  LAUNCH_PDL(h, k_set_scalar, dim3(1), dim3(1), 0, h->d_scal + idx, v);
 }
 // The reduction buffer for a launch that reduces into `slot` and whose result the host will read: tagged, so that the folding
 // thread publishes the result to the mapped mirror (`active` = the launch really reduces).
@@ -1034,7 +1061,7 @@ static int jacobi(wl_handle* h, Level& l, int x_is_zero, Level* coarse, bool* fu
     float* rc = fused ? coarse->r : nullptr;
     const int zoffc = (fused && l.slab && !coarse->slab) ? coarse->zoffc : 0;
     if (h->uni && h->divres_uni && fused && h->jacobi2)
-      LAUNCH(h, f_jacobi_uni2, l.fgrid(), dim3(32, FTY / 2), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc, x_is_zero);
+      LAUNCH_PDL(h, f_jacobi_uni2, l.fgrid(), dim3(32, FTY / 2), 0, l.g, l.coef(true), (const float*)l.r, l.r2, l.x, l.zchunk(), gc, rc, zoffc, x_is_zero);
     else if (h->uni)
       LAUNCH(h, f_jacobi<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.r, l.r2, l.x, x_is_zero, l.zchunk(), gc, rc, fused ? 1 : 0,
              zoffc);
@@ -1221,7 +1248,7 @@ static int vsmooth(wl_handle* h, size_t li, const float* wp, int with_l2) {
   }
   dim3 gr(cdiv(n0, VS_CX), cdiv(n1, cy), cdiv(n2, zc));
   prof_begin(h, "f_vsmooth");
-  vs_tab[with_l2 ? 1 : 0][f.slab ? 1 : 0][lm]<<<gr, VS_NT, VS_SMEM, h->st>>>(a, red_for(h, SLOT_R2, with_l2), SLOT_R2);
+  pdl_launch(h, vs_tab[with_l2 ? 1 : 0][f.slab ? 1 : 0][lm], gr, dim3(VS_NT), VS_SMEM, a, red_for(h, SLOT_R2, with_l2), (int)SLOT_R2);
   prof_end(h);
   h->launches++;
   std::swap(f.r, f.r2);
@@ -1360,7 +1387,7 @@ static int launch_tiny(wl_handle* h, const float* wp) {
     h->attr_tiny = true;
   }
   prof_begin(h, "k_tiny_uni");
-  k_tiny_uni<<<1, 1024, floats * sizeof(float), h->st>>>(a);
+  pdl_launch(h, k_tiny_uni, dim3(1), dim3(1024), floats * sizeof(float), a);
   prof_end(h);
   h->launches++;
   return 0;
@@ -1447,7 +1474,7 @@ static int launch_tinyg(wl_handle* h, const float* wp) {
     h->attr_tg = true;
   }
   prof_begin(h, "k_tiny_gen");
-  k_tiny_gen<<<1, dim3(16, 8, 8), bytes, h->st>>>(h->d_tgops, h->tg_nops, wp, h->tg_args);
+  pdl_launch(h, k_tiny_gen, dim3(1), dim3(16, 8, 8), bytes, (const SmallOp*)h->d_tgops, h->tg_nops, wp, h->tg_args);
   prof_end(h);
   h->launches++;
   return 0;
@@ -1474,8 +1501,28 @@ static int run_small_levels(wl_handle* h, const float* wp) {
     const SmallOp* dops = h->d_ops + first;
     void* args[] = {(void*)&dops, (void*)&n, (void*)&wp};
     prof_begin(h, "k_small_levels");
-    cudaError_t e = h->uni ? cudaLaunchCooperativeKernel((void*)k_small_levels<true>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st)
-                           : cudaLaunchCooperativeKernel((void*)k_small_levels<false>, dim3(h->small_grid), dim3(32, FTY), args, 0, h->st);
+    // cooperative + (if the driver takes the combination) programmatic dependent launch
+    auto go = [&](int nattr) -> cudaError_t {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(h->small_grid);
+      cfg.blockDim = dim3(32, FTY);
+      cfg.stream = h->st;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = nattr;
+      return h->uni ? cudaLaunchKernelEx(&cfg, k_small_levels<true>, dops, n, wp) : cudaLaunchKernelEx(&cfg, k_small_levels<false>, dops, n, wp);
+    };
+    cudaError_t e = go((h->pdl && h->coop_pdl) ? 2 : 1);
+    if (e != cudaSuccess && h->pdl && h->coop_pdl) {  // not accepted together: cooperative only, from now on
+      cudaGetLastError();
+      h->coop_pdl = false;
+      e = go(1);
+    }
     prof_end(h);
     h->launches++;
     if (e != cudaSuccess) return fail("cooperative launch of k_small_levels: %s", cudaGetErrorString(e));
@@ -1553,8 +1600,8 @@ static int residual(wl_handle* h, int with_div, float w, float* r2) {
   if (h->dist.on() && !(l.fast && with_div)) return fail("standalone residual! is not available with z-slab decomposition");
   if (l.fast && with_div) {
     if (h->uni && h->divres_uni)
-      LAUNCH(h, f_divres_uni, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, dtp(h), w, l.zchunk(),
-             red_for(h, SLOT_RSUM), SLOT_RSUM);
+      LAUNCH_PDL(h, f_divres_uni, l.fgrid(), dim3(32, FTY), 0, l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, dtp(h), w, l.zchunk(),
+                 red_for(h, SLOT_RSUM), (int)SLOT_RSUM);
     else if (h->uni)
       LAUNCH(h, f_div_residual<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)h->u, (const float*)h->p, l.x, l.r, l.z, dtp(h), w,
              l.zchunk(), red_for(h, SLOT_RSUM), SLOT_RSUM);
@@ -1642,9 +1689,9 @@ static void conv_launch(wl_handle* h, const float* ua, int mode) {
   Box all = h->levels[0].all();
   prof_begin(h, "k_conv_bdim1");
   if (h->D == 3)
-    k_conv_bdim1<3, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
+    pdl_launch(h, k_conv_bdim1<3, LAM>, grd(all, b), b, 0, g, all, ua, (const float*)h->u0, (const float*)h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
   else
-    k_conv_bdim1<2, LAM><<<grd(all, b), b, 0, h->st>>>(g, all, ua, h->u0, h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
+    pdl_launch(h, k_conv_bdim1<2, LAM>, grd(all, b), b, 0, g, all, ua, (const float*)h->u0, (const float*)h->V, h->f, h->sigma, dtp(h), h->cfg.nu, mode, h->fc);
   prof_end(h);
   h->launches++;
 }
@@ -1684,21 +1731,21 @@ static int fconv_launch(wl_handle* h, const float* ua, float* out, int corrector
     // the fast-division instance, then the IEEE-division instance on the same grid: the device-side range word picks the one that
     // runs (the other returns at once), so no host decision and no second pass over marked blocks
     prof_begin(h, "fm_conv4");
-    fm_conv4<LAM, false><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2, h->fc);
+    pdl_launch(h, fm_conv4<LAM, false>, g4, dim3(32, C4TY), C4SMEM, g, ua, (const float*)h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, (int)SLOT_PHIMAX, (const float*)h->uext, h->d_flags + 2, h->fc);
     prof_end(h);
     prof_begin(h, "fm_conv4_exact");
-    fm_conv4<LAM, true><<<g4, dim3(32, C4TY), C4SMEM, h->st>>>(g, ua, h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, SLOT_PHIMAX, h->uext, h->d_flags + 2, h->fc);
+    pdl_launch(h, fm_conv4<LAM, true>, g4, dim3(32, C4TY), C4SMEM, g, ua, (const float*)h->u0, out, dtp(h), h->cfg.nu, zc, corrector, h->red, (int)SLOT_PHIMAX, (const float*)h->uext, h->d_flags + 2, h->fc);
     prof_end(h);
     h->launches += 2;
     return 0;
   }
   prof_begin(h, "fm_conv");
   if (nowall)
-    fm_conv<LAM, FUSE, true><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                            h->red, SLOT_PHIMAX, h->uext, h->d_flags, h->fc);
+    pdl_launch(h, fm_conv<LAM, FUSE, true>, gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), g, ua, (const float*)h->u0, (const float*)h->V, out, h->sigma, dtp(h),
+               h->cfg.nu, zchunk, corrector, h->red, (int)SLOT_PHIMAX, (const float*)h->uext, h->d_flags, h->fc);
   else
-    fm_conv<LAM, FUSE, false><<<gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), h->st>>>(g, ua, h->u0, h->V, out, h->sigma, dtp(h), h->cfg.nu, zchunk, corrector,
-                                                                             h->red, SLOT_PHIMAX, h->uext, h->d_flags, h->fc);
+    pdl_launch(h, fm_conv<LAM, FUSE, false>, gr, dim3(32, CTY), sizeof(ConvTile) + 2 * 3 * CTY * 32 * sizeof(float), g, ua, (const float*)h->u0, (const float*)h->V, out, h->sigma, dtp(h),
+               h->cfg.nu, zchunk, corrector, h->red, (int)SLOT_PHIMAX, (const float*)h->uext, h->d_flags, h->fc);
   prof_end(h);
   h->launches++;
   return 0;
@@ -1791,7 +1838,7 @@ static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_don
   Box in = l.inside();
   if (l.fast && h->uni && dt_cfl && lazy_bc(h) && h->fuse_cfl) {
     const int fin = h->dist.on() ? 0 : 1;
-    LAUNCH(h, f_correct_cfl<true>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
+    LAUNCH_PDL(h, f_correct_cfl<true>, l.fgrid(), dim3(32, FTY), 0, l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
            h->cfg.nu, dt_cfl, h->red, SLOT_CFLINT, SLOT_PHIMAX, fin, h->d_flags);
     h->range_checked = true;
     std::swap(h->u, h->f);
@@ -1801,7 +1848,7 @@ static int project(wl_handle* h, float w, float* dt_cfl = nullptr, bool* cfl_don
     }
     if (cfl_done) *cfl_done = true;
   } else if (l.fast && h->uni && lazy_bc(h) && h->fuse_cfl) {  // out of place into f (free in uniform mode), then the two swap roles
-    LAUNCH(h, f_correct_cfl<false>, l.fgrid(), dim3(32, FTY), l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
+    LAUNCH_PDL(h, f_correct_cfl<false>, l.fgrid(), dim3(32, FTY), 0, l.g, l.coef(true), (const float*)l.x, (const float*)h->u, h->f, h->p, dtp(h), w, l.zchunk(),
            h->cfg.nu, (float*)nullptr, h->red, SLOT_CFLINT, SLOT_PHIMAX, 0, h->d_flags);
     h->range_checked = true;
     std::swap(h->u, h->f);
@@ -2155,6 +2202,7 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
   h->conv4 = !(cfg->flags & WL_FLAG_NO_CONV4);
   h->semi_on = !(cfg->flags & WL_FLAG_NO_SEMI);
   h->tiny_on = !(cfg->flags & WL_FLAG_NO_TINY);
+  h->pdl = !(cfg->flags & WL_FLAG_NO_PDL);
   h->fuse_cfl = h->divres_uni = h->jacobi2 = !(cfg->flags & WL_FLAG_NO_FUSED_UNI);
 
   h->itmx = cfg->itmx > 0 ? cfg->itmx : (cfg->pois_kind == WL_POIS_MULTILEVEL ? 32 : 1000);

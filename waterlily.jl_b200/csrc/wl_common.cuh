@@ -150,6 +150,17 @@ struct RangeAcc {
   }
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may be scheduled
+// while its predecessor in the stream drains; it must not touch the predecessor's results before this wait (a no-op for an
+// ordinary launch).  The uniform-mode step launches its kernels this way (pdl_launch, wl_b200.cu): the launch latency and the
+// block ramp-up of kernel n+1 overlap the tail of kernel n.
+// The trigger right behind the wait lets the NEXT kernel's blocks be scheduled as soon as every block of this one has started, i.e.
+// into the free slots of this kernel's last wave, where they sit in their own wait until this grid has completed and flushed.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- deterministic single-pass grid reduction ------------------------------------------
 // Every block reduces its values in double with a fixed shuffle tree, writes one partial
 // per value, and the last block to arrive (atomic ticket) folds all partials in a fixed

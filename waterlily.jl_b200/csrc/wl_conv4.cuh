@@ -141,6 +141,7 @@ template <int LAM, bool EXACT>
 __global__ void __launch_bounds__(32 * C4TY, 2) fm_conv4(const __grid_constant__ Grid g, const float* __restrict__ ua, const float* __restrict__ u0,
                                                          float* __restrict__ out, const float* __restrict__ dtp, float nu, int zchunk, int corrector, RedBuf R,
                                                          int slot, const float* __restrict__ uext, int* __restrict__ rflag, const Force fc) {
+  pdl_wait();
   if ((*reinterpret_cast<volatile int*>(rflag) != 0) != EXACT) return;
   const int vbx = blockIdx.x, vby = blockIdx.y, vbz = blockIdx.z;
   extern __shared__ float4 smem4[];

@@ -305,6 +305,7 @@ __device__ __forceinline__ void b_f_jacobi(const Grid& g, const Coef& c, const f
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, (UNI ? JACOBI_MINB : MARCH_MINB_GEN)) f_jacobi(Grid g, Coef c, const float* __restrict__ r, float* __restrict__ r2, float* __restrict__ x,
                                                      int x_is_zero, int zchunk, Grid gc, float* __restrict__ rc, int do_restrict, int zoffc) {
+  pdl_wait();
   b_f_jacobi<UNI>(g, c, r, r2, x, x_is_zero, zchunk, gc, rc, do_restrict, zoffc, real_block());
 }
 
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(32 * FTY, (UNI ? JACOBI_MINB : MARCH_MINB_GEN)
 __global__ void __launch_bounds__(32 * FTY / 2, 6) f_jacobi_uni2(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                                 float* __restrict__ r2, float* __restrict__ x, int zchunk, const __grid_constant__ Grid gc,
                                                                 float* __restrict__ rc, int zoffc, int x_is_zero) {
+  pdl_wait();
   const int lane = threadIdx.x;
   const int x0 = 1 + 4 * (32 * blockIdx.x + lane);
   const int ya = 1 + FTY * blockIdx.y + 2 * threadIdx.y;  // rows ya, ya+1 (the interior height is even)
@@ -499,6 +501,7 @@ template <bool UNI, bool PROLONG>
 __global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_increment(Grid g, Coef c, const float* __restrict__ eps, ProlongSrc ps, float* __restrict__ r,
                                                         float* __restrict__ x, const float* __restrict__ wp, int x_is_zero, int zchunk, int with_l2,
                                                         RedBuf R, int slot) {
+  pdl_wait();
   b_f_increment<UNI, PROLONG>(g, c, eps, ps, r, x, wp, x_is_zero, zchunk, with_l2, R, slot, real_block());
 }
 
@@ -511,6 +514,7 @@ template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, DIVRES_MINB) f_div_residual(Grid g, Coef c, const float* __restrict__ u, const float* __restrict__ p, float* __restrict__ x,
                                                            float* __restrict__ r, float* __restrict__ zarr, const float* __restrict__ dtp, float wdt,
                                                            int zchunk, RedBuf R, int slot) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk, real_block(), c);
   const float dt = wdt * (*dtp);
   SField F;
@@ -572,6 +576,7 @@ __global__ void __launch_bounds__(32 * FTY, DIVRES_MINB) f_div_residual(Grid g, 
 __global__ void __launch_bounds__(32 * FTY, 4) f_divres_uni(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ u,
                                                            const float* __restrict__ p, float* __restrict__ x, float* __restrict__ r,
                                                            const float* __restrict__ dtp, float wdt, int zchunk, RedBuf R, int slot) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk);
   const float dt = wdt * (*dtp);
   double sum = 0.0, l2 = 0.0;
@@ -641,6 +646,7 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_divres_uni(const __grid_constan
 
 // residual! part 2 + L₂ (src/Poisson.jl:95-97,189): s = Σr/|inside|; |s|>2eps ⇒ r −= s; Σr² → out[slot_out]
 __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_resid_fix(Grid g, float* __restrict__ r, float count, int zchunk, RedBuf R, int slot_in, int slot_out) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk);
   const float s = (float)R.out[slot_in] / count;
   const bool fix = fabsf(s) > 2.f * 1.1920929e-7f;
@@ -668,6 +674,7 @@ __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_resid_fix(Grid g, floa
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_correct(Grid g, Coef c, const float* __restrict__ x, float* __restrict__ u, float* __restrict__ p,
                                                       const float* __restrict__ dtp, float wdt, int zchunk) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk, real_block(), c);
   const float dt = wdt * (*dtp);
   float4 zm = f4zero();
@@ -735,6 +742,7 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_consta
                                                             const float* __restrict__ ui, float* __restrict__ uo, float* __restrict__ p,
                                                             const float* __restrict__ dtp, float wdt, int zchunk, float nu, float* __restrict__ dt_out,
                                                             RedBuf R, int slot, int slot_ghost, int finalize, int* __restrict__ flags) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk);
   const float dt = wdt * (*dtp);
   const float L0 = c.Lc[0], L1 = c.Lc[1], L2 = c.Lc[2];
@@ -839,6 +847,7 @@ __global__ void __launch_bounds__(32 * FTY, 4) f_correct_cfl(const __grid_consta
 // fluid value Lc[d], or 0 on a wall face — exactly what a body-free region holds after BC!(L,0) (src/Flow.jl:145).
 __global__ void __launch_bounds__(256) k_semi_flags(const __grid_constant__ Grid g, const float* __restrict__ L, float L0, float L1, float L2, int zchunk,
                                                     unsigned char* __restrict__ flags) {
+  pdl_wait();
   const int xlo = 1 + 128 * blockIdx.x, ylo = 1 + FTY * blockIdx.y, zlo = 1 + zchunk * blockIdx.z;
   const int xhi = min(xlo + 128, g.N[0] - 1), yhi = min(ylo + FTY, g.N[1] - 1), zhi = min(zlo + zchunk, g.N[2] - 1);  // exclusive, core
   const float Lc[3] = {L0, L1, L2};
@@ -871,6 +880,7 @@ __global__ void __launch_bounds__(256) k_semi_flags(const __grid_constant__ Grid
 // Writes the number of offending values (as a max-reduced 0/1 flag) to out[slot].
 __global__ void __launch_bounds__(256) k_check_uniform(const float* __restrict__ mu0, const float* __restrict__ mu1, const float* __restrict__ V, Grid g,
                                                        RedBuf R, int slot) {
+  pdl_wait();
   // whole allocation incl. padding is zero-initialised: test only real cells
   const i64 ncell = (i64)g.N[0] * g.N[1] * g.N[2];
   double bad = 0.0;
@@ -939,6 +949,7 @@ template <int LAM, bool FUSE, bool PER3>
 __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restrict__ ua, const float* __restrict__ u0, const float* __restrict__ V,
                                                     float* __restrict__ out, float* __restrict__ sigma, const float* __restrict__ dtp, float nu, int zchunk,
                                                     int corrector, RedBuf R, int slot, const float* __restrict__ uext, int* __restrict__ flag, const Force fc) {
+  pdl_wait();
   extern __shared__ float smem_raw[];
   float* const T = smem_raw;  // [CRING][3][CH][CW]
   constexpr int PL = CH * CW;  // one component plane
@@ -1163,6 +1174,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
 // f on the lower ghost planes (any index 0): r = 0 there, so f = u⁰ + Δt·0 − V  (src/Flow.jl:178 over CartesianIndices(f))
 __global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f, const float* __restrict__ dtp,
                              const Force fc) {
+  pdl_wait();
   const int j = blockIdx.z;  // plane I_j = 0
   if (j == 2 && g.zopen[0]) return;  // slab-internal face: that plane of f arrives by halo exchange
   const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
@@ -1179,6 +1191,7 @@ __global__ void k_f_lowghost(Grid g, const float* __restrict__ u0, const float* 
 
 // max of σ over the ghost cells (where the reference's stale Φ lives) → out[slot]; planes selected by blockIdx.z
 __global__ void __launch_bounds__(256) k_sigma_ghostmax(Grid g, const float* __restrict__ sigma, RedBuf R, int slot) {
+  pdl_wait();
   const int plane = blockIdx.z;
   const int j = plane / 2, which = plane % 2;
   const int da = (j == 0) ? 1 : 0, db = (j == 2) ? 1 : 2;
@@ -1199,6 +1212,7 @@ __global__ void __launch_bounds__(256) k_sigma_ghostmax(Grid g, const float* __r
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, MARCH_MINB) f_cfl(Grid g, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
                                                   int zchunk, RedBuf R, int slot, int slot_ghost, int finalize) {
+  pdl_wait();
   const Frame f = make_frame(g, zchunk);
   double m = 0.0;
   for (int z = f.z0; z < f.z1; z++) {
@@ -1388,6 +1402,7 @@ __device__ __forceinline__ void b_f_gs_a(const Grid& g, const Coef& c, const flo
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_gs_a(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                    float* __restrict__ eps, int zchunk) {
+  pdl_wait();
   b_f_gs_a<UNI>(g, c, r, eps, zchunk, real_block());
 }
 
@@ -1414,6 +1429,7 @@ __device__ __forceinline__ void b_f_gs_half(const Grid& g, const Coef& c, const 
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, (UNI ? MARCH_MINB : MARCH_MINB_GEN)) f_gs_half(const __grid_constant__ Grid g, const __grid_constant__ Coef c, const float* __restrict__ r,
                                                       float* eps, int k0, int zchunk) {
+  pdl_wait();
   b_f_gs_half<UNI>(g, c, r, eps, k0, zchunk, real_block());
 }
 
@@ -1443,6 +1459,7 @@ struct SmallOp {
 
 template <bool UNI>
 __global__ void __launch_bounds__(32 * FTY, 4) k_small_levels(const SmallOp* __restrict__ ops, int nops, const float* wp) {
+  pdl_wait();
   cg::grid_group grid = cg::this_grid();
   __shared__ SmallOp op;
   const int tid = threadIdx.x + 32 * threadIdx.y;
@@ -1614,6 +1631,7 @@ __device__ __forceinline__ void tiny_gs(const TinyLvl& l, float w, int x_is_zero
 // One copy of each stage's code, looped over the levels (the fully unrolled version was 11 000 instructions = 180 KB that ran once,
 // straight through: the kernel spent its time fetching instructions — `no_instruction` was its top stall, 44 µs per launch).
 __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ TinyArgs a) {
+  pdl_wait();
   extern __shared__ float tiny_sm[];
   __shared__ TinyLvl lv[TINY_MAXLEV];
   const int tid = threadIdx.x;
@@ -1743,6 +1761,7 @@ __device__ __forceinline__ float* tinyg_fix(float* arena, const float* p) {
   return p ? arena + ((reinterpret_cast<uintptr_t>(p) >> 2) - 1) : nullptr;
 }
 __global__ void __launch_bounds__(1024, 1) k_tiny_gen(const SmallOp* __restrict__ ops, int nops, const float* wp, const __grid_constant__ TinyGenArgs a) {
+  pdl_wait();
   extern __shared__ float tinyg_arena[];
   float* const arena = tinyg_arena;
   SmallOp* const sops = reinterpret_cast<SmallOp*>(arena + ((a.arena_floats + 3) & ~3));

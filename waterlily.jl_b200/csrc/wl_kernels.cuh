@@ -95,6 +95,7 @@ template <int D, int LAM>
 __global__ void __launch_bounds__(512) k_conv_bdim1(Grid g, Box box, const float* __restrict__ ua, const float* __restrict__ u0,
                                                     const float* __restrict__ V, float* __restrict__ f, float* __restrict__ sigma,
                                                     const float* __restrict__ dtp, float nu, int mode, const Force fc) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -146,6 +147,7 @@ template <int D>
 __global__ void __launch_bounds__(512) k_bdim2(Grid g, Box box, float* __restrict__ u, const float* __restrict__ f, const float* __restrict__ V,
                                                const float* __restrict__ mu0, const float* __restrict__ mu1, int corrector,
                                                const unsigned char* __restrict__ nobody) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -183,6 +185,7 @@ __device__ __forceinline__ float sgs_dudx(const Grid& g, const float* __restrict
 // stored.  Ghost cells of νₜ stay 0: the reference's S is written on inside(σ) only and the flux loops below read it on upper ghosts.
 template <int D>
 __global__ void __launch_bounds__(512) k_sgs_nut(Grid g, Box box, const float* __restrict__ u, float* __restrict__ nut, float c2) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -204,6 +207,7 @@ template <int D>
 __global__ void __launch_bounds__(512) k_sgs_apply(Grid g, Box box, const float* __restrict__ ua, const float* __restrict__ nut,
                                                    const float* __restrict__ u0, const float* __restrict__ V, float* __restrict__ f,
                                                    float* __restrict__ sigma, const float* __restrict__ dtp, const Force fc) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(512) k_sgs_apply(Grid g, Box box, const float*
 template <int D>
 __global__ void __launch_bounds__(512) k_nobody_flags(Grid g, Box box, const float* __restrict__ V, const float* __restrict__ mu0,
                                                       const float* __restrict__ mu1, unsigned char* __restrict__ flags) {
+  pdl_wait();
   int I[3];
   int ok = 1;
   if (thread_cell<D>(box, I)) {
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(512) k_nobody_flags(Grid g, Box box, const flo
 // blockIdx.z selects the plane: (j, lower ghost | upper ghost | first interior).
 template <int D>
 __global__ void k_bc_vec(Grid g, float* a, const float* keep, float U0, float U1, float U2, int saveexit) {
+  pdl_wait();
   const int plane = blockIdx.z;
   const int j = plane / 3, which = plane % 3;
   if (which == 2 && g.per[j]) return;
@@ -336,6 +342,7 @@ __global__ void k_bc_vec(Grid g, float* a, const float* keep, float U0, float U1
 // perBC!(a,perdir) for a scalar (src/core.jl:239-243) in one launch, same plane scheme.
 template <int D>
 __global__ void k_perbc(Grid g, float* __restrict__ a) {
+  pdl_wait();
   const int plane = blockIdx.z;
   const int j = plane / 2, which = plane % 2;
   if (!g.per[j]) return;
@@ -369,6 +376,7 @@ __global__ void k_perbc(Grid g, float* __restrict__ a) {
 template <int D>
 __global__ void __launch_bounds__(256) k_exitbc(Grid g, float* __restrict__ u, const float* __restrict__ u0, const float* __restrict__ dtp,
                                                 float dt_scale, RedBuf R, int slot, int stage, float len) {
+  pdl_wait();
   int J[3] = {0, 0, 0};
   J[1] = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   J[2] = (D == 3) ? 1 + blockIdx.y * blockDim.y + threadIdx.y : 0;
@@ -425,6 +433,7 @@ __device__ __forceinline__ float mult_at(const Grid& g, const float* __restrict_
 // set_diag!(D,iD,L) (src/Poisson.jl:43-55)
 template <int D>
 __global__ void k_set_diag(Grid g, Box box, const float* __restrict__ L, float* __restrict__ Dg, float* __restrict__ iD) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -438,6 +447,7 @@ __global__ void k_set_diag(Grid g, Box box, const float* __restrict__ L, float* 
 // restrictL!(a,b,c) interior part (src/MultiLevelPoisson.jl:42-46, :20-26, upL :9-11); BC!(a,0) follows via k_bc_vec.
 template <int D>
 __global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2, int zoffc) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const int c[3] = {c0, c1, c2};
@@ -470,6 +480,7 @@ __global__ void k_restrictL(Grid gc, Grid gf, Box box, float* __restrict__ a, co
 template <int D>
 __global__ void __launch_bounds__(512) k_div_residual(Lvl l, Box box, const float* __restrict__ u, const float* __restrict__ p,
                                                       const float* __restrict__ dtp, float w, int with_div, RedBuf R, int slot) {
+  pdl_wait();
   const Grid& g = l.g;
   int I[3];
   const bool ok = thread_cell<D>(box, I);
@@ -505,6 +516,7 @@ __global__ void __launch_bounds__(512) k_div_residual(Lvl l, Box box, const floa
 //   s = Σr/|inside|;  |s| > 2eps ? r -= s ;  Σ r² → out[slot_out]
 template <int D>
 __global__ void __launch_bounds__(512) k_resid_fix(Lvl l, Box box, float count, RedBuf R, int slot_in, int slot_out) {
+  pdl_wait();
   const Grid& g = l.g;
   int I[3];
   const bool ok = thread_cell<D>(box, I);
@@ -543,6 +555,7 @@ __device__ __forceinline__ void b_k_jacobi(Lvl l, Box box, int x_is_zero, const 
 }
 template <int D>
 __global__ void __launch_bounds__(512) k_jacobi(Lvl l, Box box, int x_is_zero) {
+  pdl_wait();
   b_k_jacobi<D>(l, box, x_is_zero, real_block());
 }
 
@@ -566,6 +579,7 @@ __device__ __forceinline__ void b_k_restrict(Grid gc, Grid gf, Box box, float* a
 }
 template <int D>
 __global__ void k_restrict(Grid gc, Grid gf, Box box, float* __restrict__ a, const float* __restrict__ b, int c0, int c1, int c2) {
+  pdl_wait();
   b_k_restrict<D>(gc, gf, box, a, b, c0, c1, c2, real_block());
 }
 
@@ -580,6 +594,7 @@ __device__ __forceinline__ void b_k_gs_init(Lvl l, Box box, const int3 vb) {
 }
 template <int D>
 __global__ void k_gs_init(Lvl l, Box box) {
+  pdl_wait();
   b_k_gs_init<D>(l, box, real_block());
 }
 
@@ -630,6 +645,7 @@ __device__ __forceinline__ void b_k_gs_sweep(Lvl l, Box box, int k0, const int3 
 }
 template <int D>
 __global__ void __launch_bounds__(512) k_gs_sweep(Lvl l, Box box, int k0) {
+  pdl_wait();
   b_k_gs_sweep<D>(l, box, k0, real_block());
 }
 
@@ -657,6 +673,7 @@ __device__ __forceinline__ void b_k_increment(Lvl l, Box box, const float* wp, i
 }
 template <int D>
 __global__ void __launch_bounds__(512) k_increment(Lvl l, Box box, const float* __restrict__ wp, int x_is_zero, int with_l2, RedBuf R, int slot) {
+  pdl_wait();
   b_k_increment<D>(l, box, wp, x_is_zero, with_l2, R, slot, real_block());
 }
 
@@ -698,6 +715,7 @@ __device__ __forceinline__ void b_k_prolong_inc(Lvl l, Grid gc, const float* xc,
 template <int D>
 __global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float* __restrict__ xc, Box box, const float* __restrict__ wp, int c0, int c1,
                                                      int c2) {
+  pdl_wait();
   b_k_prolong_inc<D>(l, gc, xc, box, wp, c0, c1, c2, real_block());
 }
 
@@ -705,6 +723,7 @@ __global__ void __launch_bounds__(512) k_prolong_inc(Lvl l, Grid gc, const float
 //   u[I,i] −= L[I,i]·(x[I] − x[I−δ_i]);  p = x/dt   (x keeps the scaled iterate; p is the observable pressure)
 template <int D>
 __global__ void __launch_bounds__(512) k_correct(Lvl l, Box box, float* __restrict__ u, float* __restrict__ p, const float* __restrict__ dtp, float w) {
+  pdl_wait();
   const Grid& g = l.g;
   int I[3];
   if (!thread_cell<D>(box, I)) return;
@@ -723,6 +742,7 @@ __global__ void __launch_bounds__(512) k_correct(Lvl l, Box box, float* __restri
 template <int D>
 __global__ void __launch_bounds__(512) k_cfl(Grid g, Box box, const float* __restrict__ u, float* __restrict__ sigma, float nu, float* __restrict__ dt_out,
                                              RedBuf R, int slot) {
+  pdl_wait();
   int I[3];
   const bool ok = thread_cell<D>(box, I);
   double v[1] = {0.0}, fin[1];  // lower ghosts hold 0, so the max is at least 0
@@ -752,6 +772,7 @@ __global__ void __launch_bounds__(512) k_cfl(Grid g, Box box, const float* __res
 // mult!(p,x) (src/Poisson.jl:63-69): z = A x on the interior (ghosts zeroed by the caller).
 template <int D>
 __global__ void k_mult(Lvl l, Box box, const float* __restrict__ x, float* __restrict__ z) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(l.g, I);
@@ -775,6 +796,7 @@ struct PcgCtl {
 };
 template <int D>
 __global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, PcgCtl* __restrict__ ctl, RedBuf R, int slot) {
+  pdl_wait();
   const Grid& g = l.g;
   int I[3];
   if (stage > 0 && ctl->active == 0) return;  // (written by an earlier launch only: the last block of a stage writes it after every block has started)
@@ -832,6 +854,7 @@ __global__ void __launch_bounds__(512) k_pcg(Lvl l, Box box, int stage, PcgCtl* 
 // L₂(p) = r⋅r and L∞(p) = maximum(abs,r) (src/Poisson.jl:189-190) as a standalone reduction.
 template <int D>
 __global__ void __launch_bounds__(512) k_norms(Lvl l, Box box, RedBuf R, int slot, int want_max) {
+  pdl_wait();
   int I[3];
   const bool ok = thread_cell<D>(box, I);
   double v[1] = {0.0}, fin[1];
@@ -847,14 +870,19 @@ __global__ void __launch_bounds__(512) k_norms(Lvl l, Box box, RedBuf R, int slo
 
 // generic helpers
 __global__ void k_fill(float* __restrict__ a, size_t n, float v) {
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) a[i] = v;
 }
-__global__ void k_set_scalar(float* p, float v) { *p = v; }
+__global__ void k_set_scalar(float* p, float v) {
+  pdl_wait();
+  *p = v;
+}
 
 // Exhaustive self-test of div6: counts the float bit patterns (all 2^32) where div6(x) and x/6.f differ (NaNs compare equal).
 __global__ void k_selftest_div6(unsigned long long* nbad) {
+  pdl_wait();
   unsigned long long bad = 0;
   for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += (unsigned long long)gridDim.x * blockDim.x) {
     const float x = __uint_as_float((unsigned)b);
@@ -867,6 +895,7 @@ __global__ void k_selftest_div6(unsigned long long* nbad) {
 
 // z slabs: Δt from the all-reduced maxima (the single-GPU path does this in f_cfl's last block)
 __global__ void k_cfl_final(RedBuf R, int slot_a, int slot_b, float nu, float* dt_out) {
+  pdl_wait();
   const float mm = (float)fmax(R.out[slot_a], R.out[slot_b]);
   *dt_out = fminf(10.f, 1.f / (mm + 5.f * nu));
 }
@@ -898,6 +927,7 @@ __device__ __forceinline__ void st_flag_sys(int* p, int v) { asm volatile("st.vo
 // "ready to receive" round trip is skipped and the kernel is copy → arrived → wait for the neighbours' arrived.
 __global__ void __launch_bounds__(256) k_halo_push(HaloSegs segs, int cnt4, int seq, int* my, int* peer_lo, int* peer_hi, long long timeout,
                                                    const int* myflags, int* flags_lo, int* flags_hi, int no_ready) {
+  pdl_wait();
   // A timeout is FATAL for the whole ring: the rank that gave up raises the error word of its own mailbox and of both neighbours'
   // (my[5]), never copies and never signals `arrived`, and every later exchange on a rank whose error word is set returns at once;
   // the host reads the word after every step (check_flags) and fails the call.  NCCL collectives block without a bound anyway,
@@ -970,6 +1000,7 @@ struct ArPeers {
 };
 __global__ void __launch_bounds__(32) k_allreduce(ArPeers peers, int P, int rank, long long seq, int op, int count, double* out, double* hout,
                                                   unsigned int* hseq, unsigned int tag, int* err, long long timeout) {
+  pdl_wait();
   const int t = threadIdx.x;
   const int b = (int)(seq & 1);
   const double v0 = out[0], v1 = count > 1 ? out[1] : 0.0;
@@ -1017,6 +1048,7 @@ struct BcastDst {
 };
 __global__ void __launch_bounds__(256) k_bcast_planes(const float4* __restrict__ src, BcastDst dst, long long n4, ArPeers peers, int P, int rank, long long seq,
                                                       int* counter, int* err, long long timeout) {
+  pdl_wait();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
     const float4 v = src[e];
 #pragma unroll
@@ -1053,6 +1085,7 @@ __global__ void __launch_bounds__(256) k_bcast_planes(const float4* __restrict__
 // Range check of a velocity field the library did not write itself (uploads, wl_apply_bc, kernels without the built-in check):
 // raises flags[2] / flags[0] as described at range_note (wl_common.cuh).  n4 = number of float4 to scan.
 __global__ void __launch_bounds__(256) k_range_check(const float4* __restrict__ a, long long n4, int* __restrict__ flags) {
+  pdl_wait();
   RangeAcc ra;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) ra.add4(a[i]);
   ra.publish(flags);
@@ -1176,6 +1209,7 @@ __device__ __forceinline__ float mu1_f(float d, float e) { return e * kern1_f(fm
 template <int D>
 __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ Grid g, Box box, const __grid_constant__ BodySet B, float eps, float t,
                                                  float* __restrict__ sigma, float* __restrict__ V, float* __restrict__ mu0, float* __restrict__ mu1) {
+  pdl_wait();
   int I[3];
   if (!thread_cell<D>(box, I)) return;
   const i64 o = cell_off(g, I);
@@ -1225,6 +1259,7 @@ __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ Grid g,
 template <int D>
 __global__ void __launch_bounds__(256) k_forces(const __grid_constant__ Grid g, Box box, const __grid_constant__ BodySet B, float t, float nu, float x00,
                                                 float x01, float x02, const float* __restrict__ u, const float* __restrict__ p, RedBuf R, int slot0) {
+  pdl_wait();
   int I[3];
   const bool ok = thread_cell<D>(box, I);
   double v[12], fin[12];
@@ -1285,6 +1320,7 @@ __global__ void __launch_bounds__(256) k_forces(const __grid_constant__ Grid g, 
 // over every cell of the arrays (ghosts included; the pitched layout's padding rides along).  n = floats of one scalar field.
 __global__ void __launch_bounds__(256) k_meanflow(long long n, int D, int uu, float eps, const float* __restrict__ p, const float* __restrict__ u,
                                                   float* __restrict__ P, float* __restrict__ U, float* __restrict__ UU) {
+  pdl_wait();
   const float om = 1.f - eps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     P[i] = eps * p[i] + om * P[i];

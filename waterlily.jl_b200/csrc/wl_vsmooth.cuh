@@ -180,6 +180,7 @@ __device__ __forceinline__ float4 vs_mult(const float4& c, const float4& lf, con
 
 template <bool WITH_L2, bool SLAB, int LM>
 __global__ void __launch_bounds__(VS_NT, VS_BPS) f_vsmooth(const __grid_constant__ VsArgs a, RedBuf R, int slot) {
+  pdl_wait();
   extern __shared__ float4 vs_smem4[];
   // ϵ ring [VS_DE][2][VS_TH][VS_NGX] float4, then the r¹ ring [VS_DR][2][VS_TH][VS_NGX] float4
   float* const ER = reinterpret_cast<float*>(vs_smem4) + VS_PAD;

@@ -138,7 +138,7 @@ def load_library(fmad=False):
 
 
 FLAGS = {"general_coeff": 1, "unfused_gs": 2, "no_persistent": 4, "nccl_halo": 8, "no_vsmooth": 16, "no_conv4": 32,
-         "no_fused_uni": 64, "no_semi": 128, "no_tiny": 256, "no_fast_read": 512, "no_prefetch": 1024, "nccl_allreduce": 2048}  # WL_FLAG_* (include/wl_b200.h)
+         "no_fused_uni": 64, "no_semi": 128, "no_tiny": 256, "no_fast_read": 512, "no_prefetch": 1024, "nccl_allreduce": 2048, "no_pdl": 4096}  # WL_FLAG_* (include/wl_b200.h)
 
 
 def check(L, rc):
