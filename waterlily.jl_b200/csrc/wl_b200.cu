@@ -502,7 +502,7 @@ static int p2p_push(wl_handle* h, const Grid& g, const PlaneMove* mv, int n, boo
     return 0;
   }
   prof_begin(h, "halo_exchange_p2p");
-  k_halo_push<<<nb, 256, 0, h->st>>>(segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi, no_ready);
+  pdl_launch(h, k_halo_push, dim3(nb), dim3(256), 0, segs, cnt4, seq, mb, plo, phi, 60000000000LL, myf, flo, fhi, no_ready);
   prof_end(h);
   h->launches++;
   return 0;
@@ -643,7 +643,7 @@ static int allreduce_slot(wl_handle* h, int slot, int op, int count = 1) {  // `
     h->slot_tag[slot] = tag;
     h->slot_ar[slot] = true;
     prof_begin(h, "allreduce_p2p");
-    k_allreduce<<<1, 32, 0, h->st>>>(h->ar_peers, h->dist.P, h->dist.rank, ++h->ar_seq, op == WL_NCCL_SUM ? RED_SUM : RED_MAX, count, h->red.out + slot,
+    pdl_launch(h, k_allreduce, dim3(1), dim3(32), 0, h->ar_peers, h->dist.P, h->dist.rank, ++h->ar_seq, op == WL_NCCL_SUM ? RED_SUM : RED_MAX, count, h->red.out + slot,
                                      h->red.hout + slot, h->red.hseq + slot, tag, h->mbox + 40, 60000000000LL);
     prof_end(h);
     h->launches++;
@@ -718,7 +718,7 @@ static int allgather_planes(wl_handle* h, const Level& lc, float* a, int planes_
     const long long n4 = (long long)(cnt / 4);
     const int nb = (int)std::max<long long>(1, std::min<long long>(96, (n4 + 1023) / 1024));
     prof_begin(h, "allgather_p2p");
-    k_bcast_planes<<<nb, 256, 0, h->st>>>(reinterpret_cast<const float4*>(mine), dst, n4, bar, d.P, d.rank, ++h->bc_seq, h->mbox + 44, h->mbox + 40, 60000000000LL);
+    pdl_launch(h, k_bcast_planes, dim3(nb), dim3(256), 0, reinterpret_cast<const float4*>(mine), dst, n4, bar, d.P, d.rank, ++h->bc_seq, h->mbox + 44, h->mbox + 40, 60000000000LL);
     prof_end(h);
     h->launches++;
     return 0;
