@@ -2277,6 +2277,8 @@ static int create_impl(const wl_config* cfg, int rank, int nranks, const void* n
       h->d_flags = (int*)q;
     }
     if ((rc = build_levels(h))) break;
+    // fields of this size move through the pinned staging ring: allocate it now (≈ 90 ms once per process), not inside the first download
+    if ((size_t)h->g.N[0] * h->g.N[1] * h->g.N[2] * sizeof(float) >= ((size_t)64 << 20)) pin_ring_init();
     if (h->D == 3 && h->cfg.pois_kind == WL_POIS_MULTILEVEL && h->cfg.smoother == WL_SMOOTH_GSRB && !(cfg->flags & WL_FLAG_NO_PERSISTENT)) {
       // levels of at most ~0.6 M cells (and, with z slabs, only replicated ones) go to the persistent coarse-level kernel
       for (size_t i = 1; i < h->levels.size(); i++) {
