@@ -821,10 +821,11 @@ def test_large_host_transfers_round_trip():
 def test_tiny_level_kernels_equal_the_cooperative_kernel(case):
     """The one-block shared-memory kernels for the innermost multigrid levels (k_tiny_gen with bodies / walls / semi-coarsened
     levels, k_tiny_uni in uniform mode) against the same levels run inside k_small_levels (WL_FLAG_NO_TINY), and the host reading
-    the residual norms from the mapped mirror against copy + synchronise (WL_FLAG_NO_FAST_READ): bit for bit over 8 steps."""
+    the residual norms from the mapped mirror against copy + synchronise (WL_FLAG_NO_FAST_READ), programmatic dependent launch
+    against ordinary stream order (WL_FLAG_NO_PDL): bit for bit over 8 steps."""
     import wl_b200 as wl
     outs = []
-    for flags in (0, wl.lib.FLAGS["no_tiny"] | wl.lib.FLAGS["no_fast_read"]):
+    for flags in (0, wl.lib.FLAGS["no_tiny"] | wl.lib.FLAGS["no_fast_read"] | wl.lib.FLAGS["no_pdl"]):
         if case == "sphere_walls":
             s = wl.Simulation((128, 64, 64), (1.0, 0.0, 0.0), 16.0, ν=0.01, body=wl.Sphere((31.0, 31.0, 31.0), 8.0), exitBC=True, flags=flags)
         elif case == "torus_periodic_y":
