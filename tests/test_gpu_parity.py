@@ -841,3 +841,31 @@ def test_tiny_level_kernels_equal_the_cooperative_kernel(case):
     a, b = outs
     assert a[2] == b[2] and np.array_equal(a[3], b[3])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_accelerating_circle_added_mass_on_gpu():
+    """test/test_flow.jl:161-173 through the C ABI: uBC(t) = (t, 0) as TimeBC, a circle of radius 32 in a 1024² box measured on the
+    device; pressure_force/(πL²) ≈ (−1, 0) ± 0.04 after one step, peak velocity ≈ 2U, n ≤ 2 — and the oracle's bits."""
+    import math
+    import oracle
+    import wl_b200 as wl
+    radius, H = 32, 16
+    n = radius * 2 * H
+    c = (float(H * radius), float(H * radius))
+    s = wl.Simulation((n, n), wl.TimeBC((0.0, 0.0), U1=(1.0, 0.0)), float(radius), U=1.0, body=wl.Sphere(c, float(radius)))
+    o = oracle.OracleSim((n, n), (0.0, 0.0))
+    o.measure_sphere(c, float(radius))
+    o.init_pois()
+    o.set_forcing(U1=(1.0, 0.0))
+    wl.sim_step(s)
+    o.mom_step()
+    pf = np.asarray(wl.pressure_force(s), np.float64) / (math.pi * radius ** 2)
+    assert abs(pf[0] + 1.0) < 0.04 and abs(pf[1]) < 0.04, pf
+    u = s.flow.u
+    assert float(u.max()) / float(u[0][1, 1]) > 1.91
+    assert rel_l2(u, o.field("u")) <= 1e-5 and rel_l2(s.flow.p, o.field("p")) <= 1e-5
+    for _ in range(3):
+        wl.sim_step(s)
+        o.mom_step()
+    assert all(int(k) <= 2 for k in s.pois.n), list(s.pois.n)
+    assert list(np.asarray(s.pois.n, int)) == list(np.asarray(o.iters, int))

@@ -278,3 +278,26 @@ def test_sgs_restatement_equals_array_transliteration(dims):
     before = f.copy()
     s.sgs()
     assert np.array_equal(f, before)
+
+
+# ---------------------------------------------------------------- test/test_flow.jl:161-173 ("Circle in accelerating flow")
+def test_accelerating_circle_added_mass():
+    """A circle of radius 32 in a 1024² box whose boundary velocity is uBC(t) = (t, 0): after one step the pressure force is the added
+    mass of a cylinder, pressure_force/(πL²) ≈ (−1, 0) ± 0.04, the potential flow peaks at ≈ 2U over the body and the solver needs
+    ≤ 2 V-cycles — through the enumerated boundary velocity (U1), accelerate!'s dU/dt term, BDIM, the projection and the force
+    reduction (src/Flow.jl:64-73,156-232; src/Metrics.jl:116-127)."""
+    radius, H = 32, 16
+    n = radius * 2 * H
+    s = OracleSim((n, n), (0.0, 0.0))
+    s.measure_sphere((H * radius, H * radius), float(radius))
+    s.init_pois()
+    s.set_forcing(U1=(1.0, 0.0))
+    s.mom_step()
+    prim = [dict(kind=0, op=0, center=(H * radius, H * radius), R=float(radius), r=0.0, vel=(0.0, 0.0))]
+    pf = s.body_forces(prim)[0] / (math.pi * radius ** 2)
+    assert abs(pf[0] + 1.0) < 0.04 and abs(pf[1]) < 0.04, pf
+    u = s.field("u")
+    assert float(u.max()) / float(u[0][1, 1]) > 1.91
+    for _ in range(3):
+        s.mom_step()
+    assert all(int(k) <= 2 for k in s.iters), list(s.iters)
