@@ -869,3 +869,26 @@ def test_accelerating_circle_added_mass_on_gpu():
         o.mom_step()
     assert all(int(k) <= 2 for k in s.pois.n), list(s.pois.n)
     assert list(np.asarray(s.pois.n, int)) == list(np.asarray(o.iters, int))
+
+
+@pytest.mark.parametrize("exitBC", [True, False])
+def test_remeasure_body_moving_with_the_stream_on_gpu(exitBC):
+    """test/test_simulation.jl:20-25 through the C ABI: sim_step!(sim) with remeasure=true and a circle that translates with the free
+    stream leaves u[:, radius, 1] ≈ 1; the fields equal the oracle's."""
+    import math
+    import oracle
+    import wl_b200 as wl
+    radius = 8
+    body = wl.Sphere((2.0 * radius, 2.0 * radius), float(radius), velocity=(1.0, 0.0))
+    s = wl.Simulation((4 * radius, 4 * radius), (1.0, 0.0), float(radius), ν=radius / 250, body=body, exitBC=exitBC)
+    o = oracle.OracleSim((4 * radius, 4 * radius), (1.0, 0.0), nu=radius / 250, exitBC=exitBC)
+    o.measure_prims(body.prims(), 1.0, 0.0)
+    o.init_pois()
+    o.measure_prims(body.prims(), 1.0, o.time_next())
+    o.update()
+    o.mom_step()
+    wl.sim_step(s, remeasure=True)
+    row = s.flow.u[0][radius - 1, :]
+    assert np.all(np.abs(row - 1.0) <= math.sqrt(np.finfo(np.float32).eps) * np.maximum(np.abs(row), 1.0)), row
+    assert rel_l2(s.flow.u, o.field("u")) <= 1e-5 and rel_l2(s.flow.p, o.field("p")) <= 1e-5
+    assert list(np.asarray(s.pois.n, int)) == list(np.asarray(o.iters, int))

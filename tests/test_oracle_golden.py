@@ -301,3 +301,20 @@ def test_accelerating_circle_added_mass():
     for _ in range(3):
         s.mom_step()
     assert all(int(k) <= 2 for k in s.iters), list(s.iters)
+
+
+# ---------------------------------------------------------------- test/test_simulation.jl:20-25
+@pytest.mark.parametrize("exitBC", [True, False])
+def test_remeasure_body_moving_with_the_stream(exitBC):
+    """"remeasure works perfectly when V = U = 1": a circle translating with the free stream (AutoBody(circle, x − [t,0]), measured at
+    t = ΣΔt before the step) leaves the flow undisturbed: u[:, radius, 1] ≈ 1 (isapprox of Float32: rtol √eps) after sim_step!(sim)."""
+    radius = 8
+    s = OracleSim((4 * radius, 4 * radius), (1.0, 0.0), nu=radius / 250, exitBC=exitBC)
+    prims = [dict(kind=0, op=0, center=(2.0 * radius, 2.0 * radius), R=float(radius), r=0.0, vel=(1.0, 0.0))]
+    s.measure_prims(prims, 1.0, 0.0)
+    s.init_pois()
+    s.measure_prims(prims, 1.0, s.time_next())  # sim_step!(sim): remeasure=true by default (src/WaterLily.jl:136-139,146-149)
+    s.update()
+    s.mom_step()
+    row = s.field("u")[0][radius - 1, :]
+    assert np.all(np.abs(row - 1.0) <= math.sqrt(np.finfo(np.float32).eps) * np.maximum(np.abs(row), 1.0)), row
