@@ -1499,7 +1499,6 @@ static int run_small_levels(wl_handle* h, const float* wp) {
   auto coop = [&](int first, int n) -> int {
     if (n <= 0) return 0;
     const SmallOp* dops = h->d_ops + first;
-    void* args[] = {(void*)&dops, (void*)&n, (void*)&wp};
     prof_begin(h, "k_small_levels");
     // cooperative + (if the driver takes the combination) programmatic dependent launch
     auto go = [&](int nattr) -> cudaError_t {
@@ -1930,7 +1929,6 @@ static int mom_step(wl_handle* h) {
     h->fc.on = h->forcing ? 1 : 0;
     for (int i = 0; i < 3; i++) h->fc.a[i] = (h->fg0[i] + h->fg1[i] * t) + (h->fU1[i] + h->fU2[i] * t);
   };
-  const Grid& g = h->g;
   dim3 b = blk(h->D);
   Level& l = h->levels[0];
   Box in = l.inside(), all = l.all();

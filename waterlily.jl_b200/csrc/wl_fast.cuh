@@ -1010,7 +1010,7 @@ __global__ void __launch_bounds__(32 * CTY) fm_conv(Grid g, const float* __restr
     }
   };
   // po[k]: offset of this thread's column on plane z-2+k (k = 0..5) inside the ring; refreshed every step
-  int po[6];
+  int po[6] = {0, 0, 0, 0, 0, 0};
   const int colbase = (ty + 2) * CW + lane + 2;
   // U(c, dx, dy, dz): component c at (x+dx, y+dy) on plane z+dz, dz ∈ [-2, 3]
   auto U = [&](int c, int dx, int dy, int dz) -> float { return T[po[dz + 2] + c * PL + dy * CW + dx]; };
@@ -1699,7 +1699,7 @@ __global__ void __launch_bounds__(1024, 1) k_tiny_uni(const __grid_constant__ Ti
     const bool coarsest = q == a.nlev - 1;
     if (!coarsest) {
       const TinyLvl cl = lv[q + 1];
-      const int s2 = l.n0 * l.n1, c1 = cl.n0, c2 = cl.n0 * cl.n1;
+      const int c1 = cl.n0, c2 = cl.n0 * cl.n1;
       l.each_cell(tid, [&](int c, int i, int j, int k) {
         // ϵ[J] = x_c[down(J)] on the periodic image of J
         auto ec = [&](int ii, int jj, int kk) -> float {
